@@ -1,0 +1,155 @@
+/* mupopp_b200 -- C-ABI of the B200-native MuPoPP per-timestep hot path.
+ *
+ * The reference (sashgeophysics/MuPoPP) has NO native/FFI interface: its hot path is the
+ * un-vendored DOLFIN 2017.1 / FFC / PETSc stack reached through Python calls.  Each entry
+ * point below therefore cites the reference CALL SITE whose work it replaces
+ * (paths relative to /root/reference/src).  The Python host side (mupopp_b200/) binds these
+ * with ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *  - every pointer named d_* is a DEVICE pointer owned by the caller (torch tensors); the
+ *    library never frees caller memory.  fp64 values, int32 indices.
+ *  - every call returns 0 on success, non-zero on failure; mp_last_error() gives the text.
+ *  - one CUDA stream per mp_ctx; a handle is not thread-safe, distinct handles are.
+ *  - no CPU fallback: a call without a usable CUDA device fails with an error.
+ */
+#ifndef MUPOPP_B200_H
+#define MUPOPP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mp_ctx mp_ctx;
+typedef struct mp_plan mp_plan;
+typedef struct mp_halo mp_halo;
+
+/* ------------------------------------------------------------------ context */
+int mp_version(void);
+const char *mp_last_error(void);
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private one */
+int mp_ctx_create(int device, void *stream, mp_ctx **out);
+int mp_ctx_destroy(mp_ctx *ctx);
+int mp_ctx_sync(mp_ctx *ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t mp_ctx_launch_count(const mp_ctx *ctx);
+
+/* ------------------------------------------------------------------ mesh view (device pointers) */
+typedef struct {
+    int32_t dim;            /* 2 (triangles) or 3 (tetrahedra) */
+    int64_t ncell;
+    int64_t nvert;
+    const int32_t *d_cells; /* [ncell][dim+1] vertex ids, ascending per cell (UFC ordering) */
+    const double *d_coords; /* [nvert][dim] */
+} mp_mesh;
+
+/* ------------------------------------------------------------------ scatter plan
+ * Replaces DOLFIN's dofmap + SparsityPatternBuilder + MatSetValuesLocal inside
+ * assemble_system / solve(a==L,..) (call sites: modules/mupopp.py:295-297,415-417,
+ * run/CCS2D/CCS_3comp.py:261, run/darcy_advection_diffusion/darcy_advection_diffusion.py:81,114).
+ * Built once per (row dofmap, column dofmap); holds the CSR pattern (columns ascending), the
+ * dof->(cell,local) incidence lists and the per-entry slot map used by the deterministic
+ * row-gather scatter.  d_col_dofs == NULL, lc == 0 gives a vector-only plan. */
+int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr, const int32_t *d_col_dofs, int32_t lc,
+                   int64_t ncell, int64_t nrow, int64_t ncol, mp_plan **out);
+int64_t mp_plan_nnz(const mp_plan *plan);
+int mp_plan_export_csr(mp_ctx *ctx, const mp_plan *plan, int32_t *d_rowptr, int32_t *d_colidx);
+int mp_plan_destroy(mp_plan *plan);
+
+/* vals[slot] = sum over incident cells (ascending cell id) of elem_mat[cell][i][j]   (no atomics) */
+int mp_scatter_matrix(mp_ctx *ctx, const mp_plan *plan, const double *d_elem_mat, double *d_vals);
+/* out[r] = beta*out[r] + sum over incident (cell,i) of elem_vec[cell][i] */
+int mp_scatter_vector(mp_ctx *ctx, const mp_plan *plan, const double *d_elem_vec, double beta, double *d_out);
+
+/* DOLFIN assemble_system semantics (symmetric elimination): rhs -= A[:,D] g; zero rows/cols D;
+ * A[D,D] = 1; rhs[D] = g.  d_isbc[ncol] flags, d_g[ncol] values (ignored where isbc == 0). */
+int mp_apply_dirichlet_sym(mp_ctx *ctx, int64_t nrow, const int32_t *d_rowptr, const int32_t *d_colidx, double *d_vals,
+                           double *d_rhs, const uint8_t *d_isbc, const double *d_g);
+
+/* ------------------------------------------------------------------ P1 element kernels (mode F)
+ * Replace FFC tabulate_tensor for the forms of modules/mupopp.py (line ranges per function). */
+typedef struct {
+    double Pe, Da, phi, beta, dt;
+    double sigma, rho0, gamma;   /* buoyancy sigma*K*(rho0+gamma*c0) v.zhat: mupopp.py:804-807 (sigma=-1), :1201-1204 (+1) */
+    double frac[3];              /* R1,R2,R3 prefactors: mupopp.py:818-821, :925-931, :1222-1229 */
+    double zhat[3];
+    double Kconst;               /* used when d_K == NULL */
+    int32_t reaction;            /* 0: Da*c0*c1 (CCS)   1: Da*c0*c1^2 (DarcyAdvection) */
+    int32_t ncomp;               /* 2 or 3 concentration fields */
+    int32_t supg;                /* 1 Sendur, 2 Codina, 3 Brooks-Hughes: mupopp.py:835-846 */
+    int32_t pad;
+} mp_transport_params;
+
+/* elem_mat[c][i][j] = scale * int phi_i phi_j   (P1 mass; c1/c2 rows mupopp.py:826,936-937,1234-1235) */
+int mp_elem_p1_mass(mp_ctx *ctx, const mp_mesh *mesh, double scale, double *d_elem_mat);
+/* elem_mat = scale * K_cell * int grad phi_i . grad phi_j   (pressure operator div(k grad p)); d_K nodal P1 or NULL */
+int mp_elem_p1_stiffness(mp_ctx *ctx, const mp_mesh *mesh, const double *d_K, double Kconst, double scale, double *d_elem_mat);
+/* c1/c2 rows: elem_b1 = int w (c1n - dt R2/(1-phi)), elem_b2 = int w (c2n + dt R3/(1-phi)) (NULL when ncomp==2) */
+int mp_elem_p1_reaction_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_c0n,
+                            const double *d_c1n, const double *d_c2n, double *d_elem_b1, double *d_elem_b2);
+/* c0 row (Crank-Nicolson + SUPG, mupopp.py:823-848 / :934-958 / :1231-1258) with the lagged DG0 velocity d_ucell[c][dim]:
+ * elem_mat (may be NULL to skip) and elem_vec; the new c1/c2 enter the rhs through the SUPG residual. */
+int mp_elem_p1_transport(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_ucell,
+                         const double *d_c0n, const double *d_c1n, const double *d_c2n, const double *d_c1new,
+                         const double *d_c2new, const double *d_fsrc, double *d_elem_mat, double *d_elem_vec);
+/* single-component form DarcyAdvection.advection_diffusion (mupopp.py:627-664), DG0 velocity variant */
+int mp_elem_p1_adr_single(mp_ctx *ctx, const mp_mesh *mesh, double Pe, double Da, double dt, const double *d_ucell,
+                          const double *d_cn, double *d_elem_mat, double *d_elem_vec);
+/* pressure rhs: -sigma * int (K/phi) rho(c0bar) zhat.grad q */
+int mp_elem_p1_pressure_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_K,
+                            const double *d_c0, double *d_elem_vec);
+/* fused pointwise velocity recovery u = -(K/phi)(grad p + sigma rho zhat) per cell (north_star item 3) */
+int mp_recover_velocity(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_K,
+                        const double *d_p, const double *d_c0, double *d_ucell);
+
+/* ------------------------------------------------------------------ linear algebra (PETSc Mat/Vec/KSP replacement)
+ * Call sites replaced: KrylovSolver(...).solve modules/mupopp.py:289-303,410-425; the LU inside solve(a==L,..). */
+typedef struct {
+    int64_t nrow;          /* owned rows */
+    int64_t ncol;          /* local columns (owned + ghost) */
+    int64_t nnz;
+    const int32_t *d_rowptr;
+    const int32_t *d_colidx;
+    const double *d_vals;
+} mp_csr;
+
+int mp_spmv(mp_ctx *ctx, const mp_csr *A, const double *d_x, double *d_y);
+int mp_dot(mp_ctx *ctx, int64_t n, const double *d_x, const double *d_y, double *result);      /* host result; allreduced if a communicator is attached */
+int mp_axpby(mp_ctx *ctx, int64_t n, double a, const double *d_x, double b, double *d_y);      /* y = a x + b y */
+int mp_jacobi_setup(mp_ctx *ctx, const mp_csr *A, double *d_dinv);                             /* dinv = 1/diag(A) */
+
+typedef struct {
+    double rtol, atol;     /* stop when ||r|| <= max(rtol*||b||, atol)  (true recurrence residual, 2-norm) */
+    int32_t maxit;
+    int32_t check_every;   /* host convergence poll interval (iterations); 0 -> default */
+    int32_t niter;         /* out */
+    int32_t converged;     /* out */
+    double relres;         /* out: ||r||/||b|| */
+} mp_solve_info;
+
+/* Jacobi-preconditioned CG (SPD: mass, pressure).  d_x holds the initial guess on entry. */
+int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
+                 mp_solve_info *info);
+/* Jacobi-preconditioned BiCGStab (non-symmetric transport rows). */
+int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
+                      mp_solve_info *info);
+
+/* ------------------------------------------------------------------ multi-GPU (replaces PETSc VecScatter / MPI_Allreduce)
+ * One process per GPU.  The NCCL unique id is created on rank 0 and broadcast by the host (torch.distributed). */
+int mp_nccl_unique_id(uint8_t *out128);
+int mp_comm_init(mp_ctx *ctx, int nranks, int rank, const uint8_t *id128);
+int mp_comm_destroy(mp_ctx *ctx);
+int mp_allreduce_sum(mp_ctx *ctx, double *d_buf, int count);
+/* halo plan: for each neighbour k, send x[d_send_idx[send_off[k] .. send_off[k+1])] and receive into
+ * x[recv_start[k] .. recv_start[k]+recv_count[k])  (ghost entries are contiguous per neighbour). */
+int mp_halo_create(mp_ctx *ctx, int nneigh, const int32_t *neigh_rank, const int32_t *send_off, const int32_t *d_send_idx,
+                   const int32_t *recv_start, const int32_t *recv_count, mp_halo **out);
+int mp_halo_exchange(mp_ctx *ctx, mp_halo *halo, double *d_x);
+int mp_halo_destroy(mp_halo *halo);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

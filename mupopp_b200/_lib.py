@@ -1,0 +1,113 @@
+"""ctypes binding of libmupopp_b200.so (the C-ABI declared in include/mupopp_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a call fails, an
+exception is raised.  PyTorch is used only to own device buffers and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmupopp_b200.so")
+
+c_i32p = C.POINTER(C.c_int32)
+c_f64p = C.POINTER(C.c_double)
+c_u8p = C.POINTER(C.c_uint8)
+
+
+class MpError(RuntimeError):
+    pass
+
+
+class MpMesh(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("ncell", C.c_int64), ("nvert", C.c_int64),
+                ("d_cells", C.c_void_p), ("d_coords", C.c_void_p)]
+
+
+class MpTransportParams(C.Structure):
+    _fields_ = [("Pe", C.c_double), ("Da", C.c_double), ("phi", C.c_double), ("beta", C.c_double), ("dt", C.c_double),
+                ("sigma", C.c_double), ("rho0", C.c_double), ("gamma", C.c_double),
+                ("frac", C.c_double * 3), ("zhat", C.c_double * 3), ("Kconst", C.c_double),
+                ("reaction", C.c_int32), ("ncomp", C.c_int32), ("supg", C.c_int32), ("pad", C.c_int32)]
+
+
+class MpCsr(C.Structure):
+    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nnz", C.c_int64),
+                ("d_rowptr", C.c_void_p), ("d_colidx", C.c_void_p), ("d_vals", C.c_void_p)]
+
+
+class MpSolveInfo(C.Structure):
+    _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("maxit", C.c_int32), ("check_every", C.c_int32),
+                ("niter", C.c_int32), ("converged", C.c_int32), ("relres", C.c_double)]
+
+
+# name -> (restype, argtypes); every name here must be declared in include/mupopp_b200.h
+_VP = C.c_void_p
+SIGNATURES = {
+    "mp_version": (C.c_int, []),
+    "mp_last_error": (C.c_char_p, []),
+    "mp_ctx_create": (C.c_int, [C.c_int, _VP, C.POINTER(_VP)]),
+    "mp_ctx_destroy": (C.c_int, [_VP]),
+    "mp_ctx_sync": (C.c_int, [_VP]),
+    "mp_ctx_launch_count": (C.c_int64, [_VP]),
+    "mp_plan_create": (C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_VP)]),
+    "mp_plan_nnz": (C.c_int64, [_VP]),
+    "mp_plan_export_csr": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "mp_plan_destroy": (C.c_int, [_VP]),
+    "mp_scatter_matrix": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "mp_scatter_vector": (C.c_int, [_VP, _VP, _VP, C.c_double, _VP]),
+    "mp_apply_dirichlet_sym": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "mp_elem_p1_mass": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_double, _VP]),
+    "mp_elem_p1_stiffness": (C.c_int, [_VP, C.POINTER(MpMesh), _VP, C.c_double, C.c_double, _VP]),
+    "mp_elem_p1_reaction_rhs": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, _VP, _VP, _VP]),
+    "mp_elem_p1_transport": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "mp_elem_p1_adr_single": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_double, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
+    "mp_elem_p1_pressure_rhs": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, _VP]),
+    "mp_recover_velocity": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, _VP, _VP]),
+    "mp_spmv": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP]),
+    "mp_dot": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.POINTER(C.c_double)]),
+    "mp_axpby": (C.c_int, [_VP, C.c_int64, C.c_double, _VP, C.c_double, _VP]),
+    "mp_jacobi_setup": (C.c_int, [_VP, C.POINTER(MpCsr), _VP]),
+    "mp_solve_pcg": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
+    "mp_solve_bicgstab": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
+    "mp_nccl_unique_id": (C.c_int, [_VP]),
+    "mp_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "mp_comm_destroy": (C.c_int, [_VP]),
+    "mp_allreduce_sum": (C.c_int, [_VP, _VP, C.c_int]),
+    "mp_halo_create": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, C.POINTER(_VP)]),
+    "mp_halo_exchange": (C.c_int, [_VP, _VP, _VP]),
+    "mp_halo_destroy": (C.c_int, [_VP]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises MpError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MpError("%s not found: build it with `python -m mupopp_b200.build` (or __graft_entry__.build()); "
+                      "mupopp_b200 has no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)     # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mp_last_error()
+        raise MpError("%s failed (code %d): %s" % (what or "mupopp_b200 call", rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Raw device pointer of a torch tensor (or None)."""
+    if t is None:
+        return None
+    return C.c_void_p(t.data_ptr())

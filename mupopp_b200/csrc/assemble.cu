@@ -1,0 +1,588 @@
+// P1 element kernels on triangles / tetrahedra (mode F: DG0 lagged velocity) + symmetric Dirichlet
+// elimination + fused cellwise velocity recovery.
+//
+// These replace the FFC-generated tabulate_tensor of the weak forms in
+// /root/reference/src/modules/mupopp.py (line ranges cited per kernel).  One thread per cell:
+// a 16-byte coalesced load of the cell's vertex ids, gathers of coordinates and nodal fields
+// (L2-resident neighbours), closed-form exact integration of the barycentric monomials, and a
+// contiguous [cell][i][j] store of the element tensor that the row-gather scatter (plan.cu) consumes.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kThreads = 128;
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+template <int D>
+struct Geom {
+    int32_t v[D + 1];
+    double g[D + 1][D];  // physical gradients of the barycentric (P1) basis
+    double vol;
+    double h;            // UFL CellDiameter: max vertex distance (mupopp.py:797,828)
+};
+
+template <int D>
+__device__ __forceinline__ void load_geom(const int32_t *__restrict__ cells, const double *__restrict__ coords, int64_t c,
+                                          Geom<D> &G) {
+    double x[D + 1][D];
+    if (D == 3) {
+        const int4 q = *reinterpret_cast<const int4 *>(cells + 4 * c);
+        G.v[0] = q.x; G.v[1] = q.y; G.v[2] = q.z; G.v[D] = q.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i <= D; ++i) G.v[i] = cells[(D + 1) * c + i];
+    }
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+        for (int a = 0; a < D; ++a) x[i][a] = coords[(int64_t)G.v[i] * D + a];
+    double hmax2 = 0.0;
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+        for (int j = i + 1; j <= D; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) { double d = x[i][a] - x[j][a]; s += d * d; }
+            hmax2 = fmax(hmax2, s);
+        }
+    G.h = sqrt(hmax2);
+    if (D == 2) {
+        const double a = x[1][0] - x[0][0], b = x[2][0] - x[0][0];
+        const double c2 = x[1][1] - x[0][1], d = x[2][1] - x[0][1];
+        const double det = a * d - b * c2;
+        const double inv = 1.0 / det;
+        // Jinv = 1/det [[d,-b],[-c,a]] ; grad lambda_k = row k-1 of Jinv
+        G.g[1][0] = d * inv;  G.g[1][1] = -b * inv;
+        G.g[2][0] = -c2 * inv; G.g[2][1] = a * inv;
+        G.vol = 0.5 * fabs(det);
+    } else {
+        double J[3][3];  // J[i][a] = x[a+1][i]-x[0][i]
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int a = 0; a < 3; ++a) J[i][a] = x[a + 1][i] - x[0][i];
+        const double c00 = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        const double c01 = J[1][2] * J[2][0] - J[1][0] * J[2][2];
+        const double c02 = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        const double det = J[0][0] * c00 + J[0][1] * c01 + J[0][2] * c02;
+        const double inv = 1.0 / det;
+        // Jinv[a][i] = cof[i][a]/det ; grad lambda_{a+1} = row a of Jinv
+        G.g[1][0] = c00 * inv;
+        G.g[2][0] = c01 * inv;
+        G.g[3][0] = c02 * inv;
+        G.g[1][1] = (J[0][2] * J[2][1] - J[0][1] * J[2][2]) * inv;
+        G.g[2][1] = (J[0][0] * J[2][2] - J[0][2] * J[2][0]) * inv;
+        G.g[3][1] = (J[0][1] * J[2][0] - J[0][0] * J[2][1]) * inv;
+        G.g[1][2] = (J[0][1] * J[1][2] - J[0][2] * J[1][1]) * inv;
+        G.g[2][2] = (J[0][2] * J[1][0] - J[0][0] * J[1][2]) * inv;
+        G.g[3][2] = (J[0][0] * J[1][1] - J[0][1] * J[1][0]) * inv;
+        G.vol = fabs(det) * (1.0 / 6.0);
+    }
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        double s = 0.0;
+#pragma unroll
+        for (int i = 1; i <= D; ++i) s += G.g[i][a];
+        G.g[0][a] = -s;
+    }
+}
+
+template <int D> __device__ __forceinline__ void gather(const double *__restrict__ f, const Geom<D> &G, double (&out)[D + 1]) {
+#pragma unroll
+    for (int i = 0; i <= D; ++i) out[i] = f[G.v[i]];
+}
+template <int D> __device__ __forceinline__ double sum(const double (&a)[D + 1]) {
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i <= D; ++i) s += a[i];
+    return s;
+}
+
+// exact integrals of barycentric monomials over a simplex, divided by |K|:  d! prod(alpha!) / (d+|alpha|)!
+template <int D> struct Coef {
+    static constexpr double c2 = 1.0 / ((D + 1) * (D + 2));
+    static constexpr double c3 = c2 / (D + 3);
+    static constexpr double c4 = c3 / (D + 4);
+};
+
+// (1/|K|) int lambda_i * a * b      (a, b P1 nodal)
+template <int D>
+__device__ __forceinline__ double T2(int i, const double (&a)[D + 1], const double (&b)[D + 1], double Sa, double Sb, double Sab) {
+    return Coef<D>::c3 * (Sa * Sb + a[i] * Sb + Sa * b[i] + Sab + 2.0 * a[i] * b[i]);
+}
+// (1/|K|) int a*b*c
+template <int D>
+__device__ __forceinline__ double I3(const double (&a)[D + 1], const double (&b)[D + 1], const double (&c)[D + 1]) {
+    double Sa = 0, Sb = 0, Sc = 0, Sab = 0, Sac = 0, Sbc = 0, Sabc = 0;
+#pragma unroll
+    for (int j = 0; j <= D; ++j) {
+        Sa += a[j]; Sb += b[j]; Sc += c[j];
+        Sab += a[j] * b[j]; Sac += a[j] * c[j]; Sbc += b[j] * c[j]; Sabc += a[j] * b[j] * c[j];
+    }
+    return Coef<D>::c3 * (Sa * Sb * Sc + Sa * Sbc + Sb * Sac + Sc * Sab + 2.0 * Sabc);
+}
+// (1/|K|) int lambda_i * a*b*c  (degree 4): brute force over the multi-index multiplicities (folded at compile time)
+template <int D>
+__device__ __forceinline__ void T3_all(const double (&a)[D + 1], const double (&b)[D + 1], const double (&c)[D + 1], double (&out)[D + 1]) {
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j <= D; ++j)
+#pragma unroll
+            for (int k = 0; k <= D; ++k)
+#pragma unroll
+                for (int l = 0; l <= D; ++l) {
+                    int cnt[D + 1];
+#pragma unroll
+                    for (int v = 0; v <= D; ++v) cnt[v] = (v == i) + (v == j) + (v == k) + (v == l);
+                    int m = 1;
+#pragma unroll
+                    for (int v = 0; v <= D; ++v) m *= (cnt[v] <= 1 ? 1 : cnt[v] == 2 ? 2 : cnt[v] == 3 ? 6 : 24);
+                    s += (double)m * a[j] * b[k] * c[l];
+                }
+        out[i] = Coef<D>::c4 * s;
+    }
+}
+
+// reaction base rate c0*c1 (kind 0) or c0*c1^2 (kind 1): test-weighted integrals and mean, all divided by |K|
+template <int D>
+__device__ __forceinline__ void reaction_ints(int kind, const double (&c0)[D + 1], const double (&c1)[D + 1], double (&Ti)[D + 1], double &mean) {
+    if (kind == 0) {
+        double Sa = 0, Sb = 0, Sab = 0;
+#pragma unroll
+        for (int j = 0; j <= D; ++j) { Sa += c0[j]; Sb += c1[j]; Sab += c0[j] * c1[j]; }
+#pragma unroll
+        for (int i = 0; i <= D; ++i) Ti[i] = T2<D>(i, c0, c1, Sa, Sb, Sab);
+        mean = Coef<D>::c2 * (Sa * Sb + Sab);
+    } else {
+        T3_all<D>(c0, c1, c1, Ti);
+        mean = I3<D>(c0, c1, c1);
+    }
+}
+
+__device__ __forceinline__ double tau_supg(int supg, double Pe, double Da, double h, double vn) {
+    // mupopp.py:835-846
+    if (supg == 1) return 1.0 / (4.0 / (Pe * h * h) + 2.0 * vn / h);
+    if (supg == 2) return 1.0 / (4.0 / (Pe * h * h) + 2.0 * vn / h + Da);
+    const double a = Pe * vn * h / 2.0;
+    const double e2 = exp(2.0 * a);
+    const double coth = (e2 + 1.0) / (e2 - 1.0);
+    return 0.5 * h * (coth - 1.0 / a) / vn;
+}
+
+template <int D>
+__device__ __forceinline__ void store_mat(double *__restrict__ emat, int64_t c, const double (&A)[D + 1][D + 1]) {
+    double *dst = emat + c * (D + 1) * (D + 1);
+    if (D == 3) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            reinterpret_cast<double2 *>(dst)[2 * i] = make_double2(A[i][0], A[i][1]);
+            reinterpret_cast<double2 *>(dst)[2 * i + 1] = make_double2(A[i][2], A[i][3]);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i <= D; ++i)
+#pragma unroll
+            for (int j = 0; j <= D; ++j) dst[i * (D + 1) + j] = A[i][j];
+    }
+}
+template <int D>
+__device__ __forceinline__ void store_vec(double *__restrict__ evec, int64_t c, const double (&b)[D + 1]) {
+    double *dst = evec + c * (D + 1);
+    if (D == 3) {
+        reinterpret_cast<double2 *>(dst)[0] = make_double2(b[0], b[1]);
+        reinterpret_cast<double2 *>(dst)[1] = make_double2(b[2], b[3]);
+    } else {
+#pragma unroll
+        for (int i = 0; i <= D; ++i) dst[i] = b[i];
+    }
+}
+
+template <int D>
+__device__ __forceinline__ double cell_K(const double *__restrict__ K, double Kconst, const Geom<D> &G) {
+    if (!K) return Kconst;
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i <= D; ++i) s += K[G.v[i]];
+    return s * (1.0 / (D + 1));
+}
+
+// ------------------------------------------------------------------ kernels
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_mass(mp_mesh m, double scale, double *__restrict__ emat) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double A[D + 1][D + 1];
+    const double w = scale * G.vol * Coef<D>::c2;
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+        for (int j = 0; j <= D; ++j) A[i][j] = (i == j) ? 2.0 * w : w;
+    store_mat<D>(emat, c, A);
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_stiffness(mp_mesh m, const double *__restrict__ K, double Kconst, double scale,
+                                                           double *__restrict__ emat) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    const double w = scale * cell_K<D>(K, Kconst, G) * G.vol;
+    double A[D + 1][D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+        for (int j = 0; j <= D; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) s += G.g[i][a] * G.g[j][a];
+            A[i][j] = w * s;
+        }
+    store_mat<D>(emat, c, A);
+}
+
+// c1 / c2 rows: qc*(cc-c0)*dx + dt*f21/(1-phi)*qc*dx ; qc1*(cc1-c1)*dx - dt*f31/(1-phi)*qc1*dx
+// (mupopp.py:826, :936-937, :1234-1235) -> right-hand sides of the consistent-mass solves.
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_reaction_rhs(mp_mesh m, mp_transport_params P, const double *__restrict__ c0n,
+                                                              const double *__restrict__ c1n, const double *__restrict__ c2n,
+                                                              double *__restrict__ eb1, double *__restrict__ eb2) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double a0[D + 1], a1[D + 1], Ti[D + 1], mean;
+    gather<D>(c0n, G, a0);
+    gather<D>(c1n, G, a1);
+    reaction_ints<D>(P.reaction, a0, a1, Ti, mean);
+    const double S1 = sum<D>(a1);
+    double b[D + 1];
+    const double k2 = P.dt * P.frac[1] * P.Da / (1.0 - P.phi);
+#pragma unroll
+    for (int i = 0; i <= D; ++i) b[i] = G.vol * (Coef<D>::c2 * (S1 + a1[i]) - k2 * Ti[i]);
+    store_vec<D>(eb1, c, b);
+    if (P.ncomp == 3 && eb2) {
+        double a2[D + 1];
+        gather<D>(c2n, G, a2);
+        const double S2 = sum<D>(a2);
+        const double k3 = P.dt * P.frac[2] * P.Da / (1.0 - P.phi);
+#pragma unroll
+        for (int i = 0; i <= D; ++i) b[i] = G.vol * (Coef<D>::c2 * (S2 + a2[i]) + k3 * Ti[i]);
+        store_vec<D>(eb2, c, b);
+    }
+}
+
+// c0 row, Crank-Nicolson + SUPG with the lagged velocity (mupopp.py:823-848, :934-958, :1231-1258):
+//   eta (c0-c0n) + dt [eta u.grad(cm) + grad(eta).grad(cm)/Pe] + dt R1/phi eta - beta dt f eta + tau (u.grad eta) r
+//   r = c0-c0n + dt (u.grad(cm) + R1/phi) - beta dt f + (c1-c1n + dt R2/(1-phi)) [+ (c2-c2n - dt R3/(1-phi))]
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_transport(mp_mesh m, mp_transport_params P, const double *__restrict__ ucell,
+                                                           const double *__restrict__ c0n, const double *__restrict__ c1n,
+                                                           const double *__restrict__ c2n, const double *__restrict__ c1new,
+                                                           const double *__restrict__ c2new, const double *__restrict__ fsrc,
+                                                           double *__restrict__ emat, double *__restrict__ evec) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double u[D], vn2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) { u[a] = ucell[c * D + a]; vn2 += u[a] * u[a]; }
+    const double tau = tau_supg(P.supg, P.Pe, P.Da, G.h, sqrt(vn2));
+    double ug[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) s += u[a] * G.g[i][a];
+        ug[i] = s;
+    }
+    const double vol = G.vol, dt = P.dt;
+    const double m1 = vol * (1.0 / (D + 1));
+    if (emat) {
+        double A[D + 1][D + 1];
+#pragma unroll
+        for (int i = 0; i <= D; ++i)
+#pragma unroll
+            for (int j = 0; j <= D; ++j) {
+                double gg = 0.0;
+#pragma unroll
+                for (int a = 0; a < D; ++a) gg += G.g[i][a] * G.g[j][a];
+                A[i][j] = vol * Coef<D>::c2 * (i == j ? 2.0 : 1.0) + 0.5 * dt * m1 * ug[j] + 0.5 * dt / P.Pe * vol * gg +
+                          tau * ug[i] * m1 + 0.5 * dt * tau * vol * ug[i] * ug[j];
+            }
+        store_mat<D>(emat, c, A);
+    }
+    if (evec) {
+        double a0[D + 1], a1[D + 1], f[D + 1], Ti[D + 1], meanR;
+        gather<D>(c0n, G, a0);
+        gather<D>(c1n, G, a1);
+        gather<D>(fsrc, G, f);
+        reaction_ints<D>(P.reaction, a0, a1, Ti, meanR);
+        const double S0 = sum<D>(a0), Sf = sum<D>(f), S1 = sum<D>(a1);
+        double ugc0 = 0.0, gc0[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) gc0[a] = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            ugc0 += ug[i] * a0[i];
+#pragma unroll
+            for (int a = 0; a < D; ++a) gc0[a] += a0[i] * G.g[i][a];
+        }
+        const double inv = 1.0 / (D + 1);
+        const double kR1 = dt * P.frac[0] * P.Da / P.phi;
+        double rk = -S0 * inv + 0.5 * dt * ugc0 + kR1 * meanR - P.beta * dt * Sf * inv - S1 * inv +
+                    dt * P.frac[1] * P.Da / (1.0 - P.phi) * meanR;
+        double cpl;  // mean of the NEW c1 (+c2): enters through the SUPG residual only
+        {
+            double n1[D + 1];
+            gather<D>(c1new, G, n1);
+            cpl = sum<D>(n1) * inv;
+        }
+        if (P.ncomp == 3) {
+            double a2[D + 1], n2[D + 1];
+            gather<D>(c2n, G, a2);
+            gather<D>(c2new, G, n2);
+            rk += -sum<D>(a2) * inv - dt * P.frac[2] * P.Da / (1.0 - P.phi) * meanR;
+            cpl += sum<D>(n2) * inv;
+        }
+        double b[D + 1];
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            double gg = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) gg += G.g[i][a] * gc0[a];
+            const double gal = Coef<D>::c2 * (S0 + a0[i]) - 0.5 * dt * ugc0 * inv - kR1 * Ti[i] + P.beta * dt * Coef<D>::c2 * (Sf + f[i]);
+            b[i] = vol * (gal - 0.5 * dt / P.Pe * gg - tau * ug[i] * (rk + cpl));
+        }
+        store_vec<D>(evec, c, b);
+    }
+}
+
+// DarcyAdvection.advection_diffusion (mupopp.py:627-664): tau = h/(2|w|), first-order reaction Da*c^n
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_adr_single(mp_mesh m, double Pe, double Da, double dt, const double *__restrict__ ucell,
+                                                            const double *__restrict__ cn, double *__restrict__ emat,
+                                                            double *__restrict__ evec) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double u[D], vn2 = 0.0;
+#pragma unroll
+    for (int a = 0; a < D; ++a) { u[a] = ucell[c * D + a]; vn2 += u[a] * u[a]; }
+    const double tau = G.h / (2.0 * sqrt(vn2));
+    double ug[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) s += u[a] * G.g[i][a];
+        ug[i] = s;
+    }
+    const double vol = G.vol, m1 = vol * (1.0 / (D + 1));
+    if (emat) {
+        double A[D + 1][D + 1];
+#pragma unroll
+        for (int i = 0; i <= D; ++i)
+#pragma unroll
+            for (int j = 0; j <= D; ++j) {
+                double gg = 0.0;
+#pragma unroll
+                for (int a = 0; a < D; ++a) gg += G.g[i][a] * G.g[j][a];
+                A[i][j] = vol * Coef<D>::c2 * (i == j ? 2.0 : 1.0) + 0.5 * dt * m1 * ug[j] + 0.5 * dt / Pe * vol * gg +
+                          tau * ug[i] * m1 + 0.5 * dt * tau * vol * ug[i] * ug[j];
+            }
+        store_mat<D>(emat, c, A);
+    }
+    if (evec) {
+        double a0[D + 1];
+        gather<D>(cn, G, a0);
+        const double S0 = sum<D>(a0), inv = 1.0 / (D + 1);
+        double ugc = 0.0, gc[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) gc[a] = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            ugc += ug[i] * a0[i];
+#pragma unroll
+            for (int a = 0; a < D; ++a) gc[a] += a0[i] * G.g[i][a];
+        }
+        const double rk = -S0 * inv + 0.5 * dt * ugc + dt * Da * S0 * inv;
+        double b[D + 1];
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            double gg = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) gg += G.g[i][a] * gc[a];
+            b[i] = vol * (Coef<D>::c2 * (S0 + a0[i]) * (1.0 - dt * Da) - 0.5 * dt * ugc * inv - 0.5 * dt / Pe * gg - tau * ug[i] * rk);
+        }
+        store_vec<D>(evec, c, b);
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_pressure_rhs(mp_mesh m, mp_transport_params P, const double *__restrict__ K,
+                                                              const double *__restrict__ c0, double *__restrict__ evec) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double a0[D + 1];
+    gather<D>(c0, G, a0);
+    const double rho = P.rho0 + P.gamma * sum<D>(a0) * (1.0 / (D + 1));
+    const double w = -P.sigma * G.vol * cell_K<D>(K, P.Kconst, G) / P.phi * rho;
+    double b[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) s += P.zhat[a] * G.g[i][a];
+        b[i] = w * s;
+    }
+    store_vec<D>(evec, c, b);
+}
+
+// u = -(K/phi)(grad p + sigma rho zhat): DarcyAdvection (sigma=-1) gives u = -k(grad p - drho zhat)/phi (mupopp.py:563)
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_recover_velocity(mp_mesh m, mp_transport_params P, const double *__restrict__ K,
+                                                               const double *__restrict__ p, const double *__restrict__ c0,
+                                                               double *__restrict__ ucell) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double a0[D + 1], pp[D + 1];
+    gather<D>(c0, G, a0);
+    gather<D>(p, G, pp);
+    const double rho = P.rho0 + P.gamma * sum<D>(a0) * (1.0 / (D + 1));
+    const double kf = cell_K<D>(K, P.Kconst, G) / P.phi;
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        double gp = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) gp += pp[i] * G.g[i][a];
+        ucell[c * D + a] = -kf * (gp + P.sigma * rho * P.zhat[a]);
+    }
+}
+
+// Symmetric Dirichlet elimination, 8 lanes per row, fixed reduction order.
+__global__ void __launch_bounds__(256) k_dirichlet(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                                                   double *__restrict__ vals, double *__restrict__ rhs,
+                                                   const uint8_t *__restrict__ isbc, const double *__restrict__ g) {
+    constexpr int S = 8;
+    const int lane = threadIdx.x & 31, sl = lane % S;
+    int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / S;
+    const bool active = row < nrow;
+    double acc = 0.0;
+    bool rbc = false;
+    if (active && !vals) rbc = isbc[row] != 0;  // rhs-only mode (matrix eliminated earlier, homogeneous columns)
+    if (active && vals) {
+        rbc = isbc[row] != 0;
+        const int32_t b = rowptr[row], e = rowptr[row + 1];
+        for (int32_t k = b + sl; k < e; k += S) {
+            const int32_t j = colidx[k];
+            if (rbc) {
+                vals[k] = (j == row) ? 1.0 : 0.0;
+            } else if (isbc[j]) {
+                acc += vals[k] * g[j];
+                vals[k] = 0.0;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = S / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (active && sl == 0 && rhs) rhs[row] = rbc ? g[row] : rhs[row] - acc;
+}
+
+#define DISPATCH_DIM(mesh, KERNEL, ...)                                                                        \
+    do {                                                                                                       \
+        unsigned grid = (unsigned)cdiv((mesh)->ncell, kThreads);                                               \
+        if (grid == 0) return 0;                                                                               \
+        if ((mesh)->dim == 2) KERNEL<2><<<grid, kThreads, 0, ctx->stream>>>(*(mesh), __VA_ARGS__);             \
+        else KERNEL<3><<<grid, kThreads, 0, ctx->stream>>>(*(mesh), __VA_ARGS__);                              \
+        mp::count_launch(ctx);                                                                                 \
+        MP_CUDA(cudaGetLastError());                                                                           \
+    } while (0)
+
+int check_mesh(const mp_ctx *ctx, const mp_mesh *m) {
+    MP_CHECK(ctx && m, "null ctx/mesh");
+    MP_CHECK(m->dim == 2 || m->dim == 3, "mesh dim must be 2 or 3 (got %d)", m->dim);
+    MP_CHECK(m->d_cells && m->d_coords, "mesh device pointers are null");
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mp_elem_p1_mass(mp_ctx *ctx, const mp_mesh *mesh, double scale, double *d_elem_mat) {
+    MP_TRY(check_mesh(ctx, mesh));
+    DISPATCH_DIM(mesh, k_p1_mass, scale, d_elem_mat);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_stiffness(mp_ctx *ctx, const mp_mesh *mesh, const double *d_K, double Kconst, double scale, double *d_elem_mat) {
+    MP_TRY(check_mesh(ctx, mesh));
+    DISPATCH_DIM(mesh, k_p1_stiffness, d_K, Kconst, scale, d_elem_mat);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_reaction_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_c0n,
+                                       const double *d_c1n, const double *d_c2n, double *d_elem_b1, double *d_elem_b2) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(prm && d_c0n && d_c1n && d_elem_b1, "mp_elem_p1_reaction_rhs: null argument");
+    MP_CHECK(prm->ncomp == 2 || (d_c2n && d_elem_b2), "mp_elem_p1_reaction_rhs: ncomp==3 needs c2n and elem_b2");
+    DISPATCH_DIM(mesh, k_p1_reaction_rhs, *prm, d_c0n, d_c1n, d_c2n, d_elem_b1, d_elem_b2);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_transport(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_ucell,
+                                    const double *d_c0n, const double *d_c1n, const double *d_c2n, const double *d_c1new,
+                                    const double *d_c2new, const double *d_fsrc, double *d_elem_mat, double *d_elem_vec) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(prm && d_ucell, "mp_elem_p1_transport: null argument");
+    MP_CHECK(!d_elem_vec || (d_c0n && d_c1n && d_c1new && d_fsrc), "mp_elem_p1_transport: rhs needs c0n,c1n,c1new,fsrc");
+    MP_CHECK(!d_elem_vec || prm->ncomp == 2 || (d_c2n && d_c2new), "mp_elem_p1_transport: ncomp==3 needs c2n,c2new");
+    DISPATCH_DIM(mesh, k_p1_transport, *prm, d_ucell, d_c0n, d_c1n, d_c2n, d_c1new, d_c2new, d_fsrc, d_elem_mat, d_elem_vec);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_adr_single(mp_ctx *ctx, const mp_mesh *mesh, double Pe, double Da, double dt, const double *d_ucell,
+                                     const double *d_cn, double *d_elem_mat, double *d_elem_vec) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(d_ucell && (!d_elem_vec || d_cn), "mp_elem_p1_adr_single: null argument");
+    DISPATCH_DIM(mesh, k_p1_adr_single, Pe, Da, dt, d_ucell, d_cn, d_elem_mat, d_elem_vec);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_pressure_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_K,
+                                       const double *d_c0, double *d_elem_vec) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(prm && d_c0 && d_elem_vec, "mp_elem_p1_pressure_rhs: null argument");
+    DISPATCH_DIM(mesh, k_p1_pressure_rhs, *prm, d_K, d_c0, d_elem_vec);
+    return 0;
+}
+
+extern "C" int mp_recover_velocity(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_K,
+                                   const double *d_p, const double *d_c0, double *d_ucell) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(prm && d_p && d_c0 && d_ucell, "mp_recover_velocity: null argument");
+    DISPATCH_DIM(mesh, k_recover_velocity, *prm, d_K, d_p, d_c0, d_ucell);
+    return 0;
+}
+
+extern "C" int mp_apply_dirichlet_sym(mp_ctx *ctx, int64_t nrow, const int32_t *d_rowptr, const int32_t *d_colidx, double *d_vals,
+                                      double *d_rhs, const uint8_t *d_isbc, const double *d_g) {
+    MP_CHECK(ctx && d_rowptr && d_colidx && d_isbc && d_g, "mp_apply_dirichlet_sym: null argument");
+    MP_CHECK(d_vals || d_rhs, "mp_apply_dirichlet_sym: nothing to do (vals and rhs both null)");
+    if (nrow == 0) return 0;
+    k_dirichlet<<<(unsigned)cdiv(nrow * 8, 256), 256, 0, ctx->stream>>>(nrow, d_rowptr, d_colidx, d_vals, d_rhs, d_isbc, d_g);
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,243 @@
+// Context, error reporting, workspace, NCCL glue (dlopen'ed) and halo exchange.
+//
+// Multi-GPU replaces what DOLFIN/PETSc do over MPI in the reference (aprun -n 24|48,
+// /root/reference/src/run/sphere_archer/submit.sh:25): VecScatter ghost updates become grouped
+// ncclSend/ncclRecv of interface dofs, MPI_Allreduce of inner products becomes one small ncclAllReduce.
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace mp {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ws_get(mp_ctx *ctx, int slot, size_t bytes, void **out) {
+    Workspace &w = ctx->work[slot];
+    if (w.bytes < bytes) {
+        if (w.ptr) cudaFree(w.ptr);
+        w.ptr = nullptr; w.bytes = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        MP_CUDA(cudaMalloc(&w.ptr, want));
+        w.bytes = want;
+    }
+    *out = w.ptr;
+    return 0;
+}
+
+// ---- NCCL, resolved at run time so that the library loads (and the CPU-side symbol test runs) without it
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef int (*pfn_GetUniqueId)(ncclUniqueId_t *);
+typedef int (*pfn_CommInitRank)(void **, int, ncclUniqueId_t, int);
+typedef int (*pfn_CommDestroy)(void *);
+typedef int (*pfn_AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*pfn_Send)(const void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*pfn_Recv)(void *, size_t, int, int, void *, cudaStream_t);
+typedef int (*pfn_Group)(void);
+typedef const char *(*pfn_ErrStr)(int);
+
+struct Nccl {
+    void *h = nullptr;
+    pfn_GetUniqueId GetUniqueId = nullptr;
+    pfn_CommInitRank CommInitRank = nullptr;
+    pfn_CommDestroy CommDestroy = nullptr;
+    pfn_AllReduce AllReduce = nullptr;
+    pfn_Send Send = nullptr;
+    pfn_Recv Recv = nullptr;
+    pfn_Group GroupStart = nullptr, GroupEnd = nullptr;
+    pfn_ErrStr ErrStr = nullptr;
+};
+static Nccl g_nccl;
+
+static int nccl_load() {
+    if (g_nccl.h) return 0;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    for (int i = 0; names[i] && !g_nccl.h; ++i) g_nccl.h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    MP_CHECK(g_nccl.h, "NCCL: cannot dlopen libnccl.so.2 (%s)", dlerror());
+#define LD(sym)                                                                 \
+    g_nccl.sym = (decltype(g_nccl.sym))dlsym(g_nccl.h, "nccl" #sym);            \
+    MP_CHECK(g_nccl.sym, "NCCL: missing symbol nccl" #sym)
+    LD(GetUniqueId); LD(CommInitRank); LD(CommDestroy); LD(AllReduce); LD(Send); LD(Recv); LD(GroupStart); LD(GroupEnd);
+#undef LD
+    g_nccl.ErrStr = (pfn_ErrStr)dlsym(g_nccl.h, "ncclGetErrorString");
+    return 0;
+}
+
+#define MP_NCCL(call)                                                                                         \
+    do {                                                                                                      \
+        int _r = (call);                                                                                      \
+        if (_r != 0) {                                                                                        \
+            mp::set_error("%s:%d: %s -> NCCL error %d (%s)", __FILE__, __LINE__, #call, _r,                   \
+                          mp::g_nccl.ErrStr ? mp::g_nccl.ErrStr(_r) : "?");                                   \
+            return 3;                                                                                         \
+        }                                                                                                     \
+    } while (0)
+
+constexpr int kNcclFloat64 = 8, kNcclSum = 0;
+
+}  // namespace mp
+
+struct mp_halo {
+    int nneigh = 0;
+    std::vector<int32_t> rank, send_off, recv_start, recv_count;
+    int32_t *d_send_idx = nullptr;  // owned copy
+    double *d_sendbuf = nullptr;
+    int64_t nsend = 0;
+};
+
+namespace {
+__global__ void k_pack(const double *__restrict__ x, const int32_t *__restrict__ idx, double *__restrict__ buf, int64_t n) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t < n) buf[t] = x[idx[t]];
+}
+}  // namespace
+
+extern "C" {
+
+int mp_version(void) { return 100; }
+
+const char *mp_last_error(void) { return mp::g_err; }
+
+int mp_ctx_create(int device, void *stream, mp_ctx **out) {
+    MP_CHECK(out, "mp_ctx_create: out is null");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    MP_CHECK(e == cudaSuccess && ndev > 0, "mp_ctx_create: no CUDA device (%s); this library has no CPU fallback",
+             cudaGetErrorString(e));
+    MP_CHECK(device >= 0 && device < ndev, "mp_ctx_create: device %d out of range (%d devices)", device, ndev);
+    MP_CUDA(cudaSetDevice(device));
+    mp_ctx *c = new mp_ctx();
+    c->device = device;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        MP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        c->own_stream = true;
+    }
+    cudaDeviceProp prop;
+    MP_CUDA(cudaGetDeviceProperties(&prop, device));
+    c->num_sm = prop.multiProcessorCount;
+    MP_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 64));
+    MP_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 64));
+    MP_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * 64));
+    MP_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int) * 4));
+    MP_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * 4));
+    MP_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 4096 * 4));
+    MP_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    *out = c;
+    return 0;
+}
+
+int mp_ctx_destroy(mp_ctx *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->nccl_comm && mp::g_nccl.CommDestroy) mp::g_nccl.CommDestroy(c->nccl_comm);
+    for (auto &w : c->work) if (w.ptr) cudaFree(w.ptr);
+    cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_counter); cudaFree(c->d_partials);
+    if (c->ev) cudaEventDestroy(c->ev);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int mp_ctx_sync(mp_ctx *c) {
+    MP_CHECK(c, "mp_ctx_sync: null ctx");
+    MP_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int64_t mp_ctx_launch_count(const mp_ctx *c) { return c ? c->launches : -1; }
+
+int mp_nccl_unique_id(uint8_t *out128) {
+    MP_CHECK(out128, "mp_nccl_unique_id: null");
+    MP_TRY(mp::nccl_load());
+    mp::ncclUniqueId_t id;
+    MP_NCCL(mp::g_nccl.GetUniqueId(&id));
+    memcpy(out128, id.internal, 128);
+    return 0;
+}
+
+int mp_comm_init(mp_ctx *c, int nranks, int rank, const uint8_t *id128) {
+    MP_CHECK(c && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "mp_comm_init: bad argument");
+    MP_TRY(mp::nccl_load());
+    MP_CUDA(cudaSetDevice(c->device));
+    mp::ncclUniqueId_t id;
+    memcpy(id.internal, id128, 128);
+    MP_NCCL(mp::g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank));
+    c->nranks = nranks;
+    c->rank = rank;
+    return 0;
+}
+
+int mp_comm_destroy(mp_ctx *c) {
+    if (c && c->nccl_comm) {
+        cudaStreamSynchronize(c->stream);
+        mp::g_nccl.CommDestroy(c->nccl_comm);
+        c->nccl_comm = nullptr;
+        c->nranks = 1; c->rank = 0;
+    }
+    return 0;
+}
+
+int mp_allreduce_sum(mp_ctx *c, double *d_buf, int count) {
+    MP_CHECK(c && d_buf && count >= 0, "mp_allreduce_sum: bad argument");
+    if (c->nranks <= 1 || !c->nccl_comm || count == 0) return 0;
+    MP_NCCL(mp::g_nccl.AllReduce(d_buf, d_buf, (size_t)count, mp::kNcclFloat64, mp::kNcclSum, c->nccl_comm, c->stream));
+    return 0;
+}
+
+int mp_halo_create(mp_ctx *c, int nneigh, const int32_t *neigh_rank, const int32_t *send_off, const int32_t *d_send_idx,
+                   const int32_t *recv_start, const int32_t *recv_count, mp_halo **out) {
+    MP_CHECK(c && out && nneigh >= 0, "mp_halo_create: bad argument");
+    mp_halo *h = new mp_halo();
+    h->nneigh = nneigh;
+    h->rank.assign(neigh_rank, neigh_rank + nneigh);
+    h->send_off.assign(send_off, send_off + nneigh + 1);
+    h->recv_start.assign(recv_start, recv_start + nneigh);
+    h->recv_count.assign(recv_count, recv_count + nneigh);
+    h->nsend = nneigh ? send_off[nneigh] : 0;
+    if (h->nsend > 0) {
+        MP_CUDA(cudaMalloc(&h->d_send_idx, sizeof(int32_t) * h->nsend));
+        MP_CUDA(cudaMemcpyAsync(h->d_send_idx, d_send_idx, sizeof(int32_t) * h->nsend, cudaMemcpyDeviceToDevice, c->stream));
+        MP_CUDA(cudaMalloc(&h->d_sendbuf, sizeof(double) * h->nsend));
+    }
+    *out = h;
+    return 0;
+}
+
+int mp_halo_exchange(mp_ctx *c, mp_halo *h, double *d_x) {
+    MP_CHECK(c && d_x, "mp_halo_exchange: bad argument");
+    if (!h || h->nneigh == 0 || c->nranks <= 1) return 0;
+    MP_CHECK(c->nccl_comm, "mp_halo_exchange: no communicator attached (call mp_comm_init)");
+    if (h->nsend > 0) {
+        k_pack<<<(unsigned)((h->nsend + 255) / 256), 256, 0, c->stream>>>(d_x, h->d_send_idx, h->d_sendbuf, h->nsend);
+        mp::count_launch(c);
+    }
+    MP_NCCL(mp::g_nccl.GroupStart());
+    for (int k = 0; k < h->nneigh; ++k) {
+        int32_t ns = h->send_off[k + 1] - h->send_off[k];
+        if (ns > 0) MP_NCCL(mp::g_nccl.Send(h->d_sendbuf + h->send_off[k], (size_t)ns, mp::kNcclFloat64, h->rank[k], c->nccl_comm, c->stream));
+        if (h->recv_count[k] > 0)
+            MP_NCCL(mp::g_nccl.Recv(d_x + h->recv_start[k], (size_t)h->recv_count[k], mp::kNcclFloat64, h->rank[k], c->nccl_comm, c->stream));
+    }
+    MP_NCCL(mp::g_nccl.GroupEnd());
+    return 0;
+}
+
+int mp_halo_destroy(mp_halo *h) {
+    if (!h) return 0;
+    cudaFree(h->d_send_idx); cudaFree(h->d_sendbuf);
+    delete h;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,344 @@
+// Scatter plan: CSR pattern + dof->(cell,local) incidence lists + slot map, all built on the GPU,
+// and the deterministic (atomic-free) row-gather scatter of element matrices / vectors.
+//
+// Replaces DOLFIN's SparsityPatternBuilder / GenericDofMap / MatSetValuesLocal (reached from
+// assemble_system, e.g. /root/reference/src/modules/mupopp.py:295-297,415-417).
+// CUB (part of the CUDA toolkit) is used for the one-time radix sorts / scans of plan construction;
+// everything that runs per timestep is a hand-written kernel.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+struct mp_plan {
+    int lr = 0, lc = 0;
+    int64_t ncell = 0, nrow = 0, ncol = 0, nnz = 0;
+    int32_t *d_rowptr = nullptr;
+    int32_t *d_colidx = nullptr;
+    int32_t *d_inc_ptr = nullptr;  // [nrow+1]
+    int32_t *d_inc = nullptr;      // [ninc]  id = cell*lr + li, ascending per row
+    uint16_t *d_slot = nullptr;    // [ncell*lr*lc] offset of (row(cell,li), col(cell,j)) inside its CSR row
+    int64_t ninc = 0;
+    int rows_per_block = 128;      // scatter kernel tiling: nnz of a row block must fit in shared memory
+    int smem_doubles = 0;
+    int max_row_nnz = 0;
+};
+
+namespace {
+
+constexpr int kThreads = 256;
+inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+__global__ void k_inc_keys(const int32_t *__restrict__ row_dofs, int64_t n, int32_t nrow, int32_t *keys, int32_t *ids,
+                           int32_t *cnt) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int32_t r = row_dofs[t];
+    bool ok = (r >= 0 && r < nrow);
+    keys[t] = ok ? r : nrow;  // invalid rows sort to the end
+    ids[t] = (int32_t)t;
+    if (ok) atomicAdd(&cnt[r], 1);  // integer atomics: result is order independent
+}
+
+__global__ void k_pattern_keys(const int32_t *__restrict__ row_dofs, const int32_t *__restrict__ col_dofs, int lr, int lc,
+                               int64_t ncell, int32_t nrow, int64_t ncol, uint64_t *keys) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // one thread per (cell, li)
+    if (t >= ncell * lr) return;
+    int64_t cell = t / lr;
+    int32_t r = row_dofs[t];
+    bool ok = (r >= 0 && r < nrow);
+    for (int j = 0; j < lc; ++j) {
+        int32_t c = col_dofs[cell * lc + j];
+        keys[t * lc + j] = (ok && c >= 0 && c < ncol) ? (uint64_t)r * (uint64_t)ncol + (uint64_t)c : ~0ull;
+    }
+}
+
+__global__ void k_unpack_unique(const uint64_t *__restrict__ ukeys, int64_t nu, int64_t ncol, int32_t *colidx, int32_t *rowcnt) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= nu) return;
+    uint64_t k = ukeys[t];
+    if (k == ~0ull) return;
+    colidx[t] = (int32_t)(k % (uint64_t)ncol);
+    atomicAdd(&rowcnt[k / (uint64_t)ncol], 1);
+}
+
+__global__ void k_slots(const int32_t *__restrict__ row_dofs, const int32_t *__restrict__ col_dofs, int lr, int lc,
+                        int64_t ncell, int32_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+                        uint16_t *slot) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= ncell * lr) return;
+    int64_t cell = t / lr;
+    int32_t r = row_dofs[t];
+    if (r < 0 || r >= nrow) {
+        for (int j = 0; j < lc; ++j) slot[t * lc + j] = 0xffff;
+        return;
+    }
+    int32_t b = rowptr[r], e = rowptr[r + 1];
+    for (int j = 0; j < lc; ++j) {
+        int32_t c = col_dofs[cell * lc + j];
+        int32_t lo = b, hi = e;
+        while (lo < hi) {  // lower_bound
+            int32_t mid = (lo + hi) >> 1;
+            if (colidx[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        slot[t * lc + j] = (lo < e && colidx[lo] == c) ? (uint16_t)(lo - b) : (uint16_t)0xffff;
+    }
+}
+
+__global__ void k_max_rowlen(const int32_t *__restrict__ rowptr, int32_t nrow, int *out) {
+    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int v = 0;
+    if (t < nrow) v = rowptr[t + 1] - rowptr[t];
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
+}
+
+// One CTA owns a contiguous block of rows; its CSR value segment is accumulated in shared memory
+// (each thread owns one row => no conflicts, fixed summation order) and written back coalesced.
+template <int LC>
+__global__ void __launch_bounds__(kThreads)
+k_scatter_matrix(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
+                 const uint16_t *__restrict__ slot, const double *__restrict__ emat, double *__restrict__ vals,
+                 int32_t nrow, int rows_per_block, int lc_rt) {
+    extern __shared__ double sm[];
+    const int lc = LC > 0 ? LC : lc_rt;
+    int32_t r0 = blockIdx.x * rows_per_block;
+    int32_t r1 = min(r0 + rows_per_block, nrow);
+    int32_t base = rowptr[r0];
+    int32_t seg = rowptr[r1] - base;
+    for (int k = threadIdx.x; k < seg; k += blockDim.x) sm[k] = 0.0;
+    __syncthreads();
+    for (int32_t r = r0 + threadIdx.x; r < r1; r += blockDim.x) {
+        double *row = sm + (rowptr[r] - base);
+        int32_t e0 = inc_ptr[r], e1 = inc_ptr[r + 1];
+        for (int32_t e = e0; e < e1; ++e) {
+            int64_t id = inc[e];
+            const double *src = emat + id * lc;
+            const uint16_t *sl = slot + id * lc;
+            if (LC == 4) {
+                const double2 a = *reinterpret_cast<const double2 *>(src);
+                const double2 b = *reinterpret_cast<const double2 *>(src + 2);
+                const ushort4 s = *reinterpret_cast<const ushort4 *>(sl);
+                if (s.x != 0xffff) row[s.x] += a.x;
+                if (s.y != 0xffff) row[s.y] += a.y;
+                if (s.z != 0xffff) row[s.z] += b.x;
+                if (s.w != 0xffff) row[s.w] += b.y;
+            } else {
+#pragma unroll 4
+                for (int j = 0; j < lc; ++j) {
+                    uint16_t s = sl[j];
+                    if (s != 0xffff) row[s] += src[j];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < seg; k += blockDim.x) vals[base + k] = sm[k];
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_scatter_vector(const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc, const double *__restrict__ evec,
+                 double beta, double *__restrict__ out, int32_t nrow) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nrow) return;
+    int32_t e0 = inc_ptr[r], e1 = inc_ptr[r + 1];
+    double s = 0.0;
+    for (int32_t e = e0; e < e1; ++e) s += evec[inc[e]];
+    out[r] = (beta == 0.0) ? s : beta * out[r] + s;
+}
+
+}  // namespace
+
+extern "C" int mp_plan_destroy(mp_plan *p) {
+    if (!p) return 0;
+    cudaFree(p->d_rowptr); cudaFree(p->d_colidx); cudaFree(p->d_inc_ptr); cudaFree(p->d_inc); cudaFree(p->d_slot);
+    delete p;
+    return 0;
+}
+
+extern "C" int64_t mp_plan_nnz(const mp_plan *p) { return p ? p->nnz : -1; }
+
+extern "C" int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr, const int32_t *d_col_dofs, int32_t lc,
+                              int64_t ncell, int64_t nrow, int64_t ncol, mp_plan **out) {
+    MP_CHECK(ctx && d_row_dofs && out, "mp_plan_create: null argument");
+    MP_CHECK(lr > 0 && ncell >= 0 && nrow > 0, "mp_plan_create: bad sizes");
+    MP_CHECK(ncell * lr < (int64_t)INT32_MAX, "mp_plan_create: ncell*lr exceeds int32");
+    MP_CHECK(nrow < INT32_MAX && ncol < INT32_MAX, "mp_plan_create: nrow/ncol exceed int32");
+    MP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    mp_plan *p = new mp_plan();
+    p->lr = lr; p->lc = lc; p->ncell = ncell; p->nrow = nrow; p->ncol = ncol;
+    const int64_t ninc_all = ncell * lr;
+    int rc = 0;
+    int32_t *keys = nullptr, *keys2 = nullptr, *ids = nullptr, *ids2 = nullptr, *cnt = nullptr;
+    void *tmp = nullptr;
+    uint64_t *pk = nullptr, *pk2 = nullptr, *uk = nullptr;
+    int64_t *d_nu = nullptr;
+    int32_t *rowcnt = nullptr;
+    int *d_max = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(keys); cudaFree(keys2); cudaFree(ids); cudaFree(ids2); cudaFree(cnt); cudaFree(tmp);
+        cudaFree(pk); cudaFree(pk2); cudaFree(uk); cudaFree(d_nu); cudaFree(rowcnt); cudaFree(d_max);
+    };
+#define PC(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            mp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));    \
+            cleanup(); mp_plan_destroy(p); return 1;                                                \
+        }                                                                                           \
+    } while (0)
+
+    // ---- 1. incidence lists: stable radix sort of (row, id) pairs => ascending cell id inside each row
+    PC(cudaMalloc(&keys, sizeof(int32_t) * (ninc_all + 1)));
+    PC(cudaMalloc(&keys2, sizeof(int32_t) * (ninc_all + 1)));
+    PC(cudaMalloc(&ids, sizeof(int32_t) * (ninc_all + 1)));
+    PC(cudaMalloc(&ids2, sizeof(int32_t) * (ninc_all + 1)));
+    PC(cudaMalloc(&cnt, sizeof(int32_t) * (nrow + 1)));
+    PC(cudaMemsetAsync(cnt, 0, sizeof(int32_t) * (nrow + 1), st));
+    if (ninc_all > 0) {
+        k_inc_keys<<<(unsigned)cdiv(ninc_all, kThreads), kThreads, 0, st>>>(d_row_dofs, ninc_all, (int32_t)nrow, keys, ids, cnt);
+        mp::count_launch(ctx);
+    }
+    {
+        int bits = 1;
+        while ((1ll << bits) <= nrow) ++bits;  // keys in [0, nrow]
+        size_t tb = 0;
+        PC(cub::DeviceRadixSort::SortPairs(nullptr, tb, keys, keys2, ids, ids2, (int)ninc_all, 0, bits, st));
+        PC(cudaMalloc(&tmp, tb + 16));
+        PC(cub::DeviceRadixSort::SortPairs(tmp, tb, keys, keys2, ids, ids2, (int)ninc_all, 0, bits, st));
+        cudaFree(tmp); tmp = nullptr;
+    }
+    PC(cudaMalloc(&p->d_inc_ptr, sizeof(int32_t) * (nrow + 1)));
+    {
+        size_t tb = 0;
+        PC(cub::DeviceScan::ExclusiveSum(nullptr, tb, cnt, p->d_inc_ptr, (int)(nrow + 1), st));
+        PC(cudaMalloc(&tmp, tb + 16));
+        PC(cub::DeviceScan::ExclusiveSum(tmp, tb, cnt, p->d_inc_ptr, (int)(nrow + 1), st));
+        cudaFree(tmp); tmp = nullptr;
+    }
+    int32_t ninc = 0;
+    PC(cudaMemcpyAsync(&ninc, p->d_inc_ptr + nrow, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    PC(cudaStreamSynchronize(st));
+    p->ninc = ninc;
+    PC(cudaMalloc(&p->d_inc, sizeof(int32_t) * (size_t)(ninc > 0 ? ninc : 1)));
+    PC(cudaMemcpyAsync(p->d_inc, ids2, sizeof(int32_t) * (size_t)ninc, cudaMemcpyDeviceToDevice, st));
+    PC(cudaStreamSynchronize(st));
+    cudaFree(keys); cudaFree(keys2); cudaFree(ids); cudaFree(ids2); cudaFree(cnt);
+    keys = keys2 = ids = ids2 = cnt = nullptr;
+
+    // ---- 2. CSR pattern: sort 64-bit (row,col) keys of every local entry, unique
+    if (lc > 0) {
+        MP_CHECK(d_col_dofs, "mp_plan_create: lc > 0 but d_col_dofs is null");
+        const int64_t nkeys = ninc_all * lc;
+        if (nkeys >= (int64_t)INT32_MAX) { mp::set_error("mp_plan_create: ncell*lr*lc exceeds int32"); cleanup(); mp_plan_destroy(p); return 2; }
+        PC(cudaMalloc(&pk, sizeof(uint64_t) * (nkeys + 1)));
+        PC(cudaMalloc(&pk2, sizeof(uint64_t) * (nkeys + 1)));
+        k_pattern_keys<<<(unsigned)cdiv(ninc_all, kThreads), kThreads, 0, st>>>(d_row_dofs, d_col_dofs, lr, lc, ncell, (int32_t)nrow, ncol, pk);
+        mp::count_launch(ctx);
+        {
+            size_t tb = 0;
+            PC(cub::DeviceRadixSort::SortKeys(nullptr, tb, pk, pk2, (int)nkeys, 0, 64, st));
+            PC(cudaMalloc(&tmp, tb + 16));
+            PC(cub::DeviceRadixSort::SortKeys(tmp, tb, pk, pk2, (int)nkeys, 0, 64, st));
+            cudaFree(tmp); tmp = nullptr;
+        }
+        uk = pk;  // reuse the unsorted buffer for the unique keys
+        pk = nullptr;
+        PC(cudaMalloc(&d_nu, sizeof(int64_t)));
+        {
+            size_t tb = 0;
+            PC(cub::DeviceSelect::Unique(nullptr, tb, pk2, uk, d_nu, (int)nkeys, st));
+            PC(cudaMalloc(&tmp, tb + 16));
+            PC(cub::DeviceSelect::Unique(tmp, tb, pk2, uk, d_nu, (int)nkeys, st));
+            cudaFree(tmp); tmp = nullptr;
+        }
+        int64_t nu = 0;
+        PC(cudaMemcpyAsync(&nu, d_nu, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        PC(cudaStreamSynchronize(st));
+        cudaFree(pk2); pk2 = nullptr;
+        // the sentinel (invalid rows/cols), if present, is the last unique key
+        uint64_t lastkey = 0;
+        if (nu > 0) PC(cudaMemcpy(&lastkey, uk + (nu - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost));
+        int64_t nnz = (nu > 0 && lastkey == ~0ull) ? nu - 1 : nu;
+        p->nnz = nnz;
+        PC(cudaMalloc(&p->d_colidx, sizeof(int32_t) * (size_t)(nnz > 0 ? nnz : 1)));
+        PC(cudaMalloc(&rowcnt, sizeof(int32_t) * (nrow + 1)));
+        PC(cudaMemsetAsync(rowcnt, 0, sizeof(int32_t) * (nrow + 1), st));
+        if (nnz > 0) {
+            k_unpack_unique<<<(unsigned)cdiv(nnz, kThreads), kThreads, 0, st>>>(uk, nnz, ncol, p->d_colidx, rowcnt);
+            mp::count_launch(ctx);
+        }
+        PC(cudaMalloc(&p->d_rowptr, sizeof(int32_t) * (nrow + 1)));
+        {
+            size_t tb = 0;
+            PC(cub::DeviceScan::ExclusiveSum(nullptr, tb, rowcnt, p->d_rowptr, (int)(nrow + 1), st));
+            PC(cudaMalloc(&tmp, tb + 16));
+            PC(cub::DeviceScan::ExclusiveSum(tmp, tb, rowcnt, p->d_rowptr, (int)(nrow + 1), st));
+            cudaFree(tmp); tmp = nullptr;
+        }
+        cudaFree(uk); uk = nullptr;
+        // ---- 3. slot map + row-block tiling of the scatter kernel
+        PC(cudaMalloc(&p->d_slot, sizeof(uint16_t) * (size_t)(nkeys > 0 ? nkeys : 1)));
+        if (ninc_all > 0) {
+            k_slots<<<(unsigned)cdiv(ninc_all, kThreads), kThreads, 0, st>>>(d_row_dofs, d_col_dofs, lr, lc, ncell, (int32_t)nrow,
+                                                                             p->d_rowptr, p->d_colidx, p->d_slot);
+            mp::count_launch(ctx);
+        }
+        PC(cudaMalloc(&d_max, sizeof(int)));
+        PC(cudaMemsetAsync(d_max, 0, sizeof(int), st));
+        k_max_rowlen<<<(unsigned)cdiv(nrow, kThreads), kThreads, 0, st>>>(p->d_rowptr, (int32_t)nrow, d_max);
+        mp::count_launch(ctx);
+        int mx = 0;
+        PC(cudaMemcpyAsync(&mx, d_max, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PC(cudaStreamSynchronize(st));
+        p->max_row_nnz = mx;
+        if (mx >= 0xffff) { mp::set_error("mp_plan_create: row with %d entries exceeds the 16-bit slot map", mx); cleanup(); mp_plan_destroy(p); return 2; }
+        const int cap = 12288;  // doubles of shared memory per CTA (96 KB)
+        int rpb = mx > 0 ? cap / mx : kThreads;
+        if (rpb > kThreads) rpb = kThreads;
+        if (rpb >= 32) rpb &= ~31;
+        if (rpb < 1) { mp::set_error("mp_plan_create: row with %d entries does not fit the scatter tile", mx); cleanup(); mp_plan_destroy(p); return 2; }
+        p->rows_per_block = rpb;
+        p->smem_doubles = rpb * (mx > 0 ? mx : 1);
+    }
+#undef PC
+    cleanup();
+    *out = p;
+    return 0;
+}
+
+extern "C" int mp_plan_export_csr(mp_ctx *ctx, const mp_plan *p, int32_t *d_rowptr, int32_t *d_colidx) {
+    MP_CHECK(ctx && p && p->lc > 0, "mp_plan_export_csr: plan has no matrix pattern");
+    MP_CUDA(cudaMemcpyAsync(d_rowptr, p->d_rowptr, sizeof(int32_t) * (p->nrow + 1), cudaMemcpyDeviceToDevice, ctx->stream));
+    MP_CUDA(cudaMemcpyAsync(d_colidx, p->d_colidx, sizeof(int32_t) * (size_t)p->nnz, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+
+extern "C" int mp_scatter_matrix(mp_ctx *ctx, const mp_plan *p, const double *d_elem_mat, double *d_vals) {
+    MP_CHECK(ctx && p && p->lc > 0 && d_elem_mat && d_vals, "mp_scatter_matrix: bad argument");
+    if (p->nnz == 0) return 0;
+    size_t smem = sizeof(double) * (size_t)p->smem_doubles;
+    unsigned grid = (unsigned)cdiv(p->nrow, p->rows_per_block);
+    const int kThreadsRt = p->rows_per_block >= kThreads ? kThreads : ((p->rows_per_block + 31) / 32) * 32;
+    if (p->lc == 4) {
+        MP_CUDA(cudaFuncSetAttribute(k_scatter_matrix<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_scatter_matrix<4><<<grid, kThreadsRt, smem, ctx->stream>>>(p->d_rowptr, p->d_inc_ptr, p->d_inc, p->d_slot, d_elem_mat,
+                                                                    d_vals, (int32_t)p->nrow, p->rows_per_block, p->lc);
+    } else {
+        MP_CUDA(cudaFuncSetAttribute(k_scatter_matrix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_scatter_matrix<0><<<grid, kThreadsRt, smem, ctx->stream>>>(p->d_rowptr, p->d_inc_ptr, p->d_inc, p->d_slot, d_elem_mat,
+                                                                    d_vals, (int32_t)p->nrow, p->rows_per_block, p->lc);
+    }
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp_scatter_vector(mp_ctx *ctx, const mp_plan *p, const double *d_elem_vec, double beta, double *d_out) {
+    MP_CHECK(ctx && p && d_elem_vec && d_out, "mp_scatter_vector: bad argument");
+    k_scatter_vector<<<(unsigned)cdiv(p->nrow, kThreads), kThreads, 0, ctx->stream>>>(p->d_inc_ptr, p->d_inc, d_elem_vec, beta,
+                                                                                       d_out, (int32_t)p->nrow);
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}

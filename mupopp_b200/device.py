@@ -1,0 +1,227 @@
+"""Thin object layer over the C-ABI: context, device mesh, scatter plans, CSR operators, solvers.
+
+torch owns every device buffer; the numerics are the hand-written sm_100a kernels of
+libmupopp_b200.so.  Nothing here computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MpCsr, MpMesh, MpSolveInfo, MpTransportParams, check, ptr
+
+
+class Context:
+    """One CUDA device + stream (+ optional NCCL communicator)."""
+
+    def __init__(self, device=0, use_torch_stream=True):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.MpError("mupopp_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream if use_torch_stream else None
+        h = C.c_void_p()
+        check(self.lib.mp_ctx_create(device, C.c_void_p(stream) if stream else None, C.byref(h)), "mp_ctx_create")
+        self.h = h
+        self.nranks, self.rank = 1, 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        check(self.lib.mp_ctx_sync(self.h), "mp_ctx_sync")
+
+    def launch_count(self):
+        return int(self.lib.mp_ctx_launch_count(self.h))
+
+    # ---- tensors
+    def zeros(self, n, dtype=torch.float64):
+        return torch.zeros(int(n), dtype=dtype, device=self.device)
+
+    def empty(self, n, dtype=torch.float64):
+        return torch.empty(int(n), dtype=dtype, device=self.device)
+
+    def to_device(self, a, dtype=None):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dtype is not None:
+            t = t.to(dtype)
+        return t.to(self.device)
+
+    # ---- multi-GPU
+    def init_comm(self, nranks, rank, unique_id: bytes):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(self.lib.mp_comm_init(self.h, nranks, rank, buf), "mp_comm_init")
+        self.nranks, self.rank = nranks, rank
+
+    def unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        check(self.lib.mp_nccl_unique_id(buf), "mp_nccl_unique_id")
+        return bytes(buf)
+
+    # ---- BLAS-1
+    def dot(self, x, y):
+        r = C.c_double()
+        check(self.lib.mp_dot(self.h, x.numel(), ptr(x), ptr(y), C.byref(r)), "mp_dot")
+        return r.value
+
+    def axpby(self, a, x, b, y):
+        check(self.lib.mp_axpby(self.h, y.numel(), a, ptr(x), b, ptr(y)), "mp_axpby")
+
+
+class DeviceMesh:
+    def __init__(self, ctx: Context, mesh):
+        self.ctx = ctx
+        self.host = mesh
+        self.dim = mesh.dim
+        self.ncell = mesh.num_cells()
+        self.nvert = mesh.num_vertices()
+        self.cells = ctx.to_device(mesh.cells, torch.int32)
+        self.coords = ctx.to_device(mesh.coords, torch.float64)
+        self.c = MpMesh(self.dim, self.ncell, self.nvert, self.cells.data_ptr(), self.coords.data_ptr())
+
+
+class Plan:
+    """Scatter plan for one (row dofmap, column dofmap) pair; see include/mupopp_b200.h."""
+
+    def __init__(self, ctx: Context, row_dofs, col_dofs, nrow, ncol):
+        self.ctx = ctx
+        self.row_dofs = row_dofs            # keep alive
+        self.col_dofs = col_dofs
+        ncell, self.lr = row_dofs.shape
+        self.lc = col_dofs.shape[1] if col_dofs is not None else 0
+        self.ncell, self.nrow, self.ncol = ncell, int(nrow), int(ncol)
+        h = C.c_void_p()
+        check(ctx.lib.mp_plan_create(ctx.h, ptr(row_dofs), self.lr, ptr(col_dofs), self.lc, ncell, nrow, ncol, C.byref(h)),
+              "mp_plan_create")
+        self.h = h
+        self.nnz = int(ctx.lib.mp_plan_nnz(h)) if self.lc else 0
+        self._csr = None
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.lib.mp_plan_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def csr_pattern(self):
+        if self._csr is None:
+            rowptr = self.ctx.empty(self.nrow + 1, torch.int32)
+            colidx = self.ctx.empty(max(self.nnz, 1), torch.int32)
+            check(self.ctx.lib.mp_plan_export_csr(self.ctx.h, self.h, ptr(rowptr), ptr(colidx)), "mp_plan_export_csr")
+            self._csr = (rowptr, colidx[: self.nnz])
+        return self._csr
+
+    def new_matrix(self):
+        rowptr, colidx = self.csr_pattern()
+        return CsrMatrix(self.ctx, self.nrow, self.ncol, rowptr, colidx, self.ctx.zeros(self.nnz))
+
+    def scatter_matrix(self, elem_mat, A):
+        check(self.ctx.lib.mp_scatter_matrix(self.ctx.h, self.h, ptr(elem_mat), ptr(A.vals)), "mp_scatter_matrix")
+
+    def scatter_vector(self, elem_vec, out, beta=0.0):
+        check(self.ctx.lib.mp_scatter_vector(self.ctx.h, self.h, ptr(elem_vec), beta, ptr(out)), "mp_scatter_vector")
+
+
+class CsrMatrix:
+    def __init__(self, ctx, nrow, ncol, rowptr, colidx, vals):
+        self.ctx = ctx
+        self.nrow, self.ncol = int(nrow), int(ncol)
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.nnz = int(vals.numel())
+        self.c = MpCsr(self.nrow, self.ncol, self.nnz, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr())
+        self.dinv = None
+
+    def spmv(self, x, y):
+        check(self.ctx.lib.mp_spmv(self.ctx.h, C.byref(self.c), ptr(x), ptr(y)), "mp_spmv")
+        return y
+
+    def jacobi_setup(self):
+        if self.dinv is None:
+            self.dinv = self.ctx.empty(self.nrow)
+        check(self.ctx.lib.mp_jacobi_setup(self.ctx.h, C.byref(self.c), ptr(self.dinv)), "mp_jacobi_setup")
+        return self.dinv
+
+    def apply_dirichlet(self, rhs, isbc, g, matrix=True):
+        check(self.ctx.lib.mp_apply_dirichlet_sym(self.ctx.h, self.nrow, ptr(self.rowptr), ptr(self.colidx),
+                                                  ptr(self.vals) if matrix else None, ptr(rhs), ptr(isbc), ptr(g)),
+              "mp_apply_dirichlet_sym")
+
+    def to_scipy(self):
+        """Test helper: copy to host as scipy CSR."""
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.vals.cpu().numpy(), self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
+                             shape=(self.nrow, self.ncol))
+
+    def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True):
+        if self.dinv is None or refresh_jacobi:
+            self.jacobi_setup()
+        info = MpSolveInfo(rtol, atol, int(maxit), int(check_every), 0, 0, 0.0)
+        fn = {"pcg": self.ctx.lib.mp_solve_pcg, "cg": self.ctx.lib.mp_solve_pcg,
+              "bicgstab": self.ctx.lib.mp_solve_bicgstab}[method]
+        check(fn(self.ctx.h, C.byref(self.c), ptr(self.dinv), ptr(b), ptr(x), halo.h if halo is not None else None, C.byref(info)),
+              "mp_solve_" + method)
+        return SolveResult(info.niter, bool(info.converged), info.relres)
+
+
+class SolveResult:
+    def __init__(self, niter, converged, relres):
+        self.niter, self.converged, self.relres = niter, converged, relres
+
+    def __repr__(self):
+        return "SolveResult(niter=%d, converged=%s, relres=%.3e)" % (self.niter, self.converged, self.relres)
+
+
+class Halo:
+    """Ghost-dof exchange plan (NCCL send/recv).  Ghost entries are contiguous per neighbour."""
+
+    def __init__(self, ctx: Context, neigh_rank, send_lists, recv_start, recv_count):
+        self.ctx = ctx
+        n = len(neigh_rank)
+        send_off = np.zeros(n + 1, dtype=np.int32)
+        for k, s in enumerate(send_lists):
+            send_off[k + 1] = send_off[k] + len(s)
+        send_idx = np.concatenate(send_lists).astype(np.int32) if n and send_off[-1] > 0 else np.zeros(1, dtype=np.int32)
+        self.d_send_idx = ctx.to_device(send_idx, torch.int32)
+        arr = lambda a: (C.c_int32 * max(len(a), 1))(*[int(v) for v in a])
+        h = C.c_void_p()
+        check(ctx.lib.mp_halo_create(ctx.h, n, arr(neigh_rank), arr(send_off), ptr(self.d_send_idx), arr(recv_start),
+                                     arr(recv_count), C.byref(h)), "mp_halo_create")
+        self.h = h
+
+    def exchange(self, x):
+        check(self.ctx.lib.mp_halo_exchange(self.ctx.h, self.h, ptr(x)), "mp_halo_exchange")
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.ctx.lib.mp_halo_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def transport_params(Pe, Da, phi, alpha, dt, sigma, rho0, gamma, fracs, zhat, K, reaction, ncomp, supg):
+    p = MpTransportParams()
+    p.Pe, p.Da, p.phi, p.beta, p.dt = float(Pe), float(Da), float(phi), float(alpha) / float(phi), float(dt)
+    p.sigma, p.rho0, p.gamma = float(sigma), float(rho0), float(gamma)
+    for i in range(3):
+        p.frac[i] = float(fracs[i])
+        p.zhat[i] = float(zhat[i]) if i < len(zhat) else 0.0
+    p.Kconst = float(K) if np.isscalar(K) else 0.0
+    p.reaction = {"c0c1": 0, "c0c1sq": 1}[reaction]
+    p.ncomp, p.supg, p.pad = int(ncomp), int(supg), 0
+    return p

@@ -1,0 +1,216 @@
+"""Host-side meshes with DOLFIN 2017.1 conventions (vertex/cell numbering, UFC cell ordering).
+
+Replaces `UnitSquareMesh/RectangleMesh/BoxMesh` as used by the reference run scripts
+(e.g. /root/reference/src/run/LVL_3D/LVL_RII3D.py:136-142,
+/root/reference/src/benchmark/time_marching/time_test1.py:45-58).  `mshr.generate_mesh`
+(CGAL) is replaced by these structured generators for the BASELINE configs.
+Mesh construction is one-time setup on the host; everything per timestep runs on the GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TRI_EDGES = np.array([[1, 2], [0, 2], [0, 1]], dtype=np.int64)                       # UFC: edge k opposite vertex k
+TET_EDGES = np.array([[2, 3], [1, 3], [1, 2], [0, 3], [0, 2], [0, 1]], dtype=np.int64)
+
+
+class Mesh:
+    """Simplicial mesh: coords (V,d) float64, cells (C,d+1) int32 with ascending vertex ids per cell."""
+
+    def __init__(self, coords, cells):
+        self.coords = np.ascontiguousarray(coords, dtype=np.float64)
+        self.cells = np.ascontiguousarray(cells, dtype=np.int32)
+        self._edges = None
+        self._cell_edges = None
+        self._bfacets = None
+        self.box = None
+
+    # -- DOLFIN-like accessors -------------------------------------------------
+    def coordinates(self):
+        return self.coords
+
+    def num_vertices(self):
+        return self.coords.shape[0]
+
+    def num_cells(self):
+        return self.cells.shape[0]
+
+    def geometric_dimension(self):
+        return self.coords.shape[1]
+
+    @property
+    def dim(self):
+        return self.coords.shape[1]
+
+    def ufl_cell(self):
+        return "triangle" if self.dim == 2 else "tetrahedron"
+
+    def cell_diameters(self):
+        le = TRI_EDGES if self.dim == 2 else TET_EDGES
+        x = self.coords[self.cells]
+        d = x[:, le[:, 0]] - x[:, le[:, 1]]
+        return np.sqrt((d * d).sum(-1)).max(1)
+
+    def hmax(self):
+        return float(self.cell_diameters().max())
+
+    def hmin(self):
+        return float(self.cell_diameters().min())
+
+    # -- edges (needed by P2 spaces) --------------------------------------------
+    def init_edges(self):
+        """Edge ids in first-seen order over (cell, UFC local edge): the un-reordered DOLFIN numbering
+        recorded in /root/reference/src/run/fenics_demo/dolfin_fine_velocity.xml.gz."""
+        if self._edges is not None:
+            return
+        le = TRI_EDGES if self.dim == 2 else TET_EDGES
+        nv = self.num_vertices()
+        ev = self.cells[:, le].astype(np.int64)
+        keys = (ev[..., 0] * nv + ev[..., 1]).ravel()
+        uniq, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        rank = np.empty(order.size, dtype=np.int64)
+        rank[order] = np.arange(order.size)
+        self._cell_edges = rank[inv].reshape(ev.shape[:2]).astype(np.int32)
+        u = uniq[order]
+        self._edges = np.stack([u // nv, u % nv], 1).astype(np.int32)
+
+    @property
+    def edges(self):
+        self.init_edges()
+        return self._edges
+
+    @property
+    def cell_edges(self):
+        self.init_edges()
+        return self._cell_edges
+
+    def num_edges(self):
+        return self.edges.shape[0]
+
+    # -- boundary facets -----------------------------------------------------------
+    def boundary_facets(self):
+        """(facet vertices (F,d), outward unit normals (F,d), measures (F,), owning cell (F,)).
+        A boundary facet belongs to exactly one cell; order = ascending (local facet, cell)."""
+        if self._bfacets is not None:
+            return self._bfacets
+        d = self.dim
+        nv = self.num_vertices()
+        fv, owner, opp = [], [], []
+        if getattr(self, "box", None) is not None:
+            # axis-aligned box domain: a facet is on the boundary iff all its vertices share a bounding plane
+            lo, hi = self.box
+            tol = 1e-12 * max(1.0, float(np.max(np.abs(hi - lo))))
+            mask = np.zeros(nv, dtype=np.uint8)
+            for a in range(d):
+                mask |= (np.abs(self.coords[:, a] - lo[a]) <= tol).astype(np.uint8) << np.uint8(2 * a)
+                mask |= (np.abs(self.coords[:, a] - hi[a]) <= tol).astype(np.uint8) << np.uint8(2 * a + 1)
+            cm = mask[self.cells]
+            for k in range(d + 1):
+                loc = [j for j in range(d + 1) if j != k]
+                m = cm[:, loc[0]]
+                for j in loc[1:]:
+                    m = m & cm[:, j]
+                sel = np.nonzero(m)[0]
+                fv.append(self.cells[sel][:, loc].astype(np.int64))
+                owner.append(sel)
+                opp.append(self.cells[sel, k].astype(np.int64))
+            fv, owner, opp = np.concatenate(fv), np.concatenate(owner), np.concatenate(opp)
+        else:
+            cells = self.cells.astype(np.int64)
+            for k in range(d + 1):
+                loc = [j for j in range(d + 1) if j != k]
+                fv.append(cells[:, loc])
+                owner.append(np.arange(cells.shape[0]))
+                opp.append(cells[:, k])
+            fv = np.concatenate(fv)
+            owner = np.concatenate(owner)
+            opp = np.concatenate(opp)
+            key = fv[:, 0].copy()
+            for j in range(1, d):
+                key = key * nv + fv[:, j]
+            _, idx, cnt = np.unique(key, return_index=True, return_counts=True)
+            sel = np.sort(idx[cnt == 1])
+            fv, owner, opp = fv[sel], owner[sel], opp[sel]
+        x = self.coords[fv]
+        if d == 2:
+            t = x[:, 1] - x[:, 0]
+            n = np.stack([t[:, 1], -t[:, 0]], 1)
+            meas = np.linalg.norm(t, axis=1)
+        else:
+            n = np.cross(x[:, 1] - x[:, 0], x[:, 2] - x[:, 0])
+            meas = 0.5 * np.linalg.norm(n, axis=1)
+        n = n / np.linalg.norm(n, axis=1, keepdims=True)
+        flip = ((x[:, 0] - self.coords[opp]) * n).sum(1) < 0
+        n[flip] *= -1.0
+        self._bfacets = (fv, n, meas, owner)
+        return self._bfacets
+
+
+def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
+    """DOLFIN RectangleMesh(Point, Point, nx, ny): vertex id iy*(nx+1)+ix, 'right' diagonals."""
+    if diagonal != "right":
+        raise NotImplementedError("only diagonal='right' (the DOLFIN default) is implemented")
+    x0, y0 = float(p0[0]), float(p0[1])
+    x1, y1 = float(p1[0]), float(p1[1])
+    xs = np.linspace(x0, x1, nx + 1)
+    ys = np.linspace(y0, y1, ny + 1)
+    coords = np.empty(((nx + 1) * (ny + 1), 2))
+    coords[:, 0] = np.tile(xs, ny + 1)
+    coords[:, 1] = np.repeat(ys, nx + 1)
+    ix = np.tile(np.arange(nx, dtype=np.int64), ny)
+    iy = np.repeat(np.arange(ny, dtype=np.int64), nx)
+    v0 = iy * (nx + 1) + ix
+    v1, v2 = v0 + 1, v0 + nx + 1
+    v3 = v2 + 1
+    cells = np.empty((2 * nx * ny, 3), dtype=np.int64)
+    cells[0::2] = np.stack([v0, v1, v3], 1)
+    cells[1::2] = np.stack([v0, v2, v3], 1)
+    m = Mesh(coords, cells)
+    m.box = (np.array([x0, y0]), np.array([x1, y1]))
+    m.grid = (nx, ny)
+    return m
+
+
+def UnitSquareMesh(nx, ny, diagonal="right"):
+    return RectangleMesh((0.0, 0.0), (1.0, 1.0), nx, ny, diagonal)
+
+
+def BoxMesh(p0, p1, nx, ny, nz, z_range=None):
+    """DOLFIN BoxMesh(Point, Point, nx, ny, nz): vertex id iz*(ny+1)*(nx+1)+iy*(nx+1)+ix; each hex is cut
+    into 6 tetrahedra around the body diagonal v0-v7.
+    `z_range=(k0, k1)` builds only the hex layers k0..k1-1 (a z-slab for one GPU of a partitioned run);
+    vertex ids are then local to the slab (plane k0 first), cells keep the global order."""
+    k0, k1 = (0, nz) if z_range is None else z_range
+    xs = np.linspace(float(p0[0]), float(p1[0]), nx + 1)
+    ys = np.linspace(float(p0[1]), float(p1[1]), ny + 1)
+    zs = np.linspace(float(p0[2]), float(p1[2]), nz + 1)[k0:k1 + 1]
+    nzl = k1 - k0
+    npl = (nx + 1) * (ny + 1)
+    coords = np.empty((npl * (nzl + 1), 3))
+    coords[:, 0] = np.tile(xs, (ny + 1) * (nzl + 1))
+    coords[:, 1] = np.tile(np.repeat(ys, nx + 1), nzl + 1)
+    coords[:, 2] = np.repeat(zs, npl)
+    ix = np.tile(np.arange(nx, dtype=np.int64), ny * nzl)
+    iy = np.tile(np.repeat(np.arange(ny, dtype=np.int64), nx), nzl)
+    iz = np.repeat(np.arange(nzl, dtype=np.int64), nx * ny)
+    v0 = iz * npl + iy * (nx + 1) + ix
+    v1 = v0 + 1
+    v2 = v0 + (nx + 1)
+    v3 = v2 + 1
+    v4, v5, v6, v7 = v0 + npl, v1 + npl, v2 + npl, v3 + npl
+    cells = np.empty((6 * nx * ny * nzl, 4), dtype=np.int32)
+    # rows are written already in ascending vertex order (UFC), cf. DOLFIN BoxMesh.cpp tetrahedra
+    for k, t in enumerate([(v0, v1, v3, v7), (v0, v1, v5, v7), (v0, v4, v5, v7),
+                           (v0, v2, v3, v7), (v0, v4, v6, v7), (v0, v2, v6, v7)]):
+        cells[k::6, 0], cells[k::6, 1], cells[k::6, 2], cells[k::6, 3] = t
+    m = Mesh(coords, cells)
+    if z_range is None:
+        m.box = (np.array([float(p0[0]), float(p0[1]), float(p0[2])]), np.array([float(p1[0]), float(p1[1]), float(p1[2])]))
+    m.grid = (nx, ny, nz)
+    m.z_range = (k0, k1)
+    return m
+
+
+def UnitCubeMesh(nx, ny, nz):
+    return BoxMesh((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), nx, ny, nz)

@@ -1,0 +1,228 @@
+"""Mode-F timestep driver: the segregated DarcyAdvection / CCS step on P1 fields, all numerics on the GPU.
+
+One step = the block-triangular sequence that is algebraically what the reference's monolithic
+`solve(a==L, sol, bc)` does (/root/reference/src/run/CCS2D/CCS_3comp.py:257-263):
+    1. c1, c2 consistent-mass solves (Jacobi-PCG)         mupopp.py:826, :936-937, :1234-1235
+    2. c0 Crank-Nicolson + SUPG ADR solve (Jacobi-BiCGStab) with the lagged velocity   mupopp.py:823-848
+    3. pressure solve div(k grad p) (Jacobi-PCG), warm-started from p^n
+    4. fused cellwise velocity recovery u = -(K/phi)(grad p + sigma rho zhat)
+Mode F is the primal P1 form named by BASELINE.json's north_star (DG0 velocity), see DESIGN.md.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from ._lib import check, ptr
+from .device import Context, DeviceMesh, Plan, transport_params
+
+
+@dataclass
+class TransportModel:
+    """Physical parameters of the monolithic DarcyAdvection / CCS forms (names follow mupopp.py)."""
+    Pe: float = 100.0
+    Da: float = 10.0
+    phi: float = 0.01
+    alpha: float = 0.005
+    dt: float = 0.01
+    K: object = 1.0                  # float or P1 nodal array
+    sigma: float = -1.0              # -1: DarcyAdvection (mupopp.py:807), +1: CCS (mupopp.py:1204)
+    rho0: float = 1.0
+    gamma: float = 1.0
+    reaction: str = "c0c1sq"
+    fracs: tuple = (0.75, 1.0, 0.0)
+    ncomp: int = 2
+    SUPG: int = 1
+    zhat: tuple = (0.0, 1.0)
+
+    @staticmethod
+    def darcy_two_component(Pe=100, Da=10.0, phi=0.01, alpha=0.005, dt=1e-2, K=1.0, zh=(0.0, 1.0), SUPG=1, gam_rho=-1.0, rho_0=1.0):
+        fac = (24.0 + 12.0 + 3.0 * 16.0) / 2.0 / 56.0                        # mupopp.py:820
+        return TransportModel(Pe, Da, phi, alpha, dt, K, -1.0, rho_0, -gam_rho, "c0c1sq", (fac, 1.0, 0.0), 2, SUPG, tuple(zh))
+
+    @staticmethod
+    def darcy_three_component(Pe=100, Da=10.0, phi=0.01, alpha=0.005, dt=1e-2, K=1.0, zh=(0.0, 1.0), SUPG=1, gam_rho=-1.0, rho_0=1.0):
+        T = 392.32                                                           # mupopp.py:925-931
+        return TransportModel(Pe, Da, phi, alpha, dt, K, -1.0, rho_0, -gam_rho, "c0c1sq", (84.0 / T, 112.0 / T, 12.0 / T), 3, SUPG, tuple(zh))
+
+    @staticmethod
+    def ccs_three_component(Pe=100, Da=10.0, phi=0.01, alpha=0.005, dt=1e-2, K=1.0, zh=(0.0, 1.0), SUPG=1, gam_rho=1.0):
+        T = 698.0                                                            # mupopp.py:1217-1229
+        return TransportModel(Pe, Da, phi, alpha, dt, K, 1.0, 1.0, gam_rho, "c0c1", (62.0 / T, 278.0 / T, 100.0 / T), 3, SUPG, tuple(zh))
+
+
+@dataclass
+class BoundaryDataF:
+    p_isbc: np.ndarray            # (V,) uint8: p = 0 (natural boundary of the mixed form)
+    flux_load: np.ndarray         # (V,) int_{Gamma_u} (u_D.n) q_i ds
+    c0_isbc: np.ndarray
+    c0_g: np.ndarray
+
+
+def _eval_marker(marker, x):
+    """marker: callable on an (N,d) array returning a bool array, or a pointwise callable x->bool."""
+    try:
+        r = np.asarray(marker(x))
+        if r.shape == (x.shape[0],):
+            return r.astype(bool)
+    except Exception:
+        pass
+    return np.array([bool(marker(p)) for p in x])
+
+
+def _eval_value(value, x, ncomp):
+    if callable(value):
+        try:
+            r = np.asarray(value(x), dtype=float)
+            if r.shape == (x.shape[0], ncomp) or (ncomp == 1 and r.shape == (x.shape[0],)):
+                return r.reshape(x.shape[0], ncomp)
+        except Exception:
+            pass
+        return np.array([np.atleast_1d(np.asarray(value(p), dtype=float)) for p in x]).reshape(x.shape[0], ncomp)
+    return np.broadcast_to(np.atleast_1d(np.asarray(value, dtype=float)), (x.shape[0], ncomp)).copy()
+
+
+def make_boundary_data(mesh, u_marker, u_value, c0_marker=None, c0_value=0.0):
+    """Host setup of the Dirichlet/Neumann data (DOLFIN 'topological' facet marking: a facet is on Gamma_u if
+    all its vertices and its midpoint satisfy the marker).  One-time; not part of the timestep."""
+    fv, n, meas, _ = mesh.boundary_facets()
+    d = mesh.dim
+    V = mesh.num_vertices()
+    bverts = np.unique(fv.ravel())
+    vin = np.zeros(V, dtype=bool)
+    vin[bverts] = _eval_marker(u_marker, mesh.coords[bverts])
+    inside = vin[fv].all(1)
+    if inside.any():
+        idx = np.nonzero(inside)[0]
+        inside[idx] &= _eval_marker(u_marker, mesh.coords[fv[idx]].mean(1))
+    flux = np.zeros(V)
+    idx = np.nonzero(inside)[0]
+    if idx.size:
+        mloc = (np.ones((d, d)) + np.eye(d)) / (d * (d + 1))
+        xf = mesh.coords[fv[idx]].reshape(-1, d)
+        uD = _eval_value(u_value, xf, d).reshape(idx.size, d, d)                  # (F, vertex, comp)
+        g = np.einsum("fvc,fc->fv", uD, n[idx])
+        contrib = meas[idx][:, None] * (g @ mloc.T)
+        np.add.at(flux, fv[idx].ravel(), contrib.ravel())
+    p_isbc = np.zeros(V, dtype=np.uint8)
+    p_isbc[np.unique(fv[~inside].ravel())] = 1
+    c0_isbc = np.zeros(V, dtype=np.uint8)
+    c0_g = np.zeros(V)
+    if c0_marker is not None:
+        sel = bverts[_eval_marker(c0_marker, mesh.coords[bverts])]
+        c0_isbc[sel] = 1
+        c0_g[sel] = _eval_value(c0_value, mesh.coords[sel], 1)[:, 0]
+    return BoundaryDataF(p_isbc, flux, c0_isbc, c0_g)
+
+
+class TransportSolverF:
+    """GPU state + operators of one mode-F problem.  Fields are torch fp64 tensors on the device."""
+
+    def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
+                 rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None):
+        self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
+        self.halo = halo
+        self.dm = DeviceMesh(ctx, mesh)
+        V, Cn, d = self.dm.nvert, self.dm.ncell, self.dm.dim
+        self.nloc = V
+        self.nown = V if n_owned is None else int(n_owned)
+        self.K_dev = None if np.isscalar(model.K) else ctx.to_device(np.asarray(model.K, dtype=np.float64))
+        self.prm = transport_params(model.Pe, model.Da, model.phi, model.alpha, model.dt, model.sigma, model.rho0, model.gamma,
+                                    model.fracs, model.zhat, model.K, model.reaction, model.ncomp, model.SUPG)
+        # row dofmap: rows of ghost vertices (>= nown) are not assembled (owner-computes)
+        rows = self.dm.cells
+        if self.nown < V:
+            rows = torch.where(self.dm.cells < self.nown, self.dm.cells, torch.full_like(self.dm.cells, -1))
+        self.plan = Plan(ctx, rows, self.dm.cells, self.nown, V)
+        l = d + 1
+        self.emat = ctx.empty(Cn * l * l)
+        self.evec = ctx.empty(Cn * l)
+        self.evec2 = ctx.empty(Cn * l)
+        # constant operators
+        self.M = self.plan.new_matrix()
+        check(ctx.lib.mp_elem_p1_mass(ctx.h, C.byref(self.dm.c), 1.0, ptr(self.emat)), "mp_elem_p1_mass")
+        self.plan.scatter_matrix(self.emat, self.M)
+        self.M.jacobi_setup()
+        self.p_isbc = ctx.to_device(bdata.p_isbc, torch.uint8)
+        self.c0_isbc = ctx.to_device(bdata.c0_isbc, torch.uint8)
+        self.c0_g = ctx.to_device(bdata.c0_g)
+        self.flux_load = ctx.to_device(bdata.flux_load)
+        self.zeros_loc = ctx.zeros(V)
+        self.L = self.plan.new_matrix()
+        check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(self.dm.c), ptr(self.K_dev), self.prm.Kconst, 1.0 / model.phi,
+                                           ptr(self.emat)), "mp_elem_p1_stiffness")
+        self.plan.scatter_matrix(self.emat, self.L)
+        self.L.apply_dirichlet(None, self.p_isbc, self.zeros_loc)          # p = 0: homogeneous, matrix eliminated once
+        self.L.jacobi_setup()
+        self.A = self.plan.new_matrix()
+        # state
+        self.u = ctx.zeros(Cn * d)
+        self.p = ctx.zeros(V)
+        self.c0 = ctx.zeros(V)
+        self.c1 = ctx.zeros(V)
+        self.c2 = ctx.zeros(V)
+        self.c0_new = ctx.zeros(V)
+        self.c1_new = ctx.zeros(V)
+        self.c2_new = ctx.zeros(V)
+        self.rhs = ctx.zeros(self.nown)
+        self.rhs2 = ctx.zeros(self.nown)
+        self.fsrc = ctx.zeros(V) if f_source is None else ctx.to_device(np.asarray(f_source, dtype=np.float64))
+        self.last = {}
+
+    def set_state(self, c0=None, c1=None, c2=None, p=None, u=None):
+        for name, v in (("c0", c0), ("c1", c1), ("c2", c2), ("p", p), ("u", u)):
+            if v is not None:
+                getattr(self, name).copy_(self.ctx.to_device(np.asarray(v, dtype=np.float64).ravel()))
+
+    def _exchange(self, x):
+        if self.halo is not None:
+            self.halo.exchange(x)
+
+    def step(self):
+        ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
+        three = self.model.ncomp == 3
+        kw = dict(rtol=self.rtol, maxit=self.maxit, halo=self.halo, check_every=self.check_every, refresh_jacobi=False)
+        # 1. c1 (, c2): consistent-mass solves with the reaction load
+        check(lib.mp_elem_p1_reaction_rhs(ctx.h, C.byref(m), C.byref(prm), ptr(self.c0), ptr(self.c1), ptr(self.c2) if three else None,
+                                          ptr(self.evec), ptr(self.evec2) if three else None), "mp_elem_p1_reaction_rhs")
+        self.plan.scatter_vector(self.evec, self.rhs)
+        self.c1_new.copy_(self.c1)
+        r1 = self.M.solve("pcg", self.rhs, self.c1_new, **kw)
+        self._exchange(self.c1_new)
+        r2 = None
+        if three:
+            self.plan.scatter_vector(self.evec2, self.rhs2)
+            self.c2_new.copy_(self.c2)
+            r2 = self.M.solve("pcg", self.rhs2, self.c2_new, **kw)
+            self._exchange(self.c2_new)
+        # 2. c0: CN + SUPG with the lagged velocity u^n
+        check(lib.mp_elem_p1_transport(ctx.h, C.byref(m), C.byref(prm), ptr(self.u), ptr(self.c0), ptr(self.c1),
+                                       ptr(self.c2) if three else None, ptr(self.c1_new), ptr(self.c2_new) if three else None,
+                                       ptr(self.fsrc), ptr(self.emat), ptr(self.evec)), "mp_elem_p1_transport")
+        self.plan.scatter_matrix(self.emat, self.A)
+        self.plan.scatter_vector(self.evec, self.rhs)
+        self.A.apply_dirichlet(self.rhs, self.c0_isbc, self.c0_g)
+        self.A.jacobi_setup()
+        self.c0_new.copy_(self.c0)
+        r0 = self.A.solve("bicgstab", self.rhs, self.c0_new, **kw)
+        self._exchange(self.c0_new)
+        # 3. pressure with the NEW c0, warm start from p^n
+        check(lib.mp_elem_p1_pressure_rhs(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.c0_new), ptr(self.evec)),
+              "mp_elem_p1_pressure_rhs")
+        self.plan.scatter_vector(self.evec, self.rhs)
+        ctx.axpby(-1.0, self.flux_load[: self.nown], 1.0, self.rhs)
+        self.L.apply_dirichlet(self.rhs, self.p_isbc, self.zeros_loc, matrix=False)
+        rp = self.L.solve("pcg", self.rhs, self.p, **kw)
+        self._exchange(self.p)
+        # 4. velocity recovery, then rotate the state
+        check(lib.mp_recover_velocity(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.p), ptr(self.c0_new), ptr(self.u)),
+              "mp_recover_velocity")
+        self.c0, self.c0_new = self.c0_new, self.c0
+        self.c1, self.c1_new = self.c1_new, self.c1
+        if three:
+            self.c2, self.c2_new = self.c2_new, self.c2
+        self.last = dict(c1=r1, c2=r2, c0=r0, p=rp)
+        return self.last

@@ -1,0 +1,154 @@
+"""GPU parity (through the C-ABI) of the mode-F hot path against the NumPy/SciPy oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import fem, forms, modef
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def _mesh_pair(dim, n):
+    import mupopp_b200 as mp
+    if dim == 2:
+        return mp.RectangleMesh((0, 0), (2, 1), n, n), fem.rectangle_mesh(0, 0, 2, 1, n, n)
+    return mp.BoxMesh((0, 0, 0), (2, 2, 1), n, n, n), fem.box_mesh((0, 0, 0), (2, 2, 1), n, n, n)
+
+
+@pytest.mark.parametrize("dim,n", [(2, 12), (3, 6)])
+def test_mesh_and_pattern_bit_exact(ctx, dim, n):
+    from mupopp_b200.device import DeviceMesh, Plan
+    pm, om = _mesh_pair(dim, n)
+    assert np.array_equal(pm.cells, om.cells)
+    assert np.array_equal(pm.coords, om.coords)
+    dm = DeviceMesh(ctx, pm)
+    plan = Plan(ctx, dm.cells, dm.cells, dm.nvert, dm.nvert)
+    rowptr, colidx = plan.csr_pattern()
+    rp, ci = fem.p1_csr_pattern(om)
+    assert np.array_equal(rowptr.cpu().numpy(), rp)
+    assert np.array_equal(colidx.cpu().numpy(), ci)
+
+
+@pytest.mark.parametrize("dim,n", [(2, 10), (3, 5)])
+def test_constant_operators(ctx, dim, n):
+    import ctypes as C
+    from mupopp_b200._lib import check, ptr
+    from mupopp_b200.device import DeviceMesh, Plan
+    pm, om = _mesh_pair(dim, n)
+    asm = forms.Assembler(om)
+    dm = DeviceMesh(ctx, pm)
+    plan = Plan(ctx, dm.cells, dm.cells, dm.nvert, dm.nvert)
+    l = dim + 1
+    emat = ctx.empty(dm.ncell * l * l)
+    M = plan.new_matrix()
+    check(ctx.lib.mp_elem_p1_mass(ctx.h, C.byref(dm.c), 1.0, ptr(emat)))
+    plan.scatter_matrix(emat, M)
+    Mo = asm.mass(1, 1, 2)
+    assert abs(M.to_scipy() - Mo).max() <= 1e-15 * abs(Mo).max() * 10
+    rng = np.random.default_rng(1)
+    K = 0.5 + rng.random(om.nv)
+    Kd = ctx.to_device(K)
+    L = plan.new_matrix()
+    check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(dm.c), ptr(Kd), 0.0, 2.0, ptr(emat)))
+    plan.scatter_matrix(emat, L)
+    # oracle stiffness with the cellwise (mean nodal) coefficient
+    g = modef.p1_grads(asm)
+    vol = asm.detJ / (2.0 if dim == 2 else 6.0)
+    Ae = np.einsum("c,cia,cja->cij", 2.0 * vol * modef.cell_K(asm, K), g, g)
+    Lo = fem.scatter_matrix(Ae, asm.P1.cell_dofs, asm.P1.cell_dofs, (om.nv, om.nv))
+    assert abs(L.to_scipy() - Lo).max() <= 1e-13 * abs(Lo).max()
+    # SpMV + dot + axpby
+    x = rng.standard_normal(om.nv)
+    xd = ctx.to_device(x)
+    yd = ctx.empty(om.nv)
+    L.spmv(xd, yd)
+    assert rel(yd.cpu().numpy(), Lo @ x) < 1e-14
+    assert abs(ctx.dot(xd, yd) - x @ (Lo @ x)) <= 1e-12 * abs(x @ (Lo @ x))
+    ctx.axpby(2.0, xd, -1.0, yd)
+    assert rel(yd.cpu().numpy(), 2 * x - Lo @ x) < 1e-14
+
+
+def _setup(dim, n, kind):
+    import mupopp_b200 as mp
+    from mupopp_b200.transport import TransportModel, make_boundary_data
+    pm, om = _mesh_pair(dim, n)
+    zh = (0.0, 1.0) if dim == 2 else (0.0, 0.0, 1.0)
+    top = 1.0
+    if kind == "ccs3":
+        model = TransportModel.ccs_three_component(Pe=500, Da=0.1, phi=0.05, alpha=1e-3, dt=0.1, K=1.0, zh=zh)
+        oprm = forms.ccs_three_component_params(Pe=500, Da=0.1, phi=0.05, alpha=1e-3, dt=0.1, K=1.0, zhat=zh)
+    elif kind == "darcy2":
+        model = TransportModel.darcy_two_component(Pe=1e3, Da=10.0, phi=0.01, alpha=0.01, dt=0.1, K=0.1, zh=zh, gam_rho=-1.0, rho_0=0.0)
+        oprm = forms.darcy_two_component_params(Pe=1e3, Da=10.0, phi=0.01, alpha=0.01, dt=0.1, K=0.1, zhat=zh, gam_rho=-1.0, rho_0=0.0)
+    else:
+        rng = np.random.default_rng(5)
+        K = 0.5 + rng.random(om.nv)
+        model = TransportModel.darcy_three_component(Pe=200, Da=1.0, phi=0.2, alpha=0.01, dt=0.01, K=K, zh=zh, SUPG=2)
+        oprm = forms.darcy_three_component_params(Pe=200, Da=1.0, phi=0.2, alpha=0.01, dt=0.01, K=K, zhat=zh, SUPG=2)
+    uval = np.zeros(dim)
+    uval[-1] = -0.5
+    X = om.coords
+    f = np.abs(np.sin(3 * np.pi * X[:, 0])) * (1 - np.tanh((top - X[:, -1]) / 0.1))
+    bd = make_boundary_data(pm, lambda x: x[..., -1] > top - 1e-12, uval, lambda x: x[..., -1] > top - 1e-12, 0.1)
+    obc = modef.make_bcs(om, lambda x: x[-1] > top - 1e-12, lambda x: uval, lambda x: x[-1] > top - 1e-12, 0.1)
+    return pm, om, model, oprm, bd, obc, f
+
+
+@pytest.mark.parametrize("dim,n,kind", [(2, 12, "ccs3"), (3, 6, "ccs3"), (3, 5, "darcy2"), (2, 10, "darcy3"), (3, 5, "darcy3")])
+def test_modef_steps_match_oracle(ctx, dim, n, kind):
+    """Per solve <= 1e-10, after N steps <= 1e-8 relative L2 (BASELINE.json north_star tolerances)."""
+    from mupopp_b200.transport import TransportSolverF
+    pm, om, model, oprm, bd, obc, f = _setup(dim, n, kind)
+    assert np.array_equal(bd.p_isbc.nonzero()[0], obc.p_dofs)
+    assert np.allclose(bd.flux_load, obc.flux_load, rtol=0, atol=1e-15)
+    assert np.array_equal(bd.c0_isbc.nonzero()[0], obc.c0_dofs)
+    asm = forms.Assembler(om)
+    rng = np.random.default_rng(0)
+    c1_0 = 0.1 + 0.01 * rng.random(om.nv)
+    c2_0 = 0.01 * rng.random(om.nv)
+    c0_0 = 0.05 * rng.random(om.nv)
+    st = modef.StateF(u=np.zeros((om.nc, dim)), p=np.zeros(om.nv), c0=c0_0.copy(), c1=c1_0.copy(), c2=c2_0.copy())
+    s = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-13)
+    s.set_state(c0=c0_0, c1=c1_0, c2=c2_0)
+    nsteps = 4
+    for k in range(nsteps):
+        prev = st
+        st = modef.step(asm, oprm, st, f, obc)
+        # per-solve parity: restart the GPU from the oracle's previous state
+        s.set_state(c0=prev.c0, c1=prev.c1, c2=prev.c2 if prev.c2 is not None else None, p=prev.p, u=prev.u)
+        res = s.step()
+        assert all(r is None or r.converged for r in res.values()), res
+        tol = 1e-10
+        assert rel(s.c1.cpu().numpy(), st.c1) < tol
+        if model.ncomp == 3:
+            assert rel(s.c2.cpu().numpy(), st.c2) < tol
+        assert rel(s.c0.cpu().numpy(), st.c0) < tol
+        assert rel(s.p.cpu().numpy(), st.p) < tol
+        assert rel(s.u.cpu().numpy().reshape(-1, dim), st.u) < tol
+    # free-running N steps
+    s2 = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-13)
+    s2.set_state(c0=c0_0, c1=c1_0, c2=c2_0)
+    for k in range(nsteps):
+        s2.step()
+    assert rel(s2.c0.cpu().numpy(), st.c0) < 1e-8
+    assert rel(s2.p.cpu().numpy(), st.p) < 1e-8
+    assert rel(s2.c1.cpu().numpy(), st.c1) < 1e-8
+
+
+def test_determinism_bitwise(ctx):
+    """Assembly + solves are atomic-free: two runs give bit-identical fields."""
+    from mupopp_b200.transport import TransportSolverF
+    pm, om, model, oprm, bd, obc, f = _setup(3, 6, "ccs3")
+    outs = []
+    for rep in range(2):
+        s = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-12)
+        s.set_state(c1=0.1 * np.ones(om.nv))
+        for k in range(3):
+            s.step()
+        outs.append((s.c0.cpu().numpy().copy(), s.p.cpu().numpy().copy(), s.A.vals.cpu().numpy().copy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
