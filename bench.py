@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- Darcy-ADR timesteps/s at 8M dofs (BASELINE.json metric) on 1..8 B200.
+
+Workload (config.workload): CCS reactive 3-component transport (form a5, mupopp.py:1147-1262, physics of
+/root/reference/src/run/CCS2D/CCS_3comp.py:29-39 lifted to 3-D), mode F (P1 pressure operator + cellwise velocity
+recovery + P1 transport), BoxMesh [0,4]x[0,4]x[0,1] with n^3 hexes -> 6 n^3 tets, n = 200: 8 120 601 P1 dofs per field.
+One "step" = one full timestep: c1,c2 mass solves -> c0 SUPG-ADR assemble+solve -> pressure solve -> velocity recovery.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 200]
+
+N > 1 (torchrun, one rank per GPU): the SAME mesh is partitioned into z-slabs (strong scaling), NCCL halo
+exchange + allreduce inside the Krylov loops.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Darcy-ADR timesteps/s at 8M dofs"
+UNIT = "timesteps/s"
+PHYS = dict(Pe=500.0, Da=0.1, phi=0.05, alpha=1e-8, dt=0.1, K=1.0, gam_rho=1.0)   # CCS_3comp.py:29-39
+BOX = ((0.0, 0.0, 0.0), (4.0, 4.0, 1.0))
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def source_term(X, ztop=1.0):
+    """CCS_3comp.py:146-164 lifted to 3-D: sum_{ii<20} 0.1 |sin(ii pi x)| (1 - tanh((ztop - z)/0.01))."""
+    f = np.zeros(X.shape[0])
+    for ii in range(20):
+        f += 0.1 * np.abs(np.sin(ii * np.pi * X[:, 0]))
+    return f * (1.0 - np.tanh((ztop - X[:, 2]) / 0.01))
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------- reference arm
+def oracle_step_time(n, rtol, steps, warm):
+    """The oracle's mode-F timestep (NumPy assembly + SciPy cg/bicgstab with Jacobi) on an n^3 sample."""
+    from oracle import fem, forms, modef
+    m = fem.box_mesh(BOX[0], BOX[1], n, n, n)
+    asm = forms.Assembler(m)
+    prm = forms.ccs_three_component_params(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"], dt=PHYS["dt"],
+                                           K=PHYS["K"], zhat=(0.0, 0.0, 1.0), gam_rho=PHYS["gam_rho"])
+    top = lambda x: x[2] > 1.0 - 1e-12
+    bcs = modef.make_bcs(m, top, lambda x: np.array([0.0, 0.0, -0.5]), top, 0.1)
+    f = source_term(m.coords)
+    st = modef.StateF(u=np.zeros((m.nc, 3)), p=np.zeros(m.nv), c0=np.zeros(m.nv), c1=0.1 * np.ones(m.nv), c2=np.zeros(m.nv))
+    times, iters = [], []
+    for k in range(warm + steps):
+        info = {}
+        t0 = time.perf_counter()
+        st = modef.step(asm, prm, st, f, bcs, solver="krylov", rtol=rtol, info=info)
+        dt = time.perf_counter() - t0
+        if k >= warm:
+            times.append(dt)
+            iters.append(dict(info))
+        log("[oracle] n=%d step %d: %.2f s iters %s" % (n, k, dt, info))
+    return m.nv, times, iters
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    n = args.ref_n
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+    ndof, times, iters = oracle_step_time(n, args.rtol, args.steps, min(args.warmup, 1))
+    ms = 1e3 * float(np.mean(times))
+    ndof_full = (args.n + 1) ** 3
+    # scale the sample to the full workload linearly in dofs (optimistic for the CPU: Krylov iteration counts grow with n)
+    value = 1.0 / (np.mean(times) * ndof_full / ndof)
+    sample = ("oracle mode-F timestep (NumPy assembly + SciPy cg/bicgstab+Jacobi, rtol %g) on a %d^3 sample (%d dofs/field), "
+              "scaled to %d^3 linearly in dofs (iteration growth ignored: favours the CPU)" % (args.rtol, n, ndof, args.n))
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms * ndof_full / ndof, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": workload_config(args, 1),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                            "host_cores_available": cores, "sample_ms_per_step": ms, "sample_iters": iters[-1] if iters else None},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out), flush=True)
+    return 0
+
+
+def workload_config(args, nranks):
+    return {"workload": "CCS 3-component reactive transport (mupopp CCS.advection_diffusion_three_component), mode F, "
+                        "BoxMesh [0,4]x[0,4]x[0,1] %d^3 x 6 tets, P1, %d dofs/field" % (args.n, (args.n + 1) ** 3),
+            "n": args.n, "dofs_per_field": (args.n + 1) ** 3, "cells": 6 * args.n ** 3,
+            "physics": PHYS, "krylov_rtol": args.rtol, "c0_solver": args.c0_method, "preconditioner": "jacobi",
+            "partition": "z-slabs x%d" % nranks if nranks > 1 else "single GPU",
+            "l2_policy": "inputs larger than L2 (CSR operators 1.6 GB each at n=200 vs 126 MB L2)"}
+
+
+# ----------------------------------------------------------------------------------------------- B200 arm
+def build_problem(ctx, args, rank, nranks):
+    import mupopp_b200 as mp
+    from mupopp_b200.transport import TransportModel, TransportSolverF, make_boundary_data
+    from mupopp_b200 import partition
+    n = args.n
+    model = TransportModel.ccs_three_component(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"], dt=PHYS["dt"],
+                                               K=PHYS["K"], zh=(0.0, 0.0, 1.0), gam_rho=PHYS["gam_rho"])
+    top = lambda x: x[..., 2] > 1.0 - 1e-12
+    if nranks == 1:
+        mesh = mp.BoxMesh(BOX[0], BOX[1], n, n, n)
+        bd = make_boundary_data(mesh, top, (0.0, 0.0, -0.5), top, 0.1)
+        solver = TransportSolverF(ctx, mesh, model, bd, f_source=source_term(mesh.coords), rtol=args.rtol, maxit=args.maxit,
+                                  c0_method=args.c0_method)
+        c1 = 0.1 * np.ones(mesh.num_vertices())
+    else:
+        part = partition.slab_partition(BOX, (n, n, n), rank, nranks)
+        bd = partition.slab_boundary_data(part, top, (0.0, 0.0, -0.5), top, 0.1)
+        halo = partition.make_halo(ctx, part)
+        solver = TransportSolverF(ctx, part.mesh, model, bd, f_source=source_term(part.mesh.coords), rtol=args.rtol,
+                                  maxit=args.maxit, c0_method=args.c0_method, halo=halo, n_owned=part.n_owned)
+        c1 = 0.1 * np.ones(part.mesh.num_vertices())
+    solver.set_state(c1=c1)
+    return solver
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from mupopp_b200.device import Context
+    rank = int(os.environ.get("RANK", "0"))
+    nranks = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; mupopp_b200 has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local)
+    ctx = Context(local)
+    if nranks > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        ids = [ctx.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        ctx.init_comm(nranks, rank, ids[0])
+
+    def barrier():
+        if nranks > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t0 = time.perf_counter()
+    s = build_problem(ctx, args, rank, nranks)
+    barrier()
+    log("[rank %d] setup %.1f s: %d local vertices, %d cells, nnz %d" % (rank, time.perf_counter() - t0, s.dm.nvert, s.dm.ncell, s.L.nnz))
+
+    for k in range(args.warmup):
+        t1 = time.perf_counter()
+        r = s.step()
+        torch.cuda.synchronize()
+        log("[rank %d] warmup %d: %.3f s %s" % (rank, k, time.perf_counter() - t1, {a: (b.niter if b else None) for a, b in r.items()}))
+
+    # ---- timed region 1: device-resident state (value)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ctx.timing(True, 20000)
+    ctx.timing_read()
+    launches0 = ctx.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    iters = []
+    barrier()
+    ev0.record()
+    for k in range(args.steps):
+        r = s.step()
+        iters.append({a: (b.niter if b else 0) for a, b in r.items()})
+    ev1.record()
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    n_spmv, spmv_ms = ctx.timing_read()
+    ctx.timing(False)
+    clocks = sampler.stop() if rank == 0 else None
+    tt = torch.tensor([ms_total], dtype=torch.float64, device=ctx.device)
+    if nranks > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = 1e3 / ms_step
+
+    # ---- timed region 2: end to end through the public API with HOST state buffers (e2e)
+    names = ["c0", "c1", "c2", "p", "u"]
+    host_in = {k: torch.empty_like(getattr(s, k), device="cpu").pin_memory() for k in names}
+    host_out = {k: torch.empty_like(getattr(s, k), device="cpu").pin_memory() for k in names}
+    for k in names:
+        host_in[k].copy_(getattr(s, k))
+    torch.cuda.synchronize()
+    bytes_in = sum(int(v.numel()) * 8 for v in host_in.values())
+    bytes_out = sum(int(v.numel()) * 8 for v in host_out.values())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        for nm in names:
+            getattr(s, nm).copy_(host_in[nm], non_blocking=True)          # H2D of this step's input state
+        s.step()
+        for nm in names:
+            host_out[nm].copy_(getattr(s, nm), non_blocking=True)         # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+        host_in, host_out = host_out, host_in                             # next step starts from the host copy
+    e1.record()
+    barrier()
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=ctx.device)
+    if nranks > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = 1e3 / (float(te.item()) / args.steps)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        N, nnz = s.L.nrow, s.L.nnz
+        spmv_bytes = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N        # vals+cols, rowptr, x read once + y write
+        avg_ms = spmv_ms / max(n_spmv, 1)
+        achieved = spmv_bytes / (avg_ms * 1e-3) / 1e9 if n_spmv else None
+        out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": nranks, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+               "data": "synthetic", "config": workload_config(args, nranks),
+               "krylov_iterations_per_step": iters,
+               "clocks": clocks, "gpu_launches": int(launches),
+               "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
+               "roofline": {"bound": "hbm", "kernel": "k_spmv (CSR SpMV inside PCG/GMRES, per-rank operator)", "achieved": achieved,
+                            "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                            "frac": (achieved / peak) if achieved else None, "traffic": None,
+                            "algorithmic_bytes_per_launch": spmv_bytes, "launches_timed": n_spmv, "avg_launch_ms": avg_ms,
+                            "share_of_step": spmv_ms / ms_total}}
+        if not args.no_cpu and nranks == 1:
+            try:
+                ndof, times, oit = oracle_step_time(args.ref_n, args.rtol, 1, 0)
+                cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
+                v = 1.0 / (np.mean(times) * (args.n + 1) ** 3 / ndof)
+                out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": cores,
+                                       "sample": "1 oracle mode-F timestep (NumPy assembly + SciPy cg/bicgstab+Jacobi, same rtol) on a %d^3 "
+                                                 "sample (%d dofs/field, %.1f s), scaled to %d^3 linearly in dofs (iteration growth "
+                                                 "ignored: favours the CPU)" % (args.ref_n, ndof, float(np.mean(times)), args.n),
+                                       "sample_iters": oit[-1] if oit else None}
+            except Exception as e:  # the baseline is reporting only; never let it break the GPU line
+                out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port", "sample": "failed: %r" % (e,)}
+        print(json.dumps(out), flush=True)
+    if nranks > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=200, help="hexes per direction (200 -> 8 120 601 dofs/field, the metric's size)")
+    ap.add_argument("--ref-n", type=int, default=40, help="sample size of the CPU oracle leg")
+    ap.add_argument("--rtol", type=float, default=1e-12)
+    ap.add_argument("--maxit", type=int, default=50000)
+    ap.add_argument("--c0-method", default="gmres", choices=["gmres", "bicgstab"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -35,6 +35,10 @@ int mp_ctx_destroy(mp_ctx *ctx);
 int mp_ctx_sync(mp_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 int64_t mp_ctx_launch_count(const mp_ctx *ctx);
+/* optional CUDA-event timing of every SpMV launch (the dominant kernel) on the context's stream:
+ * enable with a sample capacity, then read (count, summed milliseconds) -- used by bench.py's roofline */
+int mp_ctx_timing(mp_ctx *ctx, int enable, int max_samples);
+int mp_ctx_timing_read(mp_ctx *ctx, int *nsamples, double *total_ms);
 
 /* ------------------------------------------------------------------ mesh view (device pointers) */
 typedef struct {
@@ -135,6 +139,11 @@ int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const doubl
 /* Jacobi-preconditioned BiCGStab (non-symmetric transport rows). */
 int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
                       mp_solve_info *info);
+
+/* Restarted GMRES(m), right Jacobi preconditioning, classical Gram-Schmidt applied twice; Hessenberg/Givens on the
+ * device.  The robust choice for the SUPG transport rows (non-normal at large CFL).  restart_m <= 0 -> 50. */
+int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
+                   int restart_m, mp_solve_info *info);
 
 /* ------------------------------------------------------------------ multi-GPU (replaces PETSc VecScatter / MPI_Allreduce)
  * One process per GPU.  The NCCL unique id is created on rank 0 and broadcast by the host (torch.distributed). */

@@ -51,6 +51,8 @@ SIGNATURES = {
     "mp_ctx_destroy": (C.c_int, [_VP]),
     "mp_ctx_sync": (C.c_int, [_VP]),
     "mp_ctx_launch_count": (C.c_int64, [_VP]),
+    "mp_ctx_timing": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "mp_ctx_timing_read": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "mp_plan_create": (C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_VP)]),
     "mp_plan_nnz": (C.c_int64, [_VP]),
     "mp_plan_export_csr": (C.c_int, [_VP, _VP, _VP, _VP]),
@@ -71,6 +73,7 @@ SIGNATURES = {
     "mp_jacobi_setup": (C.c_int, [_VP, C.POINTER(MpCsr), _VP]),
     "mp_solve_pcg": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_solve_bicgstab": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
+    "mp_solve_gmres": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.c_int, C.POINTER(MpSolveInfo)]),
     "mp_nccl_unique_id": (C.c_int, [_VP]),
     "mp_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "mp_comm_destroy": (C.c_int, [_VP]),

@@ -58,6 +58,10 @@ struct mp_ctx {
     unsigned int *d_counter = nullptr;  // last-block-done counters for deterministic reductions
     double *d_partials = nullptr;       // [kMaxPartialBlocks * kMaxDots]
     cudaEvent_t ev = nullptr;
+    // optional per-launch timing of the dominant kernel (SpMV) with CUDA events on ctx->stream
+    bool timing = false;
+    std::vector<cudaEvent_t> tev;   // pairs (start, stop)
+    size_t tev_used = 0;
     // NCCL (dlopen'ed); null when single-GPU
     void *nccl_comm = nullptr;
     int nranks = 1, rank = 0;

@@ -130,7 +130,7 @@ int mp_ctx_create(int device, void *stream, mp_ctx **out) {
     MP_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * 64));
     MP_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int) * 4));
     MP_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * 4));
-    MP_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 4096 * 4));
+    MP_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 4096 * 8));
     MP_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
     *out = c;
     return 0;
@@ -144,6 +144,7 @@ int mp_ctx_destroy(mp_ctx *c) {
     for (auto &w : c->work) if (w.ptr) cudaFree(w.ptr);
     cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_counter); cudaFree(c->d_partials);
     if (c->ev) cudaEventDestroy(c->ev);
+    for (auto e : c->tev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
     return 0;
@@ -156,6 +157,37 @@ int mp_ctx_sync(mp_ctx *c) {
 }
 
 int64_t mp_ctx_launch_count(const mp_ctx *c) { return c ? c->launches : -1; }
+
+int mp_ctx_timing(mp_ctx *c, int enable, int max_samples) {
+    MP_CHECK(c, "mp_ctx_timing: null ctx");
+    MP_CUDA(cudaSetDevice(c->device));
+    if (enable) {
+        size_t want = 2 * (size_t)(max_samples > 0 ? max_samples : 4096);
+        while (c->tev.size() < want) {
+            cudaEvent_t e;
+            MP_CUDA(cudaEventCreate(&e));
+            c->tev.push_back(e);
+        }
+        c->tev_used = 0;
+    }
+    c->timing = enable != 0;
+    return 0;
+}
+
+int mp_ctx_timing_read(mp_ctx *c, int *nsamples, double *total_ms) {
+    MP_CHECK(c && nsamples && total_ms, "mp_ctx_timing_read: null argument");
+    MP_CUDA(cudaStreamSynchronize(c->stream));
+    double tot = 0.0;
+    for (size_t i = 0; i + 1 < c->tev_used; i += 2) {
+        float ms = 0.f;
+        MP_CUDA(cudaEventElapsedTime(&ms, c->tev[i], c->tev[i + 1]));
+        tot += ms;
+    }
+    *nsamples = (int)(c->tev_used / 2);
+    *total_ms = tot;
+    c->tev_used = 0;
+    return 0;
+}
 
 int mp_nccl_unique_id(uint8_t *out128) {
     MP_CHECK(out128, "mp_nccl_unique_id: null");

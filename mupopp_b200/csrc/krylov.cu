@@ -14,6 +14,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxBlocks = 4096;  // partial sums per reduction slot
+constexpr int kMaxRestart = 4;    // residual-replacement restarts of the Krylov recurrences
 inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // device scalar slots
@@ -25,6 +26,7 @@ enum {
     S_PQ = 6,                           // p.Ap (CG)  /  rhat.v (BiCGStab)
     S_TS = 7, S_TT = 8,                 // BiCGStab t.s, t.t
     S_TMP0 = 9,
+    S_NCOL = 10,                        // GMRES: Givens columns completed in the current cycle
     S_COUNT = 16
 };
 constexpr int S_RZ0 = S_A0, S_RZ1 = S_A1, S_RHO0 = S_A0, S_RHO1 = S_A1, S_RV = S_PQ;
@@ -261,6 +263,8 @@ template <int DOT, bool GUARD>
 int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double *y, const double *w, int slot0, int slot1) {
     if (A->nrow == 0) return 0;
     int grid = grid_for(ctx, A->nrow * lanes);
+    const bool timed = ctx->timing && ctx->tev_used + 2 <= ctx->tev.size();
+    if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
 #define L(S_)                                                                                                           \
     k_spmv<S_, DOT, GUARD><<<grid, kThreads, 0, ctx->stream>>>(A->nrow, A->d_rowptr, A->d_colidx, A->d_vals, x, y, w,  \
                                                                 ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1)
@@ -272,6 +276,10 @@ int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double
         default: L(32); break;
     }
 #undef L
+    if (timed) {
+        cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
+        ctx->tev_used += 2;
+    }
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
     return 0;
@@ -295,12 +303,17 @@ int check_csr(const mp_csr *A) {
     return 0;
 }
 
-// set tolerance and initial scalars from the host after the one synchronising poll at solve start
-int start_solve(mp_ctx *ctx, mp_solve_info *info, bool *done) {
+// first == true: set the tolerance from ||b|| and zero the iteration counter (one synchronising poll per solve);
+// first == false (restart): only test the freshly evaluated TRUE residual against the stored tolerance.
+int start_solve(mp_ctx *ctx, mp_solve_info *info, bool first, bool *done) {
     MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_BB, 1));
     MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RR, 1));
     MP_TRY(poll(ctx));
-    double bb = ctx->h_scalars[S_BB], rr = ctx->h_scalars[S_RR];
+    const double bb = ctx->h_scalars[S_BB], rr = ctx->h_scalars[S_RR];
+    if (!first) {
+        *done = !(rr > ctx->h_scalars[S_TOL2]);
+        return 0;
+    }
     double tol = info->rtol * sqrt(bb);
     if (info->atol > tol) tol = info->atol;
     double hs[3] = {bb, tol * tol, 0.0};  // S_BB, S_TOL2, S_ITER are contiguous; S_RR is already on the device
@@ -323,6 +336,210 @@ int finish_solve(mp_ctx *ctx, mp_solve_info *info) {
     return 0;
 }
 
+}  // namespace
+
+namespace {
+
+// ------------------------------------------------------------------ GMRES(m), right Jacobi preconditioning
+// Small dense data of one cycle, all on the device: R (upper triangular, column major, ld = m+1), Givens (cs, sn),
+// rotated rhs g, solution y, and the two Gram-Schmidt coefficient columns h1, h2 (classical GS applied twice).
+struct GmresSmall {
+    double *R, *cs, *sn, *g, *y, *h1, *h2;
+    int m;
+};
+
+// V0 = r / ||r||, z = dinv * V0, g = (||r||, 0, ...), ncol = 0
+__global__ void __launch_bounds__(kThreads) k_gmres_start(int64_t n, const double *__restrict__ r, const double *__restrict__ dinv,
+                                                          double *__restrict__ V0, double *__restrict__ z, double *scal, GmresSmall S) {
+    if (!solver_active(scal)) return;
+    const double beta = sqrt(scal[S_RR]);
+    const double inv = beta > 0.0 ? 1.0 / beta : 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        const double v = r[i] * inv;
+        V0[i] = v;
+        z[i] = dinv[i] * v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S.g[0] = beta;
+        scal[S_NCOL] = 0.0;
+    }
+}
+
+// out[k0+v] = V_{k0+v} . w   for v < cnt <= 8
+__global__ void __launch_bounds__(kThreads) k_multidot8(int64_t n, const double *__restrict__ V, int64_t ld, int k0, int cnt,
+                                                        const double *__restrict__ w, double *partials, unsigned int *counter,
+                                                        double *out, const double *scal) {
+    if (!solver_active(scal)) return;
+    double acc[8];
+#pragma unroll
+    for (int v = 0; v < 8; ++v) acc[v] = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        const double wi = w[i];
+#pragma unroll
+        for (int v = 0; v < 8; ++v)
+            if (v < cnt) acc[v] += V[(int64_t)(k0 + v) * ld + i] * wi;
+    }
+    const int sl_[8] = {k0, k0 + 1, k0 + 2, k0 + 3, k0 + 4, k0 + 5, k0 + 6, k0 + 7};
+    grid_reduce<8>(acc, partials, counter, out, sl_, false);
+}
+
+// w -= sum_{k<=j} h[k] V_k ; optionally slot S_TMP0 = ||w||^2
+template <bool NORM>
+__global__ void __launch_bounds__(kThreads) k_gmres_orth(int64_t n, const double *__restrict__ V, int64_t ld, int j,
+                                                         const double *__restrict__ h, double *__restrict__ w, double *partials,
+                                                         unsigned int *counter, double *scal) {
+    if (!solver_active(scal)) return;
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        double wi = w[i];
+        for (int k = 0; k <= j; ++k) wi -= h[k] * V[(int64_t)k * ld + i];
+        w[i] = wi;
+        if (NORM) acc[0] += wi * wi;
+    }
+    if (NORM) {
+        const int sl_[1] = {S_TMP0};
+        grid_reduce<1>(acc, partials, counter, scal, sl_, false);
+    }
+}
+
+// V_{j+1} = w / ||w|| ; z = dinv * V_{j+1}
+__global__ void __launch_bounds__(kThreads) k_gmres_normalize(int64_t n, const double *__restrict__ w, const double *__restrict__ dinv,
+                                                              double *__restrict__ Vn, double *__restrict__ z, const double *scal) {
+    if (!solver_active(scal)) return;
+    const double nrm = sqrt(scal[S_TMP0]);
+    const double inv = nrm > 0.0 ? 1.0 / nrm : 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        const double v = w[i] * inv;
+        Vn[i] = v;
+        z[i] = dinv[i] * v;
+    }
+}
+
+// one thread: new Hessenberg column -> Givens -> residual estimate
+__global__ void k_gmres_givens(int j, GmresSmall S, double *scal) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (!solver_active(scal)) return;
+    const int ld = S.m + 1;
+    double *col = S.R + (int64_t)j * ld;
+    for (int k = 0; k <= j; ++k) col[k] = S.h1[k] + S.h2[k];
+    double hn = sqrt(scal[S_TMP0]);
+    for (int i = 0; i < j; ++i) {
+        const double t = S.cs[i] * col[i] + S.sn[i] * col[i + 1];
+        col[i + 1] = -S.sn[i] * col[i] + S.cs[i] * col[i + 1];
+        col[i] = t;
+    }
+    const double a = col[j], b = hn;
+    const double d = sqrt(a * a + b * b);
+    const double c = d > 0.0 ? a / d : 1.0, s = d > 0.0 ? b / d : 0.0;
+    S.cs[j] = c; S.sn[j] = s;
+    col[j] = d;
+    const double gj = S.g[j];
+    S.g[j] = c * gj;
+    S.g[j + 1] = -s * gj;
+    scal[S_RR] = S.g[j + 1] * S.g[j + 1];
+    scal[S_ITER] += 1.0;
+    scal[S_NCOL] = (double)(j + 1);
+}
+
+// one thread: back substitution R y = g over the completed columns
+__global__ void k_gmres_solve(GmresSmall S, const double *scal) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int nc = (int)scal[S_NCOL];
+    const int ld = S.m + 1;
+    for (int k = nc - 1; k >= 0; --k) {
+        double v = S.g[k];
+        for (int l = k + 1; l < nc; ++l) v -= S.R[(int64_t)l * ld + k] * S.y[l];
+        const double d = S.R[(int64_t)k * ld + k];
+        S.y[k] = d != 0.0 ? v / d : 0.0;
+    }
+}
+
+// x += dinv * sum_k y[k] V_k
+__global__ void __launch_bounds__(kThreads) k_gmres_xupdate(int64_t n, const double *__restrict__ V, int64_t ld,
+                                                            const double *__restrict__ y, const double *__restrict__ dinv,
+                                                            double *__restrict__ x, const double *scal) {
+    const int nc = (int)scal[S_NCOL];
+    if (nc == 0) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        double a = 0.0;
+        for (int k = 0; k < nc; ++k) a += y[k] * V[(int64_t)k * ld + i];
+        x[i] += dinv[i] * a;
+    }
+}
+
+}  // namespace
+
+extern "C" int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
+                              int restart_m, mp_solve_info *info) {
+    MP_CHECK(ctx && d_dinv && d_b && d_x && info, "mp_solve_gmres: null argument");
+    MP_TRY(check_csr(A));
+    const int m = restart_m > 0 ? (restart_m > 200 ? 200 : restart_m) : 50;
+    const int64_t n = A->nrow, nc = A->ncol;
+    int64_t nnz = 0;
+    MP_TRY(nnz_of(ctx, A, &nnz));
+    const int lanes = pick_lanes(A, nnz);
+    double *wk = nullptr, *sm = nullptr;
+    MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)((m + 3) * n + nc + 8), (void **)&wk));
+    const int pad = m + 16;  // k_multidot8 always stores 8 slots
+    const size_t nsmall = (size_t)(m + 1) * m + 7 * (size_t)pad;
+    MP_TRY(mp::ws_get(ctx, 1, sizeof(double) * nsmall, (void **)&sm));
+    double *V = wk, *w = wk + (int64_t)(m + 1) * n, *r = w + n, *z = r + n;  // z has ghost entries
+    GmresSmall S;
+    S.m = m;
+    S.R = sm; S.cs = S.R + (size_t)(m + 1) * m; S.sn = S.cs + pad; S.g = S.sn + pad; S.y = S.g + pad;
+    S.h1 = S.y + pad; S.h2 = S.h1 + pad;
+    const int g1 = grid_for(ctx, n);
+    const int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 5 : 25);
+    int total = 0;
+    for (int cycle = 0; cycle < 100000; ++cycle) {
+        // true residual r = b - A x at the start of every cycle
+        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
+        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, w, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, w, d_dinv, r, nullptr, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_TMP0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        bool done = false;
+        MP_TRY(start_solve(ctx, info, cycle == 0, &done));
+        if (done || total >= info->maxit) break;
+        k_gmres_start<<<g1, kThreads, 0, ctx->stream>>>(n, r, d_dinv, V, z, ctx->d_scalars, S);
+        mp::count_launch(ctx);
+        bool conv = false;
+        for (int j = 0; j < m && total < info->maxit; ++j) {
+            MP_TRY(mp_halo_exchange(ctx, halo, z));
+            MP_TRY((launch_spmv<0, true>(ctx, A, lanes, z, w, nullptr, 0, 0)));
+            for (int pass = 0; pass < 2; ++pass) {   // classical Gram-Schmidt, applied twice
+                double *h = pass == 0 ? S.h1 : S.h2;
+                for (int k0 = 0; k0 <= j; k0 += 8) {
+                    const int cnt = (j + 1 - k0) < 8 ? (j + 1 - k0) : 8;
+                    k_multidot8<<<g1, kThreads, 0, ctx->stream>>>(n, V, n, k0, cnt, w, ctx->d_partials, ctx->d_counter, h, ctx->d_scalars);
+                    mp::count_launch(ctx);
+                }
+                MP_TRY(mp_allreduce_sum(ctx, h, j + 1));
+                if (pass == 0) k_gmres_orth<false><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_counter, ctx->d_scalars);
+                else k_gmres_orth<true><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_counter, ctx->d_scalars);
+                mp::count_launch(ctx);
+            }
+            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_TMP0, 1));
+            k_gmres_normalize<<<g1, kThreads, 0, ctx->stream>>>(n, w, d_dinv, V + (int64_t)(j + 1) * n, z, ctx->d_scalars);
+            k_gmres_givens<<<1, 32, 0, ctx->stream>>>(j, S, ctx->d_scalars);
+            mp::count_launch(ctx, 2);
+            ++total;
+            if (total % every == 0 || total == info->maxit || j + 1 == m) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_gmres: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) { conv = true; break; }
+            }
+        }
+        k_gmres_solve<<<1, 32, 0, ctx->stream>>>(S, ctx->d_scalars);
+        k_gmres_xupdate<<<g1, kThreads, 0, ctx->stream>>>(n, V, n, S.y, d_dinv, d_x, ctx->d_scalars);
+        mp::count_launch(ctx, 2);
+        (void)conv;
+    }
+    return finish_solve(ctx, info);
+}
+
+namespace {
 }  // namespace
 
 extern "C" int mp_spmv(mp_ctx *ctx, const mp_csr *A, const double *d_x, double *d_y) {
@@ -376,32 +593,37 @@ extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, 
     MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(2 * n + nc + 8), (void **)&w));
     double *r = w, *q = w + n, *p = w + 2 * n;  // p has ghost entries
     const int g1 = grid_for(ctx, n);
-    // r = b - A x
-    MP_TRY(mp_halo_exchange(ctx, halo, d_x));
-    MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, q, nullptr, 0, 0)));
-    k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, p, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RZ0);
-    mp::count_launch(ctx);
-    MP_CUDA(cudaGetLastError());
-    MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RZ0, 1));
-    bool done = false;
-    MP_TRY(start_solve(ctx, info, &done));
-    if (done) return 0;
-    int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 10 : 50);
-    int cur = S_RZ0, nxt = S_RZ1;
-    for (int it = 0; it < info->maxit; ++it) {
-        MP_TRY(mp_halo_exchange(ctx, halo, p));
-        MP_TRY((launch_spmv<1, true>(ctx, A, lanes, p, q, p, S_PQ, 0)));
-        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_PQ, 1));
-        k_cg_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_dinv, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
-        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + (nxt < S_RR ? nxt : S_RR), 2));
-        k_cg_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, r, d_dinv, p, ctx->d_scalars, cur, nxt);
-        mp::count_launch(ctx, 2);
-        int tmp = cur; cur = nxt; nxt = tmp;
-        if ((it + 1) % every == 0 || it + 1 == info->maxit) {
-            MP_CUDA(cudaGetLastError());
-            MP_TRY(poll(ctx));
-            if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
-            if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_pcg: NaN residual at iteration %d", it + 1); return 4; }
+    const int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 10 : 50);
+    int total = 0;
+    // outer loop = residual replacement: after the recurrence says "converged" the TRUE residual b - A x is
+    // evaluated and the iteration restarted from x if it is not below the tolerance yet.
+    for (int restart = 0; restart <= kMaxRestart; ++restart) {
+        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
+        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, q, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, p, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RZ0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RZ0, 1));
+        bool done = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done));
+        if (done || total >= info->maxit) break;
+        int cur = S_RZ0, nxt = S_RZ1;
+        for (; total < info->maxit;) {
+            MP_TRY(mp_halo_exchange(ctx, halo, p));
+            MP_TRY((launch_spmv<1, true>(ctx, A, lanes, p, q, p, S_PQ, 0)));
+            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_PQ, 1));
+            k_cg_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_dinv, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
+            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + (nxt < S_RR ? nxt : S_RR), 2));
+            k_cg_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, r, d_dinv, p, ctx->d_scalars, cur, nxt);
+            mp::count_launch(ctx, 2);
+            int tmp = cur; cur = nxt; nxt = tmp;
+            ++total;
+            if (total % every == 0 || total == info->maxit) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_pcg: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
+            }
         }
     }
     return finish_solve(ctx, info);
@@ -419,35 +641,39 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
     MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(6 * n + 2 * nc + 8), (void **)&w));
     double *r = w, *rhat = w + n, *p = w + 2 * n, *v = w + 3 * n, *s = w + 4 * n, *t = w + 5 * n, *y = w + 6 * n, *z = w + 6 * n + nc;
     const int g1 = grid_for(ctx, n);
-    MP_TRY(mp_halo_exchange(ctx, halo, d_x));
-    MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, v, nullptr, 0, 0)));
-    k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, v, d_dinv, r, nullptr, rhat, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RHO0);
-    mp::count_launch(ctx);
-    MP_CUDA(cudaGetLastError());
-    MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RHO0, 1));
-    bool done = false;
-    MP_TRY(start_solve(ctx, info, &done));
-    if (done) return 0;
-    int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 5 : 25);
-    int cur = S_RHO0, nxt = S_RHO1;
-    for (int it = 0; it < info->maxit; ++it) {
-        k_bicg_p<<<g1, kThreads, 0, ctx->stream>>>(n, it == 0 ? 1 : 0, r, v, d_dinv, p, y, ctx->d_scalars, cur);
-        MP_TRY(mp_halo_exchange(ctx, halo, y));
-        MP_TRY((launch_spmv<1, true>(ctx, A, lanes, y, v, rhat, S_RV, 0)));
-        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RV, 1));
-        k_bicg_s<<<g1, kThreads, 0, ctx->stream>>>(n, r, v, d_dinv, s, z, ctx->d_scalars, cur);
-        MP_TRY(mp_halo_exchange(ctx, halo, z));
-        MP_TRY((launch_spmv<2, true>(ctx, A, lanes, z, t, s, S_TS, S_TT)));
-        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_TS, 2));
-        k_bicg_x<<<g1, kThreads, 0, ctx->stream>>>(n, y, z, s, t, rhat, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
-        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + (nxt < S_RR ? nxt : S_RR), 2));
-        mp::count_launch(ctx, 3);
-        int tmp = cur; cur = nxt; nxt = tmp;
-        if ((it + 1) % every == 0 || it + 1 == info->maxit) {
-            MP_CUDA(cudaGetLastError());
-            MP_TRY(poll(ctx));
-            if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
-            if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_bicgstab: NaN residual at iteration %d", it + 1); return 4; }
+    const int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 5 : 25);
+    int total = 0;
+    for (int restart = 0; restart <= kMaxRestart; ++restart) {   // residual replacement, see mp_solve_pcg
+        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
+        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, v, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, v, d_dinv, r, nullptr, rhat, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RHO0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RHO0, 1));
+        bool done = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done));
+        if (done || total >= info->maxit) break;
+        int cur = S_RHO0, nxt = S_RHO1;
+        for (int it = 0; total < info->maxit; ++it) {
+            k_bicg_p<<<g1, kThreads, 0, ctx->stream>>>(n, it == 0 ? 1 : 0, r, v, d_dinv, p, y, ctx->d_scalars, cur);
+            MP_TRY(mp_halo_exchange(ctx, halo, y));
+            MP_TRY((launch_spmv<1, true>(ctx, A, lanes, y, v, rhat, S_RV, 0)));
+            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RV, 1));
+            k_bicg_s<<<g1, kThreads, 0, ctx->stream>>>(n, r, v, d_dinv, s, z, ctx->d_scalars, cur);
+            MP_TRY(mp_halo_exchange(ctx, halo, z));
+            MP_TRY((launch_spmv<2, true>(ctx, A, lanes, z, t, s, S_TS, S_TT)));
+            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_TS, 2));
+            k_bicg_x<<<g1, kThreads, 0, ctx->stream>>>(n, y, z, s, t, rhat, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
+            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + (nxt < S_RR ? nxt : S_RR), 2));
+            mp::count_launch(ctx, 3);
+            int tmp = cur; cur = nxt; nxt = tmp;
+            ++total;
+            if (total % every == 0 || total == info->maxit) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_bicgstab: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
+            }
         }
     }
     return finish_solve(ctx, info);

@@ -46,6 +46,14 @@ class Context:
     def launch_count(self):
         return int(self.lib.mp_ctx_launch_count(self.h))
 
+    def timing(self, enable, max_samples=4096):
+        check(self.lib.mp_ctx_timing(self.h, 1 if enable else 0, max_samples), "mp_ctx_timing")
+
+    def timing_read(self):
+        n, ms = C.c_int(), C.c_double()
+        check(self.lib.mp_ctx_timing_read(self.h, C.byref(n), C.byref(ms)), "mp_ctx_timing_read")
+        return n.value, ms.value
+
     # ---- tensors
     def zeros(self, n, dtype=torch.float64):
         return torch.zeros(int(n), dtype=dtype, device=self.device)
@@ -166,14 +174,18 @@ class CsrMatrix:
         return sp.csr_matrix((self.vals.cpu().numpy(), self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
                              shape=(self.nrow, self.ncol))
 
-    def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True):
+    def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True, restart=50):
         if self.dinv is None or refresh_jacobi:
             self.jacobi_setup()
         info = MpSolveInfo(rtol, atol, int(maxit), int(check_every), 0, 0, 0.0)
-        fn = {"pcg": self.ctx.lib.mp_solve_pcg, "cg": self.ctx.lib.mp_solve_pcg,
-              "bicgstab": self.ctx.lib.mp_solve_bicgstab}[method]
-        check(fn(self.ctx.h, C.byref(self.c), ptr(self.dinv), ptr(b), ptr(x), halo.h if halo is not None else None, C.byref(info)),
-              "mp_solve_" + method)
+        hh = halo.h if halo is not None else None
+        if method == "gmres":
+            check(self.ctx.lib.mp_solve_gmres(self.ctx.h, C.byref(self.c), ptr(self.dinv), ptr(b), ptr(x), hh, int(restart),
+                                              C.byref(info)), "mp_solve_gmres")
+        else:
+            fn = {"pcg": self.ctx.lib.mp_solve_pcg, "cg": self.ctx.lib.mp_solve_pcg,
+                  "bicgstab": self.ctx.lib.mp_solve_bicgstab}[method]
+            check(fn(self.ctx.h, C.byref(self.c), ptr(self.dinv), ptr(b), ptr(x), hh, C.byref(info)), "mp_solve_" + method)
         return SolveResult(info.niter, bool(info.converged), info.relres)
 
 

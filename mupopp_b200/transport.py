@@ -122,8 +122,9 @@ class TransportSolverF:
     """GPU state + operators of one mode-F problem.  Fields are torch fp64 tensors on the device."""
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
-                 rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None):
+                 rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="gmres", gmres_restart=50):
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
+        self.c0_method, self.gmres_restart = c0_method, gmres_restart
         self.halo = halo
         self.dm = DeviceMesh(ctx, mesh)
         V, Cn, d = self.dm.nvert, self.dm.ncell, self.dm.dim
@@ -207,7 +208,7 @@ class TransportSolverF:
         self.A.apply_dirichlet(self.rhs, self.c0_isbc, self.c0_g)
         self.A.jacobi_setup()
         self.c0_new.copy_(self.c0)
-        r0 = self.A.solve("bicgstab", self.rhs, self.c0_new, **kw)
+        r0 = self.A.solve(self.c0_method, self.rhs, self.c0_new, restart=self.gmres_restart, **kw)
         self._exchange(self.c0_new)
         # 3. pressure with the NEW c0, warm start from p^n
         check(lib.mp_elem_p1_pressure_rhs(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.c0_new), ptr(self.evec)),

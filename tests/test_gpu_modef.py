@@ -85,8 +85,7 @@ def _setup(dim, n, kind):
         model = TransportModel.darcy_two_component(Pe=1e3, Da=10.0, phi=0.01, alpha=0.01, dt=0.1, K=0.1, zh=zh, gam_rho=-1.0, rho_0=0.0)
         oprm = forms.darcy_two_component_params(Pe=1e3, Da=10.0, phi=0.01, alpha=0.01, dt=0.1, K=0.1, zhat=zh, gam_rho=-1.0, rho_0=0.0)
     else:
-        rng = np.random.default_rng(5)
-        K = 0.5 + rng.random(om.nv)
+        K = 1.0 + 0.3 * np.sin(2 * np.pi * om.coords[:, 0]) * np.cos(np.pi * om.coords[:, -1])
         model = TransportModel.darcy_three_component(Pe=200, Da=1.0, phi=0.2, alpha=0.01, dt=0.01, K=K, zh=zh, SUPG=2)
         oprm = forms.darcy_three_component_params(Pe=200, Da=1.0, phi=0.2, alpha=0.01, dt=0.01, K=K, zhat=zh, SUPG=2)
     uval = np.zeros(dim)
@@ -112,7 +111,7 @@ def test_modef_steps_match_oracle(ctx, dim, n, kind):
     c2_0 = 0.01 * rng.random(om.nv)
     c0_0 = 0.05 * rng.random(om.nv)
     st = modef.StateF(u=np.zeros((om.nc, dim)), p=np.zeros(om.nv), c0=c0_0.copy(), c1=c1_0.copy(), c2=c2_0.copy())
-    s = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-13)
+    s = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-14)
     s.set_state(c0=c0_0, c1=c1_0, c2=c2_0)
     nsteps = 4
     for k in range(nsteps):
@@ -130,7 +129,7 @@ def test_modef_steps_match_oracle(ctx, dim, n, kind):
         assert rel(s.p.cpu().numpy(), st.p) < tol
         assert rel(s.u.cpu().numpy().reshape(-1, dim), st.u) < tol
     # free-running N steps
-    s2 = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-13)
+    s2 = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-14)
     s2.set_state(c0=c0_0, c1=c1_0, c2=c2_0)
     for k in range(nsteps):
         s2.step()
@@ -152,3 +151,45 @@ def test_determinism_bitwise(ctx):
         outs.append((s.c0.cpu().numpy().copy(), s.p.cpu().numpy().copy(), s.A.vals.cpu().numpy().copy()))
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("method", ["gmres", "bicgstab", "pcg"])
+def test_krylov_solvers_against_direct(ctx, method):
+    """Each Krylov driver reproduces the LU solution of the same CSR system (SPD for pcg, SUPG transport otherwise)."""
+    import ctypes as C
+    import scipy.sparse.linalg as spla
+    from mupopp_b200._lib import check, ptr
+    from mupopp_b200.device import DeviceMesh, Plan
+    pm, om = _mesh_pair(3, 7)
+    asm = forms.Assembler(om)
+    dm = DeviceMesh(ctx, pm)
+    plan = Plan(ctx, dm.cells, dm.cells, dm.nvert, dm.nvert)
+    rng = np.random.default_rng(3)
+    emat = ctx.empty(dm.ncell * 16)
+    A = plan.new_matrix()
+    if method == "pcg":
+        check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(dm.c), None, 1.0, 1.0, ptr(emat)))
+        plan.scatter_matrix(emat, A)
+        isbc = np.zeros(om.nv, dtype=np.uint8)
+        isbc[om.coords[:, 2] < 1e-12] = 1
+        g = rng.random(om.nv)
+    else:
+        u = np.tile(np.array([0.5, -0.3, 2.0]), (om.nc, 1))
+        ud = ctx.to_device(u.ravel())
+        check(ctx.lib.mp_elem_p1_adr_single(ctx.h, C.byref(dm.c), 100.0, 1.0, 0.5, ptr(ud), None, ptr(emat), None))
+        plan.scatter_matrix(emat, A)
+        isbc = np.zeros(om.nv, dtype=np.uint8)
+        isbc[om.coords[:, 2] < 1e-12] = 1
+        g = rng.random(om.nv)
+    b = rng.standard_normal(om.nv)
+    A0 = A.to_scipy()
+    bd_ = ctx.to_device(b)
+    A.apply_dirichlet(bd_, ctx.to_device(isbc), ctx.to_device(g))
+    Ao, bo = fem.apply_dirichlet_symmetric(A0, b, np.nonzero(isbc)[0], g[isbc.astype(bool)])
+    assert abs(A.to_scipy() - Ao).max() <= 1e-15 * abs(Ao).max()
+    assert rel(bd_.cpu().numpy(), bo) < 1e-15
+    x = ctx.zeros(om.nv)
+    res = A.solve(method, bd_, x, rtol=1e-14, maxit=5000)
+    xo = spla.splu(Ao.tocsc()).solve(bo)
+    assert res.converged, res
+    assert rel(x.cpu().numpy(), xo) < 1e-10

@@ -1,0 +1,58 @@
+"""Host mesh generators of the product reproduce the oracle's DOLFIN-convention meshes bit for bit."""
+import numpy as np
+import pytest
+
+import mupopp_b200 as mp
+from mupopp_b200.transport import make_boundary_data
+from oracle import fem, modef
+
+
+@pytest.mark.parametrize("nx,ny", [(3, 2), (8, 8)])
+def test_rectangle(nx, ny):
+    a = mp.RectangleMesh((0, 0), (4, 1), nx, ny)
+    b = fem.rectangle_mesh(0, 0, 4, 1, nx, ny)
+    assert np.array_equal(a.cells, b.cells) and np.array_equal(a.coords, b.coords)
+    b.init_edges()
+    assert np.array_equal(a.edges, b.edges) and np.array_equal(a.cell_edges, b.cell_edges)
+
+
+@pytest.mark.parametrize("n", [(2, 3, 4), (5, 5, 5)])
+def test_box(n):
+    a = mp.BoxMesh((0, 0, 0), (4, 4, 1), *n)
+    b = fem.box_mesh((0, 0, 0), (4, 4, 1), *n)
+    assert np.array_equal(a.cells, b.cells) and np.array_equal(a.coords, b.coords)
+    assert a.num_cells() == 6 * n[0] * n[1] * n[2]
+    b.init_edges()
+    assert np.array_equal(a.edges, b.edges) and np.array_equal(a.cell_edges, b.cell_edges)
+    assert a.num_edges() == 7 * n[0] * n[1] * n[2] + 3 * (n[0] * n[1] + n[1] * n[2] + n[0] * n[2]) + sum(n)
+    assert np.allclose(a.cell_diameters(), b.hmax_cells())
+
+
+def test_box_slab_is_a_window_of_the_global_mesh():
+    g = mp.BoxMesh((0, 0, 0), (1, 1, 2), 3, 4, 6)
+    s = mp.BoxMesh((0, 0, 0), (1, 1, 2), 3, 4, 6, z_range=(2, 5))
+    npl = 4 * 5
+    cells_g = g.cells[6 * 3 * 4 * 2: 6 * 3 * 4 * 5]
+    assert np.array_equal(s.cells + 2 * npl, cells_g)
+    assert np.array_equal(s.coords, g.coords[2 * npl: 6 * npl])
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_boundary_data_matches_oracle(dim):
+    if dim == 2:
+        a, b = mp.RectangleMesh((0, 0), (2, 1), 6, 5), fem.rectangle_mesh(0, 0, 2, 1, 6, 5)
+    else:
+        a, b = mp.BoxMesh((0, 0, 0), (2, 2, 1), 4, 3, 5), fem.box_mesh((0, 0, 0), (2, 2, 1), 4, 3, 5)
+    uval = np.zeros(dim)
+    uval[-1] = -0.5
+    bd = make_boundary_data(a, lambda x: x[..., -1] > 1 - 1e-12, lambda x: uval * (1 + x[..., :1]), lambda x: x[..., -1] > 1 - 1e-12, 0.1)
+    ob = modef.make_bcs(b, lambda x: x[-1] > 1 - 1e-12, lambda x: uval * (1 + x[0]), lambda x: x[-1] > 1 - 1e-12, 0.1)
+    assert np.array_equal(bd.p_isbc.nonzero()[0], ob.p_dofs)
+    assert np.allclose(bd.flux_load, ob.flux_load, rtol=0, atol=1e-15)
+    assert np.array_equal(bd.c0_isbc.nonzero()[0], ob.c0_dofs)
+    assert np.allclose(bd.c0_g[ob.c0_dofs], ob.c0_vals)
+    # generic (non-box) facet detection agrees with the box fast path
+    a2 = mp.Mesh(a.coords, a.cells)
+    f1 = a.boundary_facets()[0]
+    f2 = a2.boundary_facets()[0]
+    assert sorted(map(tuple, f1.tolist())) == sorted(map(tuple, f2.tolist()))
