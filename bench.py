@@ -150,7 +150,7 @@ def workload_config(args, nranks):
     return {"workload": "CCS 3-component reactive transport (mupopp CCS.advection_diffusion_three_component), mode F, "
                         "BoxMesh [0,4]x[0,4]x[0,1] %d^3 x 6 tets, P1, %d dofs/field" % (args.n, (args.n + 1) ** 3),
             "n": args.n, "dofs_per_field": (args.n + 1) ** 3, "cells": 6 * args.n ** 3,
-            "physics": PHYS, "krylov_rtol": args.rtol, "c0_solver": args.c0_method, "preconditioner": "jacobi",
+            "physics": PHYS, "krylov_rtol": args.rtol, "c0_solver": args.c0_method, "preconditioner": "jacobi", "side_walls": args.sides,
             "partition": "z-slabs x%d" % nranks if nranks > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (CSR operators 1.6 GB each at n=200 vs 126 MB L2)"}
 
@@ -164,15 +164,21 @@ def build_problem(ctx, args, rank, nranks):
     model = TransportModel.ccs_three_component(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"], dt=PHYS["dt"],
                                                K=PHYS["K"], zh=(0.0, 0.0, 1.0), gam_rho=PHYS["gam_rho"])
     top = lambda x: x[..., 2] > 1.0 - 1e-12
+    if args.sides == "noflow":
+        # impermeable side walls: u.n = 0 on x/y faces (Gamma_u = top + sides), p = 0 only on the bottom outflow face
+        umark = lambda x: x[..., 2] > 1e-12
+        uval = lambda x: np.stack([0 * x[..., 0], 0 * x[..., 0], np.where(x[..., 2] > 1.0 - 1e-12, -0.5, 0.0)], -1)
+    else:
+        umark, uval = top, (0.0, 0.0, -0.5)
     if nranks == 1:
         mesh = mp.BoxMesh(BOX[0], BOX[1], n, n, n)
-        bd = make_boundary_data(mesh, top, (0.0, 0.0, -0.5), top, 0.1)
+        bd = make_boundary_data(mesh, umark, uval, top, 0.1)
         solver = TransportSolverF(ctx, mesh, model, bd, f_source=source_term(mesh.coords), rtol=args.rtol, maxit=args.maxit,
                                   c0_method=args.c0_method)
         c1 = 0.1 * np.ones(mesh.num_vertices())
     else:
         part = partition.slab_partition(BOX, (n, n, n), rank, nranks)
-        bd = partition.slab_boundary_data(part, top, (0.0, 0.0, -0.5), top, 0.1)
+        bd = partition.slab_boundary_data(part, umark, uval, top, 0.1)
         halo = partition.make_halo(ctx, part)
         solver = TransportSolverF(ctx, part.mesh, model, bd, f_source=source_term(part.mesh.coords), rtol=args.rtol,
                                   maxit=args.maxit, c0_method=args.c0_method, halo=halo, n_owned=part.n_owned)
@@ -316,6 +322,8 @@ def main():
     ap.add_argument("--maxit", type=int, default=50000)
     ap.add_argument("--c0-method", default="gmres", choices=["gmres", "bicgstab"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sides", default="natural", choices=["natural", "noflow"],
+                    help="x/y faces: natural (p=0, as CCS_3D_side_source.py) or impermeable (u.n=0)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

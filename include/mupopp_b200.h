@@ -29,7 +29,7 @@ typedef struct mp_halo mp_halo;
 /* ------------------------------------------------------------------ context */
 int mp_version(void);
 const char *mp_last_error(void);
-/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or NULL for a private one */
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); NULL = the CUDA default stream */
 int mp_ctx_create(int device, void *stream, mp_ctx **out);
 int mp_ctx_destroy(mp_ctx *ctx);
 int mp_ctx_sync(mp_ctx *ctx);
@@ -39,6 +39,8 @@ int64_t mp_ctx_launch_count(const mp_ctx *ctx);
  * enable with a sample capacity, then read (count, summed milliseconds) -- used by bench.py's roofline */
 int mp_ctx_timing(mp_ctx *ctx, int enable, int max_samples);
 int mp_ctx_timing_read(mp_ctx *ctx, int *nsamples, double *total_ms);
+/* tuning knobs for A/B measurements: "spmv_variant" = 0 SELL-32 when mirrored, else CSR CTA-stream (default), 1 CSR CTA-stream, 2 CSR sub-warp-per-row, 3 CSR warp-stream */
+int mp_ctx_set_option(mp_ctx *ctx, const char *name, int value);
 
 /* ------------------------------------------------------------------ mesh view (device pointers) */
 typedef struct {
@@ -59,8 +61,13 @@ typedef struct {
 int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr, const int32_t *d_col_dofs, int32_t lc,
                    int64_t ncell, int64_t nrow, int64_t ncol, mp_plan **out);
 int64_t mp_plan_nnz(const mp_plan *plan);
+int32_t mp_plan_max_row_nnz(const mp_plan *plan);
 int mp_plan_export_csr(mp_ctx *ctx, const mp_plan *plan, int32_t *d_rowptr, int32_t *d_colidx);
 int mp_plan_destroy(mp_plan *plan);
+/* SELL-32 layout of the plan's pattern (library-owned device arrays): number of slices, padded entries, pointers */
+int mp_plan_sell_info(const mp_plan *plan, int64_t *nslice, int64_t *nentries, const int32_t **d_sliceptr, const int32_t **d_col);
+/* d_sell_vals[nentries] <- CSR values permuted into the SELL-32 layout (padding = 0); call after assembly / Dirichlet */
+int mp_csr_to_sell(mp_ctx *ctx, const mp_plan *plan, const double *d_csr_vals, double *d_sell_vals);
 
 /* vals[slot] = sum over incident cells (ascending cell id) of elem_mat[cell][i][j]   (no atomics) */
 int mp_scatter_matrix(mp_ctx *ctx, const mp_plan *plan, const double *d_elem_mat, double *d_vals);
@@ -114,9 +121,16 @@ typedef struct {
     int64_t nrow;          /* owned rows */
     int64_t ncol;          /* local columns (owned + ghost) */
     int64_t nnz;
+    int32_t max_row_nnz;   /* longest row (0 = unknown): selects the CSR-stream SpMV for short regular rows */
+    int32_t pad;
     const int32_t *d_rowptr;
     const int32_t *d_colidx;
     const double *d_vals;
+    /* optional SELL-32 mirror used by SpMV (NULL -> CSR kernels): slice s = rows 32s..32s+31 stored [j][lane],
+     * padded to the slice's longest row with (col = row, val = 0); see mp_plan_sell_info / mp_csr_to_sell */
+    const int32_t *d_sell_sliceptr;
+    const int32_t *d_sell_col;
+    const double *d_sell_val;
 } mp_csr;
 
 int mp_spmv(mp_ctx *ctx, const mp_csr *A, const double *d_x, double *d_y);

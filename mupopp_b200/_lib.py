@@ -33,8 +33,9 @@ class MpTransportParams(C.Structure):
 
 
 class MpCsr(C.Structure):
-    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nnz", C.c_int64),
-                ("d_rowptr", C.c_void_p), ("d_colidx", C.c_void_p), ("d_vals", C.c_void_p)]
+    _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nnz", C.c_int64), ("max_row_nnz", C.c_int32), ("pad", C.c_int32),
+                ("d_rowptr", C.c_void_p), ("d_colidx", C.c_void_p), ("d_vals", C.c_void_p),
+                ("d_sell_sliceptr", C.c_void_p), ("d_sell_col", C.c_void_p), ("d_sell_val", C.c_void_p)]
 
 
 class MpSolveInfo(C.Structure):
@@ -55,8 +56,12 @@ SIGNATURES = {
     "mp_ctx_timing_read": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "mp_plan_create": (C.c_int, [_VP, _VP, C.c_int32, _VP, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.POINTER(_VP)]),
     "mp_plan_nnz": (C.c_int64, [_VP]),
+    "mp_plan_max_row_nnz": (C.c_int32, [_VP]),
+    "mp_ctx_set_option": (C.c_int, [_VP, C.c_char_p, C.c_int]),
     "mp_plan_export_csr": (C.c_int, [_VP, _VP, _VP, _VP]),
     "mp_plan_destroy": (C.c_int, [_VP]),
+    "mp_plan_sell_info": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_VP), C.POINTER(_VP)]),
+    "mp_csr_to_sell": (C.c_int, [_VP, _VP, _VP, _VP]),
     "mp_scatter_matrix": (C.c_int, [_VP, _VP, _VP, _VP]),
     "mp_scatter_vector": (C.c_int, [_VP, _VP, _VP, C.c_double, _VP]),
     "mp_apply_dirichlet_sym": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),

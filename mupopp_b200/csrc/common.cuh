@@ -59,6 +59,7 @@ struct mp_ctx {
     double *d_partials = nullptr;       // [kMaxPartialBlocks * kMaxDots]
     cudaEvent_t ev = nullptr;
     // optional per-launch timing of the dominant kernel (SpMV) with CUDA events on ctx->stream
+    int spmv_variant = 0;   // 0 SELL-32 if mirrored else CTA-stream (default), 1 CTA-stream, 2 sub-warp-per-row, 3 warp-stream
     bool timing = false;
     std::vector<cudaEvent_t> tev;   // pairs (start, stop)
     size_t tev_used = 0;

@@ -116,12 +116,10 @@ int mp_ctx_create(int device, void *stream, mp_ctx **out) {
     MP_CUDA(cudaSetDevice(device));
     mp_ctx *c = new mp_ctx();
     c->device = device;
-    if (stream) {
-        c->stream = (cudaStream_t)stream;
-    } else {
-        MP_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-        c->own_stream = true;
-    }
+    // NULL = the CUDA default stream (what torch's default stream is): kernels are then ordered with the
+    // caller's torch copies on that stream without any extra synchronisation.
+    c->stream = (cudaStream_t)stream;
+    c->own_stream = false;
     cudaDeviceProp prop;
     MP_CUDA(cudaGetDeviceProperties(&prop, device));
     c->num_sm = prop.multiProcessorCount;
@@ -157,6 +155,13 @@ int mp_ctx_sync(mp_ctx *c) {
 }
 
 int64_t mp_ctx_launch_count(const mp_ctx *c) { return c ? c->launches : -1; }
+
+int mp_ctx_set_option(mp_ctx *c, const char *name, int value) {
+    MP_CHECK(c && name, "mp_ctx_set_option: null argument");
+    if (!strcmp(name, "spmv_variant")) { c->spmv_variant = value; return 0; }
+    mp::set_error("mp_ctx_set_option: unknown option '%s'", name);
+    return 2;
+}
 
 int mp_ctx_timing(mp_ctx *c, int enable, int max_samples) {
     MP_CHECK(c, "mp_ctx_timing: null ctx");

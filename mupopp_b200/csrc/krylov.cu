@@ -121,6 +121,134 @@ k_spmv(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restri
     if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
 }
 
+
+// ------------------------------------------------------------------ SpMV, CSR-stream variant (short, regular rows: P1 operators)
+// A CTA owns `rpb` consecutive rows.  Phase 1 streams the block's nonzeros fully coalesced (every load independent => deep
+// memory-level parallelism) and parks the products val*x[col] in shared memory; phase 2 sums each row's segment in a fixed
+// order with one thread per row.  Same DOT/GUARD modes as k_spmv.
+template <int DOT, bool GUARD>
+__global__ void __launch_bounds__(kThreads)
+k_spmv_stream(int64_t nrow, int rpb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+              const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
+              double *partials, unsigned int *counter, double *scal, int slot0, int slot1) {
+    if (GUARD && !solver_active(scal)) return;
+    extern __shared__ double prod[];
+    double acc[DOT == 0 ? 1 : DOT];
+#pragma unroll
+    for (int r = 0; r < (DOT == 0 ? 1 : DOT); ++r) acc[r] = 0.0;
+    (void)acc;
+    const int64_t nblk = (nrow + rpb - 1) / rpb;
+    for (int64_t blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+        const int64_t r0 = blk * rpb;
+        const int64_t r1 = min(r0 + (int64_t)rpb, nrow);
+        const int32_t k0 = rowptr[r0], k1 = rowptr[r1];
+#pragma unroll 4
+        for (int32_t k = k0 + threadIdx.x; k < k1; k += kThreads) prod[k - k0] = vals[k] * x[colidx[k]];
+        __syncthreads();
+        for (int64_t r = r0 + threadIdx.x; r < r1; r += kThreads) {
+            const int32_t b = rowptr[r] - k0, e = rowptr[r + 1] - k0;
+            double sum = 0.0;
+            for (int32_t k = b; k < e; ++k) sum += prod[k];
+            y[r] = sum;
+            if constexpr (DOT == 1) acc[0] += w[r] * sum;
+            if constexpr (DOT == 2) { acc[0] += sum * w[r]; acc[1] += sum * sum; }
+        }
+        __syncthreads();
+    }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, counter, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
+}
+
+// ------------------------------------------------------------------ SpMV, warp-stream variant (short regular rows: P1 operators)
+// Each warp owns tiles of 32 consecutive rows.  Phase 1: the lanes pull the tile's (col,val) pairs fully coalesced and park
+// them in the warp's private shared-memory strip (a transposition; no block barrier).  Phase 2: lane l walks row l of the
+// tile, so that at step j the 32 lanes gather x at 32 NEIGHBOURING columns (FEM rows of consecutive vertices are shifted
+// copies of one another): ~2-3 L1 wavefronts per gather instruction instead of ~18 when lanes hold consecutive nonzeros.
+// The L1 wavefront rate of the gather, not DRAM, was what bounded the nonzero-parallel variants (profiles/r1_spmv.md).
+template <int MAXJ, int DOT, bool GUARD>
+__global__ void __launch_bounds__(kThreads)
+k_spmv_warp(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
+            const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
+            double *partials, unsigned int *counter, double *scal, int slot0, int slot1) {
+    if (GUARD && !solver_active(scal)) return;
+    extern __shared__ double smem_d[];
+    const int lane = threadIdx.x & 31;
+    const int wib = threadIdx.x >> 5;
+    double *sval = smem_d + wib * (32 * MAXJ);
+    int32_t *scol = reinterpret_cast<int32_t *>(smem_d + (kThreads / 32) * (32 * MAXJ)) + wib * (32 * MAXJ);
+    double acc[DOT == 0 ? 1 : DOT];
+#pragma unroll
+    for (int r = 0; r < (DOT == 0 ? 1 : DOT); ++r) acc[r] = 0.0;
+    (void)acc;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    const int64_t ntile = (nrow + 31) >> 5;
+    for (int64_t tile = warp; tile < ntile; tile += nwarp) {
+        const int64_t row = (tile << 5) + lane;
+        const int32_t b = rowptr[row < nrow ? row : nrow];
+        const int32_t e = rowptr[row < nrow ? row + 1 : nrow];
+        const int32_t k0 = __shfl_sync(0xffffffffu, b, 0);
+        const int32_t k1 = __shfl_sync(0xffffffffu, e, 31);
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            const int32_t k = k0 + lane + 32 * j;
+            if (k < k1) {
+                scol[k - k0] = colidx[k];
+                sval[k - k0] = vals[k];
+            }
+        }
+        __syncwarp();
+        const int len = e - b, off = b - k0;
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j)
+            if (j < len) sum += sval[off + j] * x[scol[off + j]];
+        if (row < nrow) {
+            y[row] = sum;
+            if constexpr (DOT == 1) acc[0] += w[row] * sum;
+            if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
+        }
+        __syncwarp();
+    }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, counter, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
+}
+
+// ------------------------------------------------------------------ SpMV, SELL-32 (production kernel for P1 operators)
+// One lane per row; slice entries are stored [j][lane], so the (col,val) loads are perfectly coalesced and at step j the 32
+// lanes gather x at neighbouring columns.  Measured 0.26 ms at 200^3 (6.2 TB/s algorithmic, 94% of the measured copy peak)
+// against 0.34 ms for the best CSR variant (tools/spmv_lab.cu, profiles/r1_spmv_lab.txt).  __launch_bounds__(256, 8) keeps
+// 2048 resident threads per SM: the kernel is latency-bound below that.
+template <int DOT, bool GUARD>
+__global__ void __launch_bounds__(kThreads, 8)
+k_spmv_sell(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *__restrict__ scol, const double *__restrict__ sval,
+            const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
+            unsigned int *counter, double *scal, int slot0, int slot1) {
+    if (GUARD && !solver_active(scal)) return;
+    const int lane = threadIdx.x & 31;
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    const int64_t nslice = (nrow + 31) >> 5;
+    double acc[DOT == 0 ? 1 : DOT];
+#pragma unroll
+    for (int r = 0; r < (DOT == 0 ? 1 : DOT); ++r) acc[r] = 0.0;
+    (void)acc;
+    for (int64_t s = warp; s < nslice; s += nwarp) {
+        const int32_t b = sliceptr[s], e = sliceptr[s + 1];
+        double sum = 0.0;
+#pragma unroll 4
+        for (int32_t k = b + lane; k < e; k += 32) sum += sval[k] * x[scol[k]];
+        const int64_t row = (s << 5) + lane;
+        if (row < nrow) {
+            y[row] = sum;
+            if constexpr (DOT == 1) acc[0] += w[row] * sum;
+            if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
+        }
+    }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, counter, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
+}
+
 // ------------------------------------------------------------------ BLAS-1
 __global__ void __launch_bounds__(kThreads) k_axpby(int64_t n, double a, const double *__restrict__ x, double b, double *__restrict__ y) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x)
@@ -167,6 +295,7 @@ __global__ void __launch_bounds__(kThreads) k_init_residual(int64_t n, const dou
 }
 
 // CG: alpha = rz/pq ; x += alpha p ; r -= alpha q ; rz' = r.(dinv r) ; rr = r.r ; iter++
+// (4 independent element groups per thread and trip => 20 loads in flight per thread)
 __global__ void __launch_bounds__(kThreads) k_cg_update(int64_t n, const double *__restrict__ p, const double *__restrict__ q,
                                                         const double *__restrict__ dinv, double *__restrict__ x,
                                                         double *__restrict__ r, double *partials, unsigned int *counter,
@@ -174,12 +303,25 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int64_t n, const double 
     if (!solver_active(scal)) return;
     const double alpha = safe_div(scal[rz_cur], scal[S_PQ]);
     double acc[2] = {0.0, 0.0};
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
-        x[i] += alpha * p[i];
-        const double ri = r[i] - alpha * q[i];
-        r[i] = ri;
-        acc[0] += ri * ri * dinv[i];
-        acc[1] += ri * ri;
+    const int64_t stride = gridDim.x * (int64_t)blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double pp[4], qq[4], dd[4], xx[4], rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) { pp[u] = p[i]; qq[u] = q[i]; dd[u] = dinv[i]; xx[u] = x[i]; rr[u] = r[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) {
+                x[i] = xx[u] + alpha * pp[u];
+                const double ri = rr[u] - alpha * qq[u];
+                r[i] = ri;
+                acc[0] += ri * ri * dd[u];
+                acc[1] += ri * ri;
+            }
+        }
     }
     const int sl_[2] = {rz_nxt, S_RR};
     grid_reduce<2>(acc, partials, counter, scal, sl_, true);
@@ -190,8 +332,20 @@ __global__ void __launch_bounds__(kThreads) k_cg_pupdate(int64_t n, const double
                                                          double *__restrict__ p, const double *scal, int rz_cur, int rz_nxt) {
     if (!solver_active(scal)) return;
     const double beta = safe_div(scal[rz_nxt], scal[rz_cur]);
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x)
-        p[i] = dinv[i] * r[i] + beta * p[i];
+    const int64_t stride = gridDim.x * (int64_t)blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+        double rr[4], dd[4], pp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) { rr[u] = r[i]; dd[u] = dinv[i]; pp[u] = p[i]; }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i < n) p[i] = dd[u] * rr[u] + beta * pp[u];
+        }
+    }
 }
 
 // BiCGStab A: beta = rho'/rv * tt/ts ; omega = ts/tt ; p = r + beta (p - omega v) ; y = dinv p
@@ -259,12 +413,78 @@ int pick_lanes(const mp_csr *A, int64_t nnz_hint) {
     return 32;
 }
 
+constexpr int kStreamCap = 2048;  // products (doubles) parked in shared memory per CTA
+
 template <int DOT, bool GUARD>
 int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double *y, const double *w, int slot0, int slot1) {
     if (A->nrow == 0) return 0;
     int grid = grid_for(ctx, A->nrow * lanes);
     const bool timed = ctx->timing && ctx->tev_used + 2 <= ctx->tev.size();
     if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
+    const double avg = (double)A->nnz / (double)A->nrow;
+    if (A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0) {
+        const int64_t nslice = (A->nrow + 31) / 32;
+        int64_t nblk = (nslice + (kThreads / 32) - 1) / (kThreads / 32);
+        int64_t cap = (int64_t)ctx->num_sm * 8;
+        if (cap > kMaxBlocks) cap = kMaxBlocks;
+        const int g = (int)(nblk < cap ? nblk : cap);
+        k_spmv_sell<DOT, GUARD><<<g, kThreads, 0, ctx->stream>>>(A->nrow, A->d_sell_sliceptr, A->d_sell_col, A->d_sell_val, x, y, w,
+                                                                  ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1);
+        if (timed) {
+            cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
+            ctx->tev_used += 2;
+        }
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (ctx->spmv_variant == 3 && A->max_row_nnz > 0 && A->max_row_nnz <= 32 && A->max_row_nnz <= 3.0 * avg + 2.0) {
+        // warp-stream kernel: MAXJ = row-length bound rounded up to 8/16/32
+        const int maxj = A->max_row_nnz <= 8 ? 8 : (A->max_row_nnz <= 16 ? 16 : 32);
+        const size_t smem = (sizeof(double) + sizeof(int32_t)) * 32 * (size_t)maxj * (kThreads / 32);
+        const int64_t ntile = (A->nrow + 31) / 32;
+        int64_t nblk = (ntile + (kThreads / 32) - 1) / (kThreads / 32);
+        const int per_sm = maxj == 8 ? 8 : (maxj == 16 ? 6 : 3);   // CTAs resident per SM (registers / shared memory)
+        int64_t cap = (int64_t)ctx->num_sm * per_sm;
+        int g = (int)(nblk < cap ? nblk : cap);
+#define LW(MJ)                                                                                                              \
+        do {                                                                                                                \
+            static bool attr_set = false;                                                                                   \
+            if (!attr_set) {                                                                                                \
+                MP_CUDA(cudaFuncSetAttribute(k_spmv_warp<MJ, DOT, GUARD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                attr_set = true;                                                                                            \
+            }                                                                                                               \
+            k_spmv_warp<MJ, DOT, GUARD><<<g, kThreads, smem, ctx->stream>>>(A->nrow, A->d_rowptr, A->d_colidx, A->d_vals, x, y, w, \
+                                                                             ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1); \
+        } while (0)
+        if (maxj == 8) LW(8); else if (maxj == 16) LW(16); else LW(32);
+#undef LW
+        if (timed) {
+            cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
+            ctx->tev_used += 2;
+        }
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        return 0;
+    }
+    if (ctx->spmv_variant <= 1 && A->max_row_nnz > 0 && A->max_row_nnz <= 32 && A->max_row_nnz <= 3.0 * avg + 2.0) {
+        int rpb = kStreamCap / A->max_row_nnz;
+        if (rpb > kThreads) rpb = kThreads;
+        rpb &= ~31;
+        const size_t smem = sizeof(double) * (size_t)rpb * A->max_row_nnz;
+        int64_t nblk = (A->nrow + rpb - 1) / rpb;
+        int64_t cap = (int64_t)ctx->num_sm * 8;
+        int g = (int)(nblk < cap ? nblk : cap);
+        k_spmv_stream<DOT, GUARD><<<g, kThreads, smem, ctx->stream>>>(A->nrow, rpb, A->d_rowptr, A->d_colidx, A->d_vals, x, y, w,
+                                                                       ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1);
+        if (timed) {
+            cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
+            ctx->tev_used += 2;
+        }
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        return 0;
+    }
 #define L(S_)                                                                                                           \
     k_spmv<S_, DOT, GUARD><<<grid, kThreads, 0, ctx->stream>>>(A->nrow, A->d_rowptr, A->d_colidx, A->d_vals, x, y, w,  \
                                                                 ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1)

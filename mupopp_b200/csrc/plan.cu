@@ -18,6 +18,9 @@ struct mp_plan {
     int32_t *d_inc = nullptr;      // [ninc]  id = cell*lr + li, ascending per row
     uint16_t *d_slot = nullptr;    // [ncell*lr*lc] offset of (row(cell,li), col(cell,j)) inside its CSR row
     int64_t ninc = 0;
+    int32_t *d_sell_ptr = nullptr; // [nslice+1] SELL-32 slice offsets (entries)
+    int32_t *d_sell_col = nullptr; // [nsell]
+    int64_t nslice = 0, nsell = 0;
     int rows_per_block = 128;      // scatter kernel tiling: nnz of a row block must fit in shared memory
     int smem_doubles = 0;
     int max_row_nnz = 0;
@@ -92,6 +95,34 @@ __global__ void k_max_rowlen(const int32_t *__restrict__ rowptr, int32_t nrow, i
     if ((threadIdx.x & 31) == 0 && v > 0) atomicMax(out, v);
 }
 
+// SELL-32: per-slice width = longest row of the slice
+__global__ void k_sell_width(const int32_t *__restrict__ rowptr, int32_t nrow, int64_t nslice, int32_t *width32) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslice) return;
+    const int64_t r = s * 32 + lane;
+    int v = r < nrow ? rowptr[r + 1] - rowptr[r] : 0;
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) width32[s] = 32 * v;
+}
+
+// fill SELL columns (padding: the row itself) or values (padding: 0)
+template <bool VALS>
+__global__ void k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+                            int32_t nrow, int64_t nslice, const int32_t *__restrict__ sell_ptr, int32_t *__restrict__ scol,
+                            double *__restrict__ sval) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslice) return;
+    const int64_t r = s * 32 + lane;
+    const int32_t b = sell_ptr[s], w = (sell_ptr[s + 1] - b) >> 5;
+    const int32_t rb = r < nrow ? rowptr[r] : 0, len = r < nrow ? rowptr[r + 1] - rb : 0;
+    for (int j = 0; j < w; ++j) {
+        if (VALS) sval[b + 32 * j + lane] = j < len ? vals[rb + j] : 0.0;
+        else scol[b + 32 * j + lane] = j < len ? colidx[rb + j] : (int32_t)(r < nrow ? r : 0);
+    }
+}
+
 // One CTA owns a contiguous block of rows; its CSR value segment is accumulated in shared memory
 // (each thread owns one row => no conflicts, fixed summation order) and written back coalesced.
 template <int LC>
@@ -151,11 +182,13 @@ k_scatter_vector(const int32_t *__restrict__ inc_ptr, const int32_t *__restrict_
 extern "C" int mp_plan_destroy(mp_plan *p) {
     if (!p) return 0;
     cudaFree(p->d_rowptr); cudaFree(p->d_colidx); cudaFree(p->d_inc_ptr); cudaFree(p->d_inc); cudaFree(p->d_slot);
+    cudaFree(p->d_sell_ptr); cudaFree(p->d_sell_col);
     delete p;
     return 0;
 }
 
 extern "C" int64_t mp_plan_nnz(const mp_plan *p) { return p ? p->nnz : -1; }
+extern "C" int32_t mp_plan_max_row_nnz(const mp_plan *p) { return p ? p->max_row_nnz : -1; }
 
 extern "C" int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr, const int32_t *d_col_dofs, int32_t lc,
                               int64_t ncell, int64_t nrow, int64_t ncol, mp_plan **out) {
@@ -300,6 +333,31 @@ extern "C" int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr
         if (rpb < 1) { mp::set_error("mp_plan_create: row with %d entries does not fit the scatter tile", mx); cleanup(); mp_plan_destroy(p); return 2; }
         p->rows_per_block = rpb;
         p->smem_doubles = rpb * (mx > 0 ? mx : 1);
+        // ---- 4. SELL-32 mirror of the pattern (SpMV layout)
+        p->nslice = (nrow + 31) / 32;
+        int32_t *width = nullptr;
+        PC(cudaMalloc(&width, sizeof(int32_t) * (p->nslice + 1)));
+        PC(cudaMemsetAsync(width, 0, sizeof(int32_t) * (p->nslice + 1), st));
+        k_sell_width<<<(unsigned)cdiv(p->nslice * 32, kThreads), kThreads, 0, st>>>(p->d_rowptr, (int32_t)nrow, p->nslice, width);
+        mp::count_launch(ctx);
+        PC(cudaMalloc(&p->d_sell_ptr, sizeof(int32_t) * (p->nslice + 1)));
+        {
+            size_t tb = 0;
+            PC(cub::DeviceScan::ExclusiveSum(nullptr, tb, width, p->d_sell_ptr, (int)(p->nslice + 1), st));
+            PC(cudaMalloc(&tmp, tb + 16));
+            PC(cub::DeviceScan::ExclusiveSum(tmp, tb, width, p->d_sell_ptr, (int)(p->nslice + 1), st));
+            cudaFree(tmp); tmp = nullptr;
+        }
+        int32_t nsell = 0;
+        PC(cudaMemcpyAsync(&nsell, p->d_sell_ptr + p->nslice, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        PC(cudaStreamSynchronize(st));
+        cudaFree(width);
+        p->nsell = nsell;
+        PC(cudaMalloc(&p->d_sell_col, sizeof(int32_t) * (size_t)(nsell > 0 ? nsell : 1)));
+        k_sell_fill<false><<<(unsigned)cdiv(p->nslice * 32, kThreads), kThreads, 0, st>>>(p->d_rowptr, p->d_colidx, nullptr, (int32_t)nrow,
+                                                                                          p->nslice, p->d_sell_ptr, p->d_sell_col, nullptr);
+        mp::count_launch(ctx);
+        PC(cudaStreamSynchronize(st));
     }
 #undef PC
     cleanup();
@@ -338,6 +396,25 @@ extern "C" int mp_scatter_vector(mp_ctx *ctx, const mp_plan *p, const double *d_
     MP_CHECK(ctx && p && d_elem_vec && d_out, "mp_scatter_vector: bad argument");
     k_scatter_vector<<<(unsigned)cdiv(p->nrow, kThreads), kThreads, 0, ctx->stream>>>(p->d_inc_ptr, p->d_inc, d_elem_vec, beta,
                                                                                        d_out, (int32_t)p->nrow);
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp_plan_sell_info(const mp_plan *p, int64_t *nslice, int64_t *nentries, const int32_t **d_sliceptr, const int32_t **d_col) {
+    MP_CHECK(p && p->lc > 0 && p->d_sell_ptr, "mp_plan_sell_info: plan has no matrix pattern");
+    if (nslice) *nslice = p->nslice;
+    if (nentries) *nentries = p->nsell;
+    if (d_sliceptr) *d_sliceptr = p->d_sell_ptr;
+    if (d_col) *d_col = p->d_sell_col;
+    return 0;
+}
+
+extern "C" int mp_csr_to_sell(mp_ctx *ctx, const mp_plan *p, const double *d_csr_vals, double *d_sell_vals) {
+    MP_CHECK(ctx && p && p->d_sell_ptr && d_csr_vals && d_sell_vals, "mp_csr_to_sell: bad argument");
+    if (p->nsell == 0) return 0;
+    k_sell_fill<true><<<(unsigned)cdiv(p->nslice * 32, kThreads), kThreads, 0, ctx->stream>>>(p->d_rowptr, p->d_colidx, d_csr_vals, (int32_t)p->nrow,
+                                                                                               p->nslice, p->d_sell_ptr, nullptr, d_sell_vals);
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
     return 0;

@@ -46,6 +46,9 @@ class Context:
     def launch_count(self):
         return int(self.lib.mp_ctx_launch_count(self.h))
 
+    def set_option(self, name, value):
+        check(self.lib.mp_ctx_set_option(self.h, name.encode(), int(value)), "mp_ctx_set_option")
+
     def timing(self, enable, max_samples=4096):
         check(self.lib.mp_ctx_timing(self.h, 1 if enable else 0, max_samples), "mp_ctx_timing")
 
@@ -115,6 +118,7 @@ class Plan:
               "mp_plan_create")
         self.h = h
         self.nnz = int(ctx.lib.mp_plan_nnz(h)) if self.lc else 0
+        self.max_row_nnz = int(ctx.lib.mp_plan_max_row_nnz(h)) if self.lc else 0
         self._csr = None
 
     def __del__(self):
@@ -133,27 +137,49 @@ class Plan:
             self._csr = (rowptr, colidx[: self.nnz])
         return self._csr
 
-    def new_matrix(self):
+    def sell_info(self):
+        ns, ne, sp, sc = C.c_int64(), C.c_int64(), C.c_void_p(), C.c_void_p()
+        check(self.ctx.lib.mp_plan_sell_info(self.h, C.byref(ns), C.byref(ne), C.byref(sp), C.byref(sc)), "mp_plan_sell_info")
+        return ns.value, ne.value, sp.value, sc.value
+
+    def new_matrix(self, sell=True):
         rowptr, colidx = self.csr_pattern()
-        return CsrMatrix(self.ctx, self.nrow, self.ncol, rowptr, colidx, self.ctx.zeros(self.nnz))
+        return CsrMatrix(self.ctx, self.nrow, self.ncol, rowptr, colidx, self.ctx.zeros(self.nnz), self.max_row_nnz,
+                         plan=self if sell else None)
 
     def scatter_matrix(self, elem_mat, A):
         check(self.ctx.lib.mp_scatter_matrix(self.ctx.h, self.h, ptr(elem_mat), ptr(A.vals)), "mp_scatter_matrix")
+        A.sell_dirty = True
 
     def scatter_vector(self, elem_vec, out, beta=0.0):
         check(self.ctx.lib.mp_scatter_vector(self.ctx.h, self.h, ptr(elem_vec), beta, ptr(out)), "mp_scatter_vector")
 
 
 class CsrMatrix:
-    def __init__(self, ctx, nrow, ncol, rowptr, colidx, vals):
+    def __init__(self, ctx, nrow, ncol, rowptr, colidx, vals, max_row_nnz=0, plan=None):
         self.ctx = ctx
         self.nrow, self.ncol = int(nrow), int(ncol)
         self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
         self.nnz = int(vals.numel())
-        self.c = MpCsr(self.nrow, self.ncol, self.nnz, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr())
+        self.plan = plan
+        self.sell_vals, self.sell_dirty = None, True
+        sp = sc = sv = None
+        if plan is not None and plan.lc > 0:
+            _, nent, sp, sc = plan.sell_info()
+            self.sell_vals = ctx.zeros(max(nent, 1))
+            sv = self.sell_vals.data_ptr()
+        self.c = MpCsr(self.nrow, self.ncol, self.nnz, int(max_row_nnz), 0, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(),
+                       sp, sc, sv)
         self.dinv = None
 
+    def sync_sell(self):
+        """Refresh the SELL-32 mirror used by SpMV after the CSR values changed (assembly / Dirichlet)."""
+        if self.sell_vals is not None and self.sell_dirty:
+            check(self.ctx.lib.mp_csr_to_sell(self.ctx.h, self.plan.h, ptr(self.vals), ptr(self.sell_vals)), "mp_csr_to_sell")
+            self.sell_dirty = False
+
     def spmv(self, x, y):
+        self.sync_sell()
         check(self.ctx.lib.mp_spmv(self.ctx.h, C.byref(self.c), ptr(x), ptr(y)), "mp_spmv")
         return y
 
@@ -167,6 +193,8 @@ class CsrMatrix:
         check(self.ctx.lib.mp_apply_dirichlet_sym(self.ctx.h, self.nrow, ptr(self.rowptr), ptr(self.colidx),
                                                   ptr(self.vals) if matrix else None, ptr(rhs), ptr(isbc), ptr(g)),
               "mp_apply_dirichlet_sym")
+        if matrix:
+            self.sell_dirty = True
 
     def to_scipy(self):
         """Test helper: copy to host as scipy CSR."""
@@ -177,6 +205,7 @@ class CsrMatrix:
     def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True, restart=50):
         if self.dinv is None or refresh_jacobi:
             self.jacobi_setup()
+        self.sync_sell()
         info = MpSolveInfo(rtol, atol, int(maxit), int(check_every), 0, 0, 0.0)
         hh = halo.h if halo is not None else None
         if method == "gmres":
