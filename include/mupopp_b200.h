@@ -87,9 +87,9 @@ typedef struct {
     double frac[3];              /* R1,R2,R3 prefactors: mupopp.py:818-821, :925-931, :1222-1229 */
     double zhat[3];
     double Kconst;               /* used when d_K == NULL */
-    int32_t reaction;            /* 0: Da*c0*c1 (CCS)   1: Da*c0*c1^2 (DarcyAdvection) */
-    int32_t ncomp;               /* 2 or 3 concentration fields */
-    int32_t supg;                /* 1 Sendur, 2 Codina, 3 Brooks-Hughes: mupopp.py:835-846 */
+    int32_t reaction;            /* 0: Da*c0*c1 (CCS)   1: Da*c0*c1^2 (DarcyAdvection)   2: Da*c0 (single component, mupopp.py:650) */
+    int32_t ncomp;               /* 1 (quadrature kernel only), 2 or 3 concentration fields */
+    int32_t supg;                /* 1 Sendur, 2 Codina, 3 Brooks-Hughes: mupopp.py:835-846; 4: h/(2|w|) (mupopp.py:663) */
     int32_t pad;
 } mp_transport_params;
 
@@ -115,6 +115,27 @@ int mp_elem_p1_pressure_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport
 int mp_recover_velocity(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_K,
                         const double *d_p, const double *d_c0, double *d_ucell);
 
+/* Generic affine element kernel ("tensor representation"): elem_mat[c][i][j] = scale * sum_t geo_t(c) * T0[t][i][j]
+ *   kind 0 MASS  (1 tensor,  geo = |detJ|)                      kind 1 GRAD  (dim tensors, geo_a = |detJ| Jinv[a][dir]: row value x column d/dx_dir)
+ *   kind 2 GRADT (as GRAD with row derivative x column value)   kind 3 STIFF (dim^2 tensors, geo_ab = |detJ| (Jinv Jinv^T)_ab)
+ * coef_kind 0 none | 1 nodal P1 d_coef[nvert], integrated exactly (T0 then has (dim+1) sub-tensors per t) | 2 cellwise d_coef[ncell].
+ * T0 comes from mupopp_b200/reference_element.py.  Mode R operators: P2 mass u.v, K div(v) p, div(u) q (mupopp.py:620,804-807,1201-1204). */
+int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
+                      const double *d_coef, int coef_kind, double scale, double *d_elem_mat);
+
+/* quadrature tables (device): weights [nq] (sum = 1/dim!), barycentric coordinates [nq][dim+1], velocity basis values [nq][nbv] */
+typedef struct {
+    int32_t nq, nbv;
+    const double *d_w, *d_lam, *d_vphi;
+} mp_quad;
+/* c0 row by numerical quadrature with a Lagrange (P1/P2) lagged velocity given per component (mode R); d_vel_dofs [ncell][nbv].
+ * prm->ncomp may be 1 with prm->reaction == 2 (first order Da*c) and prm->supg == 4 (tau = h/(2|w|)):
+ * DarcyAdvection.advection_diffusion, mupopp.py:650-664. */
+int mp_elem_p1_transport_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const mp_quad *quad,
+                              const int32_t *d_vel_dofs, const double *d_vel0, const double *d_vel1, const double *d_vel2,
+                              const double *d_c0n, const double *d_c1n, const double *d_c2n, const double *d_c1new,
+                              const double *d_c2new, const double *d_fsrc, double *d_elem_mat, double *d_elem_vec);
+
 /* ------------------------------------------------------------------ linear algebra (PETSc Mat/Vec/KSP replacement)
  * Call sites replaced: KrylovSolver(...).solve modules/mupopp.py:289-303,410-425; the LU inside solve(a==L,..). */
 typedef struct {
@@ -136,6 +157,7 @@ typedef struct {
 int mp_spmv(mp_ctx *ctx, const mp_csr *A, const double *d_x, double *d_y);
 int mp_dot(mp_ctx *ctx, int64_t n, const double *d_x, const double *d_y, double *result);      /* host result; allreduced if a communicator is attached */
 int mp_axpby(mp_ctx *ctx, int64_t n, double a, const double *d_x, double b, double *d_y);      /* y = a x + b y */
+ int mp_vmul(mp_ctx *ctx, int64_t n, double a, const double *d_x, const double *d_y, double *d_z);   /* z = a * x .* y (Jacobi apply) */
 int mp_jacobi_setup(mp_ctx *ctx, const mp_csr *A, double *d_dinv);                             /* dinv = 1/diag(A) */
 
 typedef struct {

@@ -32,6 +32,10 @@ class MpTransportParams(C.Structure):
                 ("reaction", C.c_int32), ("ncomp", C.c_int32), ("supg", C.c_int32), ("pad", C.c_int32)]
 
 
+class MpQuad(C.Structure):
+    _fields_ = [("nq", C.c_int32), ("nbv", C.c_int32), ("d_w", C.c_void_p), ("d_lam", C.c_void_p), ("d_vphi", C.c_void_p)]
+
+
 class MpCsr(C.Structure):
     _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nnz", C.c_int64), ("max_row_nnz", C.c_int32), ("pad", C.c_int32),
                 ("d_rowptr", C.c_void_p), ("d_colidx", C.c_void_p), ("d_vals", C.c_void_p),
@@ -72,9 +76,13 @@ SIGNATURES = {
     "mp_elem_p1_adr_single": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_double, C.c_double, C.c_double, _VP, _VP, _VP, _VP]),
     "mp_elem_p1_pressure_rhs": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, _VP]),
     "mp_recover_velocity": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, _VP, _VP]),
+    "mp_elem_reftensor": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int, C.c_double, _VP]),
+    "mp_elem_p1_transport_quad": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), C.POINTER(MpQuad), _VP, _VP, _VP, _VP,
+                                            _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mp_spmv": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP]),
     "mp_dot": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.POINTER(C.c_double)]),
     "mp_axpby": (C.c_int, [_VP, C.c_int64, C.c_double, _VP, C.c_double, _VP]),
+    "mp_vmul": (C.c_int, [_VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
     "mp_jacobi_setup": (C.c_int, [_VP, C.POINTER(MpCsr), _VP]),
     "mp_solve_pcg": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_solve_bicgstab": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),

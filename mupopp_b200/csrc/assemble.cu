@@ -472,6 +472,193 @@ __global__ void __launch_bounds__(kThreads) k_recover_velocity(mp_mesh m, mp_tra
     }
 }
 
+
+// ------------------------------------------------------------------ generic affine "reference tensor" element kernel
+// A_e[i][j] = scale * sum_t geo_t(cell) * T0[t][i][j]   (FFC's tensor representation): P2 mass, P1xP2 divergence/gradient blocks,
+// stiffness, with an optional exact nodal-P1 or cellwise coefficient.  Used for the mixed (mode R) operators of
+// DarcyAdvection.darcy_bilinear (mupopp.py:620: u.v, K div(v) p, div(u) q) and the Darcy rows of the monolithic forms (:807, :1204).
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_reftensor(mp_mesh m, int kind, int dir, int L, const double *__restrict__ T0,
+                                                        const double *__restrict__ coef, int coef_kind, double scale,
+                                                        double *__restrict__ emat) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double detJ = G.vol;
+#pragma unroll
+    for (int k = 2; k <= D; ++k) detJ *= k;
+    double geo[D * D];
+    int nT;
+    if (kind == 0) { nT = 1; geo[0] = detJ; }
+    else if (kind == 1 || kind == 2) {
+        nT = D;
+#pragma unroll
+        for (int a = 0; a < D; ++a) geo[a] = detJ * G.g[a + 1][dir];
+    } else {
+        nT = D * D;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+                double t = 0.0;
+#pragma unroll
+                for (int i = 0; i < D; ++i) t += G.g[a + 1][i] * G.g[b + 1][i];
+                geo[a * D + b] = detJ * t;
+            }
+    }
+    double *dst = emat + c * (int64_t)L;
+    if (coef_kind == 1) {
+        double Kv[D + 1];
+#pragma unroll
+        for (int v = 0; v <= D; ++v) Kv[v] = coef[G.v[v]];
+        for (int e = 0; e < L; ++e) {
+            double sum = 0.0;
+            for (int t = 0; t < nT; ++t) {
+                double inner = 0.0;
+#pragma unroll
+                for (int v = 0; v <= D; ++v) inner += Kv[v] * T0[((int64_t)t * (D + 1) + v) * L + e];
+                sum += geo[t] * inner;
+            }
+            dst[e] = scale * sum;
+        }
+    } else {
+        const double f = coef_kind == 2 ? scale * coef[c] : scale;
+        for (int e = 0; e < L; ++e) {
+            double sum = 0.0;
+            for (int t = 0; t < nT; ++t) sum += geo[t] * T0[(int64_t)t * L + e];
+            dst[e] = f * sum;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ c0 row with numerical quadrature (mode R)
+// Same form as k_p1_transport, but the lagged velocity is a continuous Lagrange field (P2 in the reference's mixed space,
+// run/CCS2D/CCS_3comp.py:206-212) evaluated at the quadrature points, so tau(|u|,h) is non-polynomial and the shared
+// quadrature table (SURVEY.md finding 7) is part of the parity contract.  ncomp==1 / reaction==2 / supg==4 give
+// DarcyAdvection.advection_diffusion (mupopp.py:650-664).
+struct QuadView {
+    int nq, nbv;
+    const double *w, *lam, *vphi;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_transport_quad(mp_mesh m, mp_transport_params P, QuadView Q,
+                                                                const int32_t *__restrict__ vdofs, const double *__restrict__ v0,
+                                                                const double *__restrict__ v1, const double *__restrict__ v2,
+                                                                const double *__restrict__ c0n, const double *__restrict__ c1n,
+                                                                const double *__restrict__ c2n, const double *__restrict__ c1new,
+                                                                const double *__restrict__ c2new, const double *__restrict__ fsrc,
+                                                                double *__restrict__ emat, double *__restrict__ evec) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double detJ = G.vol;
+#pragma unroll
+    for (int k = 2; k <= D; ++k) detJ *= k;
+    const double dt = P.dt;
+    double a0[D + 1], a1[D + 1], a2[D + 1], n1[D + 1], n2[D + 1], f[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) { a0[i] = a1[i] = a2[i] = n1[i] = n2[i] = f[i] = 0.0; }
+    if (evec) {
+        gather<D>(c0n, G, a0);
+        if (fsrc) gather<D>(fsrc, G, f);
+        if (P.ncomp >= 2) { gather<D>(c1n, G, a1); gather<D>(c1new, G, n1); }
+        if (P.ncomp == 3) { gather<D>(c2n, G, a2); gather<D>(c2new, G, n2); }
+    }
+    double gc0[D], gg[D + 1][D + 1];
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        gc0[a] = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) gc0[a] += a0[i] * G.g[i][a];
+    }
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+        for (int j = 0; j <= D; ++j) {
+            double t = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) t += G.g[i][a] * G.g[j][a];
+            gg[i][j] = t;
+        }
+    double A[D + 1][D + 1], b[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+        b[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j <= D; ++j) A[i][j] = 0.0;
+    }
+    const int32_t *vd = vdofs + c * (int64_t)Q.nbv;
+    const double kR1 = dt * P.frac[0] * P.Da / P.phi;
+    const double kR2 = dt * P.frac[1] * P.Da / (1.0 - P.phi);
+    const double kR3 = dt * P.frac[2] * P.Da / (1.0 - P.phi);
+    for (int q = 0; q < Q.nq; ++q) {
+        const double w = Q.w[q] * detJ;
+        double lam[D + 1];
+#pragma unroll
+        for (int i = 0; i <= D; ++i) lam[i] = Q.lam[q * (D + 1) + i];
+        double u[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) u[a] = 0.0;
+        for (int k = 0; k < Q.nbv; ++k) {
+            const double ph = Q.vphi[q * Q.nbv + k];
+            const int32_t dk = vd[k];
+            u[0] += ph * v0[dk];
+            u[1] += ph * v1[dk];
+            if (D == 3) u[D - 1] += ph * v2[dk];
+        }
+        double vn2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) vn2 += u[a] * u[a];
+        const double vn = sqrt(vn2);
+        const double tau = P.supg == 4 ? G.h / (2.0 * vn) : tau_supg(P.supg, P.Pe, P.Da, G.h, vn);
+        double ug[D + 1];
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) t += u[a] * G.g[i][a];
+            ug[i] = t;
+        }
+        if (emat) {
+#pragma unroll
+            for (int i = 0; i <= D; ++i)
+#pragma unroll
+                for (int j = 0; j <= D; ++j)
+                    A[i][j] += w * (lam[i] * lam[j] + 0.5 * dt * lam[i] * ug[j] + 0.5 * dt / P.Pe * gg[i][j] +
+                                    tau * ug[i] * (lam[j] + 0.5 * dt * ug[j]));
+        }
+        if (evec) {
+            double c0q = 0.0, c1q = 0.0, c2q = 0.0, n1q = 0.0, n2q = 0.0, fq = 0.0, ugc0 = 0.0;
+#pragma unroll
+            for (int i = 0; i <= D; ++i) {
+                c0q += lam[i] * a0[i]; c1q += lam[i] * a1[i]; c2q += lam[i] * a2[i];
+                n1q += lam[i] * n1[i]; n2q += lam[i] * n2[i]; fq += lam[i] * f[i];
+                ugc0 += ug[i] * a0[i];
+            }
+            const double R = P.reaction == 2 ? P.Da * c0q : (P.reaction == 0 ? P.Da * c0q * c1q : P.Da * c0q * c1q * c1q);
+            // dt*R for the single-component form (mupopp.py:650: f = Da*u0), dt*frac0*R/phi otherwise (mupopp.py:825)
+            const double R1 = P.reaction == 2 ? dt * R : kR1 / P.Da * R;
+            const double gal = c0q - 0.5 * dt * ugc0 - R1 + P.beta * dt * fq;
+            double rk = -c0q + 0.5 * dt * ugc0 + R1 - P.beta * dt * fq;
+            double cpl = 0.0;
+            if (P.ncomp >= 2) { rk += -c1q + kR2 / P.Da * R; cpl += n1q; }
+            if (P.ncomp == 3) { rk += -c2q - kR3 / P.Da * R; cpl += n2q; }
+#pragma unroll
+            for (int i = 0; i <= D; ++i) {
+                double gd = 0.0;
+#pragma unroll
+                for (int a = 0; a < D; ++a) gd += G.g[i][a] * gc0[a];
+                b[i] += w * (lam[i] * gal - 0.5 * dt / P.Pe * gd - tau * ug[i] * (rk + cpl));
+            }
+        }
+    }
+    if (emat) store_mat<D>(emat, c, A);
+    if (evec) store_vec<D>(evec, c, b);
+}
+
 // Symmetric Dirichlet elimination, 8 lanes per row, fixed reduction order.
 __global__ void __launch_bounds__(256) k_dirichlet(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                                                    double *__restrict__ vals, double *__restrict__ rhs,
@@ -584,5 +771,30 @@ extern "C" int mp_apply_dirichlet_sym(mp_ctx *ctx, int64_t nrow, const int32_t *
     k_dirichlet<<<(unsigned)cdiv(nrow * 8, 256), 256, 0, ctx->stream>>>(nrow, d_rowptr, d_colidx, d_vals, d_rhs, d_isbc, d_g);
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
+                                 const double *d_coef, int coef_kind, double scale, double *d_elem_mat) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(kind >= 0 && kind <= 3 && dir >= 0 && dir < mesh->dim && lr > 0 && lc > 0 && d_T0 && d_elem_mat, "mp_elem_reftensor: bad argument");
+    MP_CHECK(coef_kind == 0 || d_coef, "mp_elem_reftensor: coefficient pointer is null");
+    DISPATCH_DIM(mesh, k_reftensor, kind, dir, lr * lc, d_T0, d_coef, coef_kind, scale, d_elem_mat);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_transport_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const mp_quad *quad,
+                                         const int32_t *d_vel_dofs, const double *d_vel0, const double *d_vel1, const double *d_vel2,
+                                         const double *d_c0n, const double *d_c1n, const double *d_c2n, const double *d_c1new,
+                                         const double *d_c2new, const double *d_fsrc, double *d_elem_mat, double *d_elem_vec) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(prm && quad && quad->nq > 0 && quad->nbv > 0 && quad->d_w && quad->d_lam && quad->d_vphi, "mp_elem_p1_transport_quad: bad quadrature");
+    MP_CHECK(d_vel_dofs && d_vel0 && d_vel1 && (mesh->dim == 2 || d_vel2), "mp_elem_p1_transport_quad: velocity pointers");
+    MP_CHECK(!d_elem_vec || d_c0n, "mp_elem_p1_transport_quad: rhs needs c0n");
+    MP_CHECK(!d_elem_vec || prm->ncomp < 2 || (d_c1n && d_c1new), "mp_elem_p1_transport_quad: ncomp>=2 needs c1n,c1new");
+    MP_CHECK(!d_elem_vec || prm->ncomp < 3 || (d_c2n && d_c2new), "mp_elem_p1_transport_quad: ncomp==3 needs c2n,c2new");
+    QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
+    DISPATCH_DIM(mesh, k_p1_transport_quad, *prm, Q, d_vel_dofs, d_vel0, d_vel1, d_vel2 ? d_vel2 : d_vel1, d_c0n, d_c1n, d_c2n, d_c1new,
+                 d_c2new, d_fsrc, d_elem_mat, d_elem_vec);
     return 0;
 }

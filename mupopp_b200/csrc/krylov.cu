@@ -255,6 +255,11 @@ __global__ void __launch_bounds__(kThreads) k_axpby(int64_t n, double a, const d
         y[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];
 }
 
+__global__ void __launch_bounds__(kThreads) k_vmul(int64_t n, double a, const double *__restrict__ x, const double *__restrict__ y,
+                                                   double *__restrict__ z) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) z[i] = a * x[i] * y[i];
+}
+
 __global__ void __launch_bounds__(kThreads) k_dot(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
                                                   double *partials, unsigned int *counter, double *scal, int slot) {
     double acc[1] = {0.0};
@@ -517,9 +522,10 @@ int poll(mp_ctx *ctx) {
     return 0;
 }
 
-int check_csr(const mp_csr *A) {
+int check_csr(const mp_csr *A, bool for_solver = true) {
     MP_CHECK(A && A->d_rowptr && A->d_colidx && A->d_vals, "csr: null pointer");
-    MP_CHECK(A->nrow >= 0 && A->ncol >= A->nrow, "csr: need ncol >= nrow >= 0 (owned rows first, then ghosts)");
+    MP_CHECK(A->nrow >= 0 && A->ncol >= 0, "csr: negative size");
+    MP_CHECK(!for_solver || A->ncol >= A->nrow, "csr: a solver needs ncol >= nrow (owned rows first, then ghosts)");
     return 0;
 }
 
@@ -764,7 +770,7 @@ namespace {
 
 extern "C" int mp_spmv(mp_ctx *ctx, const mp_csr *A, const double *d_x, double *d_y) {
     MP_CHECK(ctx && d_x && d_y, "mp_spmv: null argument");
-    MP_TRY(check_csr(A));
+    MP_TRY(check_csr(A, false));
     int64_t nnz = 0;
     MP_TRY(nnz_of(ctx, A, &nnz));
     return launch_spmv<0, false>(ctx, A, pick_lanes(A, nnz), d_x, d_y, nullptr, 0, 0);
@@ -774,6 +780,15 @@ extern "C" int mp_axpby(mp_ctx *ctx, int64_t n, double a, const double *d_x, dou
     MP_CHECK(ctx && d_x && d_y && n >= 0, "mp_axpby: bad argument");
     if (n == 0) return 0;
     k_axpby<<<grid_for(ctx, n), kThreads, 0, ctx->stream>>>(n, a, d_x, b, d_y);
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp_vmul(mp_ctx *ctx, int64_t n, double a, const double *d_x, const double *d_y, double *d_z) {
+    MP_CHECK(ctx && d_x && d_y && d_z && n >= 0, "mp_vmul: bad argument");
+    if (n == 0) return 0;
+    k_vmul<<<grid_for(ctx, n), kThreads, 0, ctx->stream>>>(n, a, d_x, d_y, d_z);
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
     return 0;

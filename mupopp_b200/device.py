@@ -87,6 +87,9 @@ class Context:
         check(self.lib.mp_dot(self.h, x.numel(), ptr(x), ptr(y), C.byref(r)), "mp_dot")
         return r.value
 
+    def vmul(self, a, x, y, z):
+        check(self.lib.mp_vmul(self.h, z.numel(), a, ptr(x), ptr(y), ptr(z)), "mp_vmul")
+
     def axpby(self, a, x, b, y):
         check(self.lib.mp_axpby(self.h, y.numel(), a, ptr(x), b, ptr(y)), "mp_axpby")
 
