@@ -1,0 +1,499 @@
+"""Minimal dolfin-compatible facade: the subset of `from fenics import *` / `from mshr import *` that the in-scope MuPoPP
+run scripts touch, backed by the B200 path.
+
+"Forms" are opaque operator descriptors produced by `mupopp_b200.mupopp`; `solve(a == L, u, bcs)` dispatches them to the
+GPU solvers of `mupopp_b200.moder` (the reference's own mixed P2/P1 discretisation, i.e. mode R).
+Call sites mirrored: /root/reference/src/run/darcy_advection_diffusion/darcy_advection_diffusion.py:50-117,
+/root/reference/src/run/CCS2D/CCS_3comp.py:206-263.  Not a general FEniCS replacement: anything else raises.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import mesh as _mesh
+from .device import Context
+
+DOLFIN_EPS = 3.0e-16
+parameters = {"std_out_all_processes": False, "form_compiler": {"quadrature_degree": None, "cpp_optimize": True}}
+_CTX = None
+
+
+def default_context():
+    """The process-wide GPU context (device 0 or LOCAL_RANK)."""
+    global _CTX
+    if _CTX is None:
+        import os
+        _CTX = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _CTX
+
+
+def info(msg, *a):
+    print(msg)
+
+
+def set_log_level(level):
+    pass
+
+
+def near(a, b, eps=DOLFIN_EPS):
+    return abs(a - b) < eps
+
+
+def has_linear_algebra_backend(name):
+    return True
+
+
+def has_krylov_solver_method(name):
+    return name in ("cg", "gmres", "bicgstab", "minres", "tfqmr")
+
+
+def has_krylov_solver_preconditioner(name):
+    return name in ("jacobi", "amg", "none")
+
+
+class Point:
+    def __init__(self, *xs):
+        self.x = tuple(float(v) for v in xs)
+
+    def __getitem__(self, i):
+        return self.x[i]
+
+    def __len__(self):
+        return len(self.x)
+
+
+# ------------------------------------------------------------------ meshes (structured stand-ins for mshr)
+def UnitSquareMesh(nx, ny, diagonal="right"):
+    return _mesh.UnitSquareMesh(nx, ny, diagonal)
+
+
+def UnitCubeMesh(nx, ny, nz):
+    return _mesh.UnitCubeMesh(nx, ny, nz)
+
+
+def RectangleMesh(p0, p1, nx, ny, diagonal="right"):
+    return _mesh.RectangleMesh(p0, p1, nx, ny, diagonal)
+
+
+def BoxMesh(p0, p1, nx, ny, nz):
+    return _mesh.BoxMesh(p0, p1, nx, ny, nz)
+
+
+class Rectangle:
+    def __init__(self, p0, p1):
+        self.p0, self.p1 = p0, p1
+
+
+class Box:
+    def __init__(self, p0, p1):
+        self.p0, self.p1 = p0, p1
+
+
+def generate_mesh(domain, resolution):
+    """mshr.generate_mesh stand-in: a structured mesh with cell size ~ (domain diagonal)/resolution (CGAL is not available)."""
+    p0, p1 = domain.p0, domain.p1
+    ext = [abs(p1[i] - p0[i]) for i in range(len(p0))]
+    h = math.sqrt(sum(e * e for e in ext)) / float(resolution)
+    n = [max(1, int(round(e / h))) for e in ext]
+    if len(ext) == 2:
+        return _mesh.RectangleMesh(p0, p1, n[0], n[1])
+    return _mesh.BoxMesh(p0, p1, n[0], n[1], n[2])
+
+
+class _UfcCell:
+    def __init__(self, index, local_facet):
+        self.index, self.local_facet = index, local_facet
+
+
+class Cell:
+    """dolfin.Cell(mesh, index): only .normal(local_facet) (used by BoundarySource, darcy_advection_diffusion.py:29-34)."""
+
+    def __init__(self, mesh, index):
+        self.mesh, self.index = mesh, int(index)
+
+    def normal(self, local_facet):
+        m = self.mesh
+        d = m.dim
+        vs = m.cells[self.index]
+        loc = [j for j in range(d + 1) if j != local_facet]
+        x = m.coords[vs[loc]]
+        if d == 2:
+            t = x[1] - x[0]
+            n = np.array([t[1], -t[0]])
+        else:
+            n = np.cross(x[1] - x[0], x[2] - x[0])
+        n = n / np.linalg.norm(n)
+        if np.dot(x[0] - m.coords[vs[local_facet]], n) < 0:
+            n = -n
+        return n
+
+
+# ------------------------------------------------------------------ elements / spaces
+class FiniteElement:
+    def __init__(self, family, cell=None, degree=1):
+        if family not in ("Lagrange", "CG", "P"):
+            raise NotImplementedError("element family %r" % (family,))
+        self.degree, self.ncomp = int(degree), 1
+
+
+class VectorElement(FiniteElement):
+    def __init__(self, family, cell=None, degree=1, dim=None):
+        super().__init__(family, cell, degree)
+        self.ncomp = dim if dim is not None else (2 if cell in ("triangle", None) else 3)
+        self._cell = cell
+
+
+class MixedElement:
+    def __init__(self, elements):
+        self.elements = list(elements)
+
+
+class FunctionSpace:
+    """Scalar, vector or mixed Lagrange space with UFC block numbering; blocks = [(degree, offset, ndof)]."""
+
+    def __init__(self, mesh, element, degree=None, constrained_domain=None, _parent=None, _sub=None):
+        if constrained_domain is not None:
+            raise NotImplementedError("periodic constrained_domain is not on the B200 path yet (SURVEY.md section 8 f1)")
+        self.mesh = mesh
+        if isinstance(element, str):
+            element = FiniteElement(element, mesh.ufl_cell(), degree)
+        if isinstance(element, VectorElement):
+            element.ncomp = mesh.dim
+        if isinstance(element, MixedElement):
+            for e in element.elements:
+                if isinstance(e, VectorElement):
+                    e.ncomp = mesh.dim
+        self.element = element
+        self.parent, self.sub_index = _parent, _sub
+        subs = element.elements if isinstance(element, MixedElement) else [element]
+        self.sub_elements = subs
+        self.blocks = []         # (degree, offset, ndof) per scalar block
+        self.sub_blocks = []     # block indices per sub-element
+        off = 0
+        for e in subs:
+            idx = []
+            nd = mesh.num_vertices() + (mesh.num_edges() if e.degree == 2 else 0)
+            if e.degree not in (1, 2):
+                raise NotImplementedError("Lagrange degree %d" % e.degree)
+            for _ in range(e.ncomp):
+                idx.append(len(self.blocks))
+                self.blocks.append((e.degree, off, nd))
+                off += nd
+            self.sub_blocks.append(idx)
+        self._dim = off
+
+    def dim(self):
+        return self._dim
+
+    def sub(self, i):
+        if self.parent is not None:          # W.sub(0).sub(c): one component of a vector sub-space
+            return _SubSpace(self.parent, self.sub_index, i)
+        return _SubSpace(self, i, None)
+
+    def num_sub_spaces(self):
+        return len(self.sub_elements)
+
+    def dof_coords(self, degree):
+        if degree == 1:
+            return self.mesh.coords
+        e = self.mesh.edges
+        return np.concatenate([self.mesh.coords, 0.5 * (self.mesh.coords[e[:, 0]] + self.mesh.coords[e[:, 1]])], axis=0)
+
+
+class _SubSpace:
+    def __init__(self, parent, isub, comp):
+        self.parent, self.isub, self.comp = parent, isub, comp
+        self.mesh = parent.mesh
+
+    def sub(self, c):
+        return _SubSpace(self.parent, self.isub, c)
+
+    def block_ids(self):
+        ids = self.parent.sub_blocks[self.isub]
+        return ids if self.comp is None else [ids[self.comp]]
+
+
+def VectorFunctionSpace(mesh, family, degree, dim=None):
+    return FunctionSpace(mesh, VectorElement(family, mesh.ufl_cell(), degree, dim or mesh.dim))
+
+
+# ------------------------------------------------------------------ coefficients
+class Constant:
+    def __init__(self, value):
+        self.value = np.atleast_1d(np.asarray(value, dtype=float))
+
+    def assign(self, v):
+        self.value = np.atleast_1d(np.asarray(getattr(v, "value", v), dtype=float))
+
+    def value_shape(self):
+        return () if self.value.size == 1 else (self.value.size,)
+
+    def values(self):
+        return self.value
+
+    def __float__(self):
+        return float(self.value[0])
+
+    def __getitem__(self, i):
+        return float(self.value[i])
+
+    def __len__(self):
+        return self.value.size
+
+
+class Expression:
+    """String expressions (`Expression("0.1", degree=1)`, `Expression("dt", dt=0.1)`) or user subclasses overriding
+    eval(values, x) / eval_cell(values, x, ufc_cell) / value_shape()."""
+
+    def __init__(self, code=None, degree=1, element=None, **kw):
+        self._code = code
+        self.degree = degree
+        self.element = element
+        self.user = dict(kw)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+    def value_shape(self):
+        if isinstance(self._code, (tuple, list)):
+            return (len(self._code),)
+        return ()
+
+    def eval(self, values, x):
+        codes = self._code if isinstance(self._code, (tuple, list)) else [self._code]
+        ns = {k: getattr(math, k) for k in ("sin", "cos", "tan", "exp", "sqrt", "tanh", "log", "pow", "fabs")}
+        ns.update(pi=math.pi, x=x, DOLFIN_EPS=DOLFIN_EPS)
+        for k in self.user:
+            ns[k] = getattr(self, k)
+        for i, c in enumerate(codes):
+            values[i] = eval(str(c).replace("&&", " and ").replace("||", " or "), {"__builtins__": {}}, ns)
+
+    def _nvals(self):
+        vs = self.value_shape()
+        return int(np.prod(vs)) if len(vs) else 1
+
+
+def _evaluate(value, pts, ncomp, cell_info=None):
+    """Evaluate a Constant / Expression / Function-like / number at points -> (N, ncomp)."""
+    n = pts.shape[0]
+    if isinstance(value, (int, float)):
+        return np.full((n, ncomp), float(value))
+    if isinstance(value, Constant):
+        return np.broadcast_to(value.value.reshape(1, -1), (n, ncomp)).copy()
+    if isinstance(value, Expression):
+        out = np.zeros((n, ncomp))
+        use_cell = hasattr(value, "eval_cell") and cell_info is not None
+        buf = np.zeros(max(ncomp, 1))
+        for i in range(n):
+            buf[:] = 0.0
+            if use_cell:
+                value.eval_cell(buf, pts[i], _UfcCell(int(cell_info[0][i]), int(cell_info[1][i])))
+            else:
+                value.eval(buf, pts[i])
+            out[i] = buf[:ncomp]
+        return out
+    raise TypeError("cannot evaluate %r" % (value,))
+
+
+class Function:
+    """Coefficient vector(s) of a FunctionSpace, stored per scalar block on the GPU."""
+
+    def __init__(self, V, _blocks=None, _ids=None):
+        self.space = V
+        ctx = default_context()
+        if _blocks is None:
+            self.blocks = [ctx.zeros(nd) for (_, _, nd) in V.blocks]
+            self.ids = list(range(len(V.blocks)))
+        else:
+            self.blocks, self.ids = _blocks, _ids
+        self._name = "f"
+
+    def function_space(self):
+        return self.space
+
+    def rename(self, name, label=""):
+        self._name = name
+
+    def split(self, deepcopy=False):
+        out = []
+        for idx in self.space.sub_blocks:
+            blks = [self.blocks[self.ids.index(i)] for i in idx]
+            if deepcopy:
+                blks = [b.clone() for b in blks]
+            out.append(Function(self.space, blks, list(idx)))
+        return tuple(out)
+
+    def sub(self, i):
+        return self.split()[i]
+
+    def block_degree(self, k):
+        return self.space.blocks[self.ids[k]][0]
+
+    def vector(self):
+        return _VectorView(self)
+
+    def assign(self, other):
+        for a, b in zip(self.blocks, other.blocks):
+            a.copy_(b)
+
+    def interpolate(self, v):
+        ctx = default_context()
+        if isinstance(v, Function):
+            if len(v.blocks) != len(self.blocks):
+                raise ValueError("interpolate: block structure differs")
+            for a, b in zip(self.blocks, v.blocks):
+                if a.numel() != b.numel():
+                    raise NotImplementedError("interpolation between different degrees")
+                a.copy_(b)
+            return
+        ncomp = len(self.blocks)
+        deg = self.block_degree(0)
+        X = self.space.dof_coords(deg)
+        vals = _evaluate(v, X, ncomp)
+        for c in range(ncomp):
+            self.blocks[c].copy_(ctx.to_device(np.ascontiguousarray(vals[:, c])))
+
+    def get(self, k=0):
+        """Host copy of scalar block k (test / output helper)."""
+        return self.blocks[k].cpu().numpy()
+
+
+class _VectorView:
+    def __init__(self, f):
+        self.f = f
+
+    def get_local(self):
+        return np.concatenate([b.cpu().numpy() for b in self.f.blocks])
+
+    def array(self):
+        return self.get_local()
+
+    def set_local(self, a):
+        ctx = default_context()
+        off = 0
+        for b in self.f.blocks:
+            b.copy_(ctx.to_device(np.asarray(a[off:off + b.numel()], dtype=np.float64)))
+            off += b.numel()
+
+    def __setitem__(self, key, a):
+        self.set_local(np.broadcast_to(a, (sum(b.numel() for b in self.f.blocks),)) if np.isscalar(a) else a)
+
+
+def assign(dst, src):
+    dst.assign(src)
+
+
+def interpolate(v, V):
+    f = Function(V)
+    f.interpolate(v)
+    return f
+
+
+# ------------------------------------------------------------------ boundary conditions
+class DirichletBC:
+    """DirichletBC(V | V.sub(i)[.sub(c)], value, marker): 'topological' marking -- a boundary facet is constrained when the
+    marker holds at all its vertices and its midpoint; every dof on it (vertices, and edge midpoints for P2) is set."""
+
+    def __init__(self, V, value, marker, method="topological"):
+        self.V, self.value, self.marker = V, value, marker
+        if isinstance(V, _SubSpace):
+            self.space, self.block_ids = V.parent, V.block_ids()
+        else:
+            self.space, self.block_ids = V, list(range(len(V.blocks)))
+
+    def _mark(self, x):
+        try:
+            return bool(self.marker(x, True))
+        except TypeError:
+            return bool(self.marker(x))
+
+    def dofs_and_values(self):
+        """-> {block id: (dof indices, values)} in the block's own numbering."""
+        mesh = self.space.mesh
+        d = mesh.dim
+        fv, nrm, meas, owner = mesh.boundary_facets()
+        oloc = mesh.boundary_facet_local_index()
+        vx = mesh.coords
+        bverts = np.unique(fv.ravel())
+        vin = np.zeros(mesh.num_vertices(), dtype=bool)
+        vin[bverts] = [self._mark(vx[i]) for i in bverts]
+        inside = vin[fv].all(1)
+        for f in np.nonzero(inside)[0]:
+            inside[f] = self._mark(vx[fv[f]].mean(0))
+        marked = np.nonzero(inside)[0]
+        degree = self.space.blocks[self.block_ids[0]][0]
+        ncomp = len(self.block_ids)
+        # collect (dof, point, owning cell, local facet) over marked facets, first occurrence wins
+        seen = {}
+        from .reference_element import TET_EDGES, TRI_EDGES
+        le = TRI_EDGES if d == 2 else TET_EDGES
+        nv = mesh.num_vertices()
+        for f in marked:
+            c, k = int(owner[f]), int(oloc[f])
+            for v in fv[f]:
+                seen.setdefault(int(v), (vx[v], c, k))
+            if degree == 2:
+                ce = mesh.cell_edges[c]
+                for e, (a, b) in enumerate(le):
+                    if a != k and b != k:            # edge lies on the facet opposite local vertex k
+                        gid = nv + int(ce[e])
+                        if gid not in seen:
+                            va, vb = mesh.cells[c][a], mesh.cells[c][b]
+                            seen[gid] = (0.5 * (vx[va] + vx[vb]), c, k)
+        if not seen:
+            return {b: (np.zeros(0, dtype=np.int64), np.zeros(0)) for b in self.block_ids}
+        dofs = np.array(sorted(seen), dtype=np.int64)
+        pts = np.array([seen[i][0] for i in dofs])
+        cinfo = (np.array([seen[i][1] for i in dofs]), np.array([seen[i][2] for i in dofs]))
+        vals = _evaluate(self.value, pts, ncomp, cinfo)
+        return {b: (dofs, vals[:, j].copy()) for j, b in enumerate(self.block_ids)}
+
+
+# ------------------------------------------------------------------ forms, solve, output
+class Form:
+    """Opaque operator descriptor returned by the mupopp form methods."""
+
+    def __init__(self, kind, side, **data):
+        self.kind, self.side, self.data = kind, side, data
+
+    def __eq__(self, other):
+        if isinstance(other, Form):
+            return Equation(self, other)
+        return NotImplemented
+
+    __hash__ = object.__hash__
+
+
+class Equation:
+    def __init__(self, a, L):
+        if a.data is not L.data and a.kind != L.kind:
+            raise ValueError("a and L come from different forms")
+        self.a, self.L = a, L
+
+
+def solve(eq, u, bcs=None, solver_parameters=None, **kw):
+    """dolfin.solve(a == L, u, bcs): dispatch the form descriptor to its GPU solver (mode R)."""
+    if not isinstance(eq, Equation):
+        raise TypeError("solve expects `a == L` built from mupopp_b200.mupopp forms")
+    from . import mupopp as _mp
+    bcs = [] if bcs is None else (list(bcs) if isinstance(bcs, (list, tuple)) else [bcs])
+    return _mp._dispatch_solve(eq.a, u, bcs, solver_parameters or {})
+
+
+class File:
+    """Output sink: `File(name, "compressed") << f`.  VTK writing is out of scope; fields are kept as
+    .npy next to the requested name only when MUPOPP_B200_WRITE=1."""
+
+    def __init__(self, name, *a):
+        self.name, self.count = name, 0
+
+    def __lshift__(self, f):
+        import os
+        if os.environ.get("MUPOPP_B200_WRITE") == "1":
+            os.makedirs(os.path.dirname(self.name) or ".", exist_ok=True)
+            fn = f[0] if isinstance(f, tuple) else f
+            np.save("%s.%06d.npy" % (self.name, self.count), fn.vector().get_local())
+        self.count += 1
+        return self

@@ -96,7 +96,7 @@ class Mesh:
             return self._bfacets
         d = self.dim
         nv = self.num_vertices()
-        fv, owner, opp = [], [], []
+        fv, owner, opp, oloc = [], [], [], []
         if getattr(self, "box", None) is not None:
             # axis-aligned box domain: a facet is on the boundary iff all its vertices share a bounding plane
             lo, hi = self.box
@@ -115,7 +115,8 @@ class Mesh:
                 fv.append(self.cells[sel][:, loc].astype(np.int64))
                 owner.append(sel)
                 opp.append(self.cells[sel, k].astype(np.int64))
-            fv, owner, opp = np.concatenate(fv), np.concatenate(owner), np.concatenate(opp)
+                oloc.append(np.full(sel.size, k, dtype=np.int64))
+            fv, owner, opp, oloc = np.concatenate(fv), np.concatenate(owner), np.concatenate(opp), np.concatenate(oloc)
         else:
             cells = self.cells.astype(np.int64)
             for k in range(d + 1):
@@ -123,15 +124,17 @@ class Mesh:
                 fv.append(cells[:, loc])
                 owner.append(np.arange(cells.shape[0]))
                 opp.append(cells[:, k])
+                oloc.append(np.full(cells.shape[0], k, dtype=np.int64))
             fv = np.concatenate(fv)
             owner = np.concatenate(owner)
             opp = np.concatenate(opp)
+            oloc = np.concatenate(oloc)
             key = fv[:, 0].copy()
             for j in range(1, d):
                 key = key * nv + fv[:, j]
             _, idx, cnt = np.unique(key, return_index=True, return_counts=True)
             sel = np.sort(idx[cnt == 1])
-            fv, owner, opp = fv[sel], owner[sel], opp[sel]
+            fv, owner, opp, oloc = fv[sel], owner[sel], opp[sel], oloc[sel]
         x = self.coords[fv]
         if d == 2:
             t = x[:, 1] - x[:, 0]
@@ -144,7 +147,12 @@ class Mesh:
         flip = ((x[:, 0] - self.coords[opp]) * n).sum(1) < 0
         n[flip] *= -1.0
         self._bfacets = (fv, n, meas, owner)
+        self._bfacet_local = oloc          # UFC local facet index (= local index of the opposite vertex) in the owning cell
         return self._bfacets
+
+    def boundary_facet_local_index(self):
+        self.boundary_facets()
+        return self._bfacet_local
 
 
 def RectangleMesh(p0, p1, nx, ny, diagonal="right"):

@@ -1,0 +1,277 @@
+"""The `mupopp` module API on the B200 path: same classes, method names, positional order and defaults as
+/root/reference/src/modules/mupopp.py (DarcyAdvection :560, CCS :1104, StokesAdvection :965, compaction :125, utilities :23-115).
+
+As in the reference, the form methods do not solve anything: they return `(a, L)` descriptors; `solve(a == L, sol, bcs)` from
+`mupopp_b200.fenics` runs them.  The solve is the reference's own discretisation (mode R: mixed P2/P1, segregated
+block-triangular sequence == the monolithic LU solve) executed by the CUDA kernels of libmupopp_b200.so.
+Forms whose kernels are not built yet raise NotImplementedError at solve time with the row of SURVEY.md section 8 they belong to.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .fenics import Constant, DirichletBC, Expression, Form, Function, default_context, info  # noqa: F401
+
+
+# ------------------------------------------------------------------ utilities (mupopp.py:23-115)
+def symgrad(u):
+    raise NotImplementedError("symgrad builds a UFL expression; UFL is not part of the B200 path")
+
+
+def iteration_output_info(niter, h, l2_u, l2_p, l2_c):
+    print("Number of Krylov iterations:", niter)
+    print("hmax:", h)
+    print("L2 error in velocity:", l2_u)
+    print("L2 error in pressure:", l2_p)
+    print("L2 error in compaction:", l2_c)
+
+
+def iteration_output_write(niter, h, l2_u, l2_p, l2_c, fname="output/iter.out"):
+    import os
+    os.makedirs(os.path.dirname(fname) or ".", exist_ok=True)
+    with open(fname, "a") as f:
+        f.write("%d,%g,%g,%g,%g\n" % (niter, h, l2_u, l2_p, l2_c))
+
+
+def int_float_string(val):
+    if val.isdigit():
+        return int(val)
+    try:
+        return float(val)
+    except ValueError:
+        return val.replace(" ", "")
+
+
+def parse_param_file(filename):
+    """`key = value  # comment` files (e.g. benchmark/time_marching/time_test1.cfg) -> dict with int/float/str values."""
+    out = {}
+    with open(filename, "r") as f:
+        for raw in f.read().splitlines():
+            if raw.strip() == "" or raw.startswith("#"):
+                continue
+            opt = raw.rstrip().replace(" ", "").partition("#")[0]
+            if "=" not in opt:
+                continue
+            key, val = opt.split("=", 1)
+            out[key] = int_float_string(val)
+    return out
+
+
+def _zhat(zh, dim):
+    v = np.asarray(getattr(zh, "value", zh), dtype=float).ravel()
+    return tuple(float(v[i]) if i < v.size else 0.0 for i in range(dim))
+
+
+def _kvalue(K):
+    if isinstance(K, (int, float)):
+        return float(K)
+    if isinstance(K, Constant):
+        return float(K)
+    raise NotImplementedError("mode R on the GPU supports a constant permeability K (P1 K: mode F, mupopp_b200.transport)")
+
+
+def _pair(kind, **data):
+    return Form(kind, "a", **data), Form(kind, "L", **data)
+
+
+# ------------------------------------------------------------------ classes
+class DarcyAdvection:
+    """mupopp.py:560-960."""
+
+    def __init__(self, Pe=100, Da=10.0, phi=0.01, alpha=0.005, cfl=1.0e-2, dt=1.0e-2):
+        self.Pe, self.Da, self.phi, self.cfl, self.dt, self.alpha = Pe, Da, phi, cfl, dt, alpha
+        self.beta = alpha / phi
+
+    def darcy_bilinear(self, W, mesh, K=0.1, zh=Constant((0.0, 1.0)), TwodTrue=True):
+        zhat = _zhat(zh, 2) if TwodTrue else (0.0, 0.0, 1.0)
+        return _pair("darcy_bilinear", W=W, mesh=mesh, K=_kvalue(K), zhat=zhat)
+
+    def advection_diffusion(self, Q, u0, velocity, dt, mesh):
+        return _pair("advection_diffusion", Q=Q, u0=u0, velocity=velocity, dt=float(dt), mesh=mesh, Pe=float(self.Pe), Da=float(self.Da))
+
+    def advection_diffusion_two_component_adaptive(self, Q, c_prev, velocity, mesh):
+        return _pair("two_component_adaptive", Q=Q, c_prev=c_prev, velocity=velocity, mesh=mesh, owner=self)
+
+    def _multi(self, kind, W, mesh, sol_prev, dt, f1, K, zh, SUPG, gam_rho, rho_0):
+        from .transport import TransportModel
+        mk = TransportModel.darcy_two_component if kind == 2 else TransportModel.darcy_three_component
+        model = mk(Pe=self.Pe, Da=self.Da, phi=self.phi, alpha=self.alpha, dt=float(getattr(dt, "dt", dt)), K=_kvalue(K),
+                   zh=_zhat(zh, mesh.dim), SUPG=SUPG, gam_rho=gam_rho, rho_0=rho_0)
+        return _pair("multi_component", W=W, mesh=mesh, sol_prev=sol_prev, f=f1, model=model)
+
+    def advection_diffusion_two_component(self, W, mesh, sol_prev, dt, f1, K=1.0, zh=Constant((0.0, 1.0)), SUPG=1, gam_rho=-1.0, rho_0=1.0):
+        return self._multi(2, W, mesh, sol_prev, dt, f1, K, zh, SUPG, gam_rho, rho_0)
+
+    def advection_diffusion_three_component(self, W, mesh, sol_prev, dt, f1, K=1.0, zh=Constant((0.0, 1.0)), SUPG=1, gam_rho=-1.0, rho_0=1.0):
+        return self._multi(3, W, mesh, sol_prev, dt, f1, K, zh, SUPG, gam_rho, rho_0)
+
+
+class CCS:
+    """mupopp.py:1104-1262."""
+
+    def __init__(self, Pe=100, Da=10.0, phi=0.01, alpha=0.005, cfl=1.0e-2, dt=1.0e-2):
+        self.Pe, self.Da, self.phi, self.cfl, self.dt, self.alpha = Pe, Da, phi, cfl, dt, alpha
+        self.beta = alpha / phi
+
+    def advection_diffusion_three_component(self, W, mesh, sol_prev, dt, f_source, K=1.0, zh=Constant((0.0, 1.0)), SUPG=1, gam_rho=1.0):
+        from .transport import TransportModel
+        model = TransportModel.ccs_three_component(Pe=self.Pe, Da=self.Da, phi=self.phi, alpha=self.alpha, dt=float(getattr(dt, "dt", dt)),
+                                                   K=_kvalue(K), zh=_zhat(zh, mesh.dim), SUPG=SUPG, gam_rho=gam_rho)
+        return _pair("multi_component", W=W, mesh=mesh, sol_prev=sol_prev, f=f_source, model=model)
+
+
+class StokesAdvection:
+    """mupopp.py:965-1099 (P3 velocity Stokes + ADR + precipitation): API kept; kernels are SURVEY.md section 8 row a7 (not built yet)."""
+
+    def __init__(self, Pe=100, Da=10.0, alpha=0.005, cfl=1.0e-2, dt=1.0e-2):
+        self.Pe, self.Da, self.cfl, self.dt, self.alpha = Pe, Da, cfl, dt, alpha
+
+    def stokes_ADR_precipitation(self, W, mesh, sol_prev, dt, SUPG=2):
+        return _pair("stokes_adr", W=W, mesh=mesh, sol_prev=sol_prev, dt=dt, SUPG=SUPG, owner=self)
+
+
+class compaction:
+    """mupopp.py:125-471: parameters come from a `key = value` file; forms are rows a8-a10 of SURVEY.md section 8 (not built yet)."""
+
+    def __init__(self, param_file, ksp="minres"):
+        param = parse_param_file(param_file)
+        self.da, self.R, self.B = param["da"], param["R"], param["B"]
+        self.theta, self.dL, self.T = param["theta"], param["dL"], param["T"]
+        self.dt, self.out_freq = param["dt"], param["out_freq"]
+        self.krylov_method = ksp
+
+    def surface_tension_2(self, phi):
+        # mupopp.py:206-215: chi(phi) polynomial, theta passed raw to cos (radians)
+        p1, p2, p3, p4 = -8065.0, 6149.0, -1778.0, 249.0
+        return (2.0 * np.cos(self.theta) - 1.0) * (2.0 * p4 + 20.0 * p1 * phi ** 3 + 12.0 * p2 * phi ** 2 + 6.0 * p3 * phi)
+
+    def mass_conservation(self, V, phi0, u, dt, gam, mesh):
+        a, L = _pair("compaction_mass", V=V, phi0=phi0, u=u, dt=dt, gam=gam, mesh=mesh, owner=self)
+        return a, L, Form("compaction_mass", "b", **a.data)
+
+    def mass_solver(self, X, a_phi, L_phi, bb_phi, nits=100, tol=1.0e-6, monitor=False):
+        raise NotImplementedError("compaction.mass_solver: SURVEY.md section 8 row a10 is not on the B200 path yet")
+
+    def momentum_conservation(self, W, phi, gam, buyoancy, zh=Constant((0.0, 0.0, 1.0))):
+        a, L = _pair("compaction_momentum", W=W, phi=phi, gam=gam, buoyancy=buyoancy, zh=zh, owner=self)
+        return a, L, Form("compaction_momentum", "b", **a.data)
+
+    def momentum_solver(self, W, a, L, b, bcs, pc="amg", tol=1.0e-6, max_its=3000, monitor=False):
+        raise NotImplementedError("compaction.momentum_solver: SURVEY.md section 8 rows a8-a9 are not on the B200 path yet")
+
+    def momentum_solver_direct(self, W, a, L, b, bcs, pc="amg", tol=1.0e-6, max_its=3000, monitor=False):
+        raise NotImplementedError("compaction.momentum_solver_direct: SURVEY.md section 8 rows a8-a9 are not on the B200 path yet")
+
+
+# ------------------------------------------------------------------ solve dispatch (called by fenics.solve)
+_CACHE = {}
+
+
+def _bc_arrays(space, bcs, block_ids):
+    """isbc / g arrays per requested scalar block from a list of DirichletBC (later BCs override earlier ones)."""
+    out = {}
+    for b in block_ids:
+        nd = space.blocks[b][2]
+        out[b] = (np.zeros(nd, dtype=np.uint8), np.zeros(nd))
+    for bc in bcs:
+        if bc.space is not space:
+            raise ValueError("DirichletBC defined on a different FunctionSpace than the solution")
+        for b, (dofs, vals) in bc.dofs_and_values().items():
+            if b in out and dofs.size:
+                out[b][0][dofs] = 1
+                out[b][1][dofs] = vals
+    return out
+
+
+def _bc_key(bcs):
+    return tuple(id(b) for b in bcs)
+
+
+def _nodal(f, space_mesh):
+    """A P1 coefficient given as Function / Expression / Constant / number -> nodal numpy array."""
+    from .fenics import _evaluate
+    if f is None:
+        return None
+    if isinstance(f, Function):
+        return f.blocks[0].cpu().numpy()
+    return _evaluate(f, space_mesh.coords, 1)[:, 0]
+
+
+def _dispatch_solve(form, u, bcs, solver_parameters):
+    from . import moder
+    ctx = default_context()
+    d = form.data
+    kind = form.kind
+    if kind == "darcy_bilinear":
+        W, mesh = d["W"], d["mesh"]
+        dim = mesh.dim
+        key = ("darcy", id(W), d["K"], _bc_key(bcs))
+        if key not in _CACHE:
+            sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+            arr = _bc_arrays(W, bcs, W.sub_blocks[0])
+            isbc = [arr[b][0] for b in W.sub_blocks[0]]
+            g = [arr[b][1] for b in W.sub_blocks[0]]
+            _CACHE[key] = moder.MixedDarcyR(ctx, sp, K=d["K"], phi=1.0, u_isbc=isbc, u_g=g)
+        darcy = _CACHE[key]
+        sp = darcy.sp
+        import torch
+        ones = torch.ones(sp.n1, dtype=torch.float64, device=ctx.device)
+        lK = ctx.zeros(sp.n2)
+        darcy.G.spmv(ones, lK)                                   # L = K f v.zhat with f == 1 (mupopp.py:616,621)
+        rhs = []
+        for c in range(dim):
+            rc = ctx.zeros(sp.n2)
+            ctx.axpby(float(d["zhat"][c]), lK, 0.0, rc)
+            rhs.append(rc)
+        p = u.blocks[dim]
+        uu, its = darcy.solve(rhs, p)
+        for c in range(dim):
+            u.blocks[c].copy_(uu[c])
+        return its
+    if kind == "advection_diffusion":
+        Q, mesh = d["Q"], d["mesh"]
+        key = ("adr", id(Q), d["Pe"], d["Da"], d["dt"], _bc_key(bcs))
+        if key not in _CACHE:
+            sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+            arr = _bc_arrays(Q, bcs, [0])
+            vdeg = d["velocity"].block_degree(0)
+            _CACHE[key] = moder.AdrSolverR(ctx, sp, moder.adr_single_params(d["Pe"], d["Da"], d["dt"]), arr[0][0], arr[0][1], vel_degree=vdeg)
+        adr = _CACHE[key]
+        c_in = d["u0"].blocks[0].clone()             # u0 may alias the solution Function (c0 = sol_c in the script)
+        res = adr.solve(d["velocity"].blocks, c_in, u.blocks[0])
+        return res.niter
+    if kind == "multi_component":
+        W, mesh, model = d["W"], d["mesh"], d["model"]
+        dim = mesh.dim
+        nc = model.ncomp
+        key = ("multi", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.K, model.phi)
+        fs = _nodal(d["f"], mesh)
+        if key not in _CACHE:
+            ub = W.sub_blocks[0]
+            arr = _bc_arrays(W, bcs, list(ub) + [W.sub_blocks[2][0]])
+            _CACHE[key] = moder.TransportSolverR(ctx, mesh, model, [arr[b][0] for b in ub], [arr[b][1] for b in ub],
+                                                 arr[W.sub_blocks[2][0]][0], arr[W.sub_blocks[2][0]][1], f_source=fs)
+        s = _CACHE[key]
+        s.model, s.prm = model, moder.transport_params(model.Pe, model.Da, model.phi, model.alpha, model.dt, model.sigma, model.rho0,
+                                                        model.gamma, model.fracs, model.zhat, model.K, model.reaction, model.ncomp, model.SUPG)
+        s.adr.prm = s.prm
+        prev = d["sol_prev"]
+        for c in range(dim):
+            s.u[c].copy_(prev.blocks[c])
+        s.p.copy_(prev.blocks[dim])
+        s.c0.copy_(prev.blocks[dim + 1])
+        s.c1.copy_(prev.blocks[dim + 2])
+        if nc == 3:
+            s.c2.copy_(prev.blocks[dim + 3])
+        if fs is not None:
+            s.fsrc.copy_(ctx.to_device(np.asarray(fs, dtype=np.float64)))
+        info_ = s.step()
+        for c in range(dim):
+            u.blocks[c].copy_(s.u[c])
+        u.blocks[dim].copy_(s.p)
+        u.blocks[dim + 1].copy_(s.c0)
+        u.blocks[dim + 2].copy_(s.c1)
+        if nc == 3:
+            u.blocks[dim + 3].copy_(s.c2)
+        return info_
+    raise NotImplementedError("solve: form kind %r is not on the B200 path yet (SURVEY.md section 8 rows a6-a10)" % kind)

@@ -1,0 +1,88 @@
+"""The drop-in boundary: mupopp classes + fenics facade drive the GPU path and reproduce the oracle (config 1 and a CCS step)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+from oracle import fem, forms
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+def test_config1_script_matches_oracle(ctx):
+    """BASELINE configs[0] through the reference-facing API (examples/config1_darcy_adr.py) at 16x16, 5 steps."""
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import config1_darcy_adr as ex
+    n, nsteps = 16, 5
+    up, c = ex.run(n, nsteps, verbose=False)
+    om = fem.unit_square_mesh(n, n)
+    asm = forms.Assembler(om)
+    n1, n2 = asm.P1.ndof, asm.P2.ndof
+    X2 = asm.P2.dof_coords()
+    bot, top = np.where(X2[:, 1] < 1e-14)[0], np.where(X2[:, 1] > 1 - 1e-14)[0]
+    D = np.concatenate([bot, top])
+    gy = np.concatenate([np.sin(2 * np.pi * X2[bot, 0]), np.ones(len(top))])
+    A, b = forms.darcy_bilinear_system(asm, K=0.1, zhat=(0.0, 1.0))
+    Abc, bbc = fem.apply_dirichlet_symmetric(A, b, np.concatenate([D, n2 + D]), np.concatenate([np.zeros(len(D)), gy]))
+    x = spla.splu(Abc.tocsc()).solve(bbc)
+    uo = [x[:n2], x[n2:2 * n2]]
+    assert rel(up.get(0), uo[0]) < 1e-9 and rel(up.get(1), uo[1]) < 1e-9 and rel(up.get(2), x[2 * n2:]) < 1e-9
+    X1 = om.coords
+    cb, ct = np.where(X1[:, 1] < 1e-14)[0], np.where(X1[:, 1] > 1 - 1e-14)[0]
+    co = 0.1 * np.ones(n1)
+    for k in range(nsteps):
+        Ao, bo = forms.adr_single_system(asm, 100.0, 10.0, 0.1, ("P2", uo), co)
+        Ab, bb = fem.apply_dirichlet_symmetric(Ao, bo, np.concatenate([ct, cb]), np.concatenate([np.zeros(len(ct)), np.ones(len(cb))]))
+        co = spla.splu(Ab.tocsc()).solve(bb)
+    assert rel(c.get(), co) < 1e-8
+
+
+def test_ccs_three_component_through_api(ctx):
+    """CCS.advection_diffusion_three_component + solve(a == L, sol, bc) for two steps == oracle monolithic LU (CCS_3comp.py:257-263)."""
+    from mupopp_b200.fenics import (Constant, DirichletBC, DOLFIN_EPS, Expression, FiniteElement, Function, FunctionSpace,
+                                    MixedElement, UnitSquareMesh, VectorElement, solve)
+    from mupopp_b200.mupopp import CCS
+    n = 6
+    mesh = UnitSquareMesh(n, n)
+    cell = mesh.ufl_cell()
+    Qc = FiniteElement("Lagrange", cell, 1)
+    W = FunctionSpace(mesh, MixedElement([VectorElement("Lagrange", cell, 2), FiniteElement("Lagrange", cell, 1), Qc, Qc, Qc]))
+    top = lambda x: x[1] > 1.0 - DOLFIN_EPS
+    bcs = [DirichletBC(W.sub(0), Constant((0.0, -0.5)), top), DirichletBC(W.sub(2), Constant(0.1), top)]
+
+    class Source(Expression):
+        def __init__(self):
+            pass
+
+        def eval(self, values, x):
+            values[0] = abs(np.sin(3 * np.pi * x[0])) * (1 - np.tanh((1.0 - x[1]) / 0.1))
+
+    ccs = CCS(Pe=500, Da=0.1, phi=0.05, alpha=1e-3)
+    sol_0 = Function(W)
+    sol_0.blocks[4].fill_(0.1)        # c1(0) = 0.1 (CCS_3comp.py:233-237); block order [ux, uy, p, c0, c1, c2]
+    sol = Function(W)
+    om = fem.unit_square_mesh(n, n)
+    asm = forms.Assembler(om)
+    n1, n2 = asm.P1.ndof, asm.P2.ndof
+    oprm = forms.ccs_three_component_params(Pe=500, Da=0.1, phi=0.05, alpha=1e-3, dt=0.1, K=1.0, zhat=(0.0, 1.0))
+    X2, X1 = asm.P2.dof_coords(), om.coords
+    top2, top1 = np.where(X2[:, 1] > 1 - 1e-12)[0], np.where(X1[:, 1] > 1 - 1e-12)[0]
+    obc = forms.BCs(u_dofs=[top2, top2], u_vals=[np.zeros(len(top2)), -0.5 * np.ones(len(top2))], c0_dofs=top1, c0_vals=0.1 * np.ones(len(top1)))
+    f = np.abs(np.sin(3 * np.pi * X1[:, 0])) * (1 - np.tanh((1.0 - X1[:, 1]) / 0.1))
+    prev = forms.State(u=[np.zeros(n2), np.zeros(n2)], p=np.zeros(n1), c0=np.zeros(n1), c1=0.1 * np.ones(n1), c2=np.zeros(n1))
+    S = Source()
+    for k in range(2):
+        a, L = ccs.advection_diffusion_three_component(W, mesh, sol_0, 0.1, f_source=S, K=1.0)
+        solve(a == L, sol, bcs)
+        sol_0 = sol                                     # the aliasing the reference scripts do (CCS_3comp.py:262)
+        prev, _ = forms.monolithic_step(asm, oprm, prev, f, obc)
+        assert rel(sol.get(3), prev.c0) < 1e-8 and rel(sol.get(4), prev.c1) < 1e-8 and rel(sol.get(5), prev.c2) < 1e-8
+        assert rel(sol.get(2), prev.p) < 1e-8
+        assert rel(np.concatenate([sol.get(0), sol.get(1)]), np.concatenate(prev.u)) < 1e-8
