@@ -6,7 +6,7 @@ Workload (config.workload): CCS reactive 3-component transport (form a5, mupopp.
 recovery + P1 transport), BoxMesh [0,4]x[0,4]x[0,1] with n^3 hexes -> 6 n^3 tets, n = 200: 8 120 601 P1 dofs per field.
 One "step" = one full timestep: c1,c2 mass solves -> c0 SUPG-ADR assemble+solve -> pressure solve -> velocity recovery.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n 200]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size 200]
 
 N > 1 (torchrun, one rank per GPU): the SAME mesh is partitioned into z-slabs (strong scaling), NCCL halo
 exchange + allreduce inside the Krylov loops.
@@ -316,12 +316,12 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=200, help="hexes per direction (200 -> 8 120 601 dofs/field, the metric's size)")
+    ap.add_argument("--size", dest="n", type=int, default=200, help="hexes per direction (200 -> 8 120 601 dofs/field, the metric's size)")
     ap.add_argument("--ref-n", type=int, default=40, help="sample size of the CPU oracle leg")
     ap.add_argument("--rtol", type=float, default=1e-12)
     ap.add_argument("--maxit", type=int, default=50000)
     ap.add_argument("--c0-method", default="gmres", choices=["gmres", "bicgstab"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--sides", default="natural", choices=["natural", "noflow"],
                     help="x/y faces: natural (p=0, as CCS_3D_side_source.py) or impermeable (u.n=0)")
     args = ap.parse_args()

@@ -203,6 +203,18 @@ int mp_nccl_unique_id(uint8_t *out128) {
     return 0;
 }
 
+}  // extern "C"
+
+namespace mp {
+int allreduce_oop(mp_ctx *c, const double *d_send, double *d_recv, int count) {
+    if (c->nranks <= 1 || !c->nccl_comm || count == 0) return 0;
+    MP_NCCL(g_nccl.AllReduce(d_send, d_recv, (size_t)count, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream));
+    return 0;
+}
+}  // namespace mp
+
+extern "C" {
+
 int mp_comm_init(mp_ctx *c, int nranks, int rank, const uint8_t *id128) {
     MP_CHECK(c && id128 && nranks >= 1 && rank >= 0 && rank < nranks, "mp_comm_init: bad argument");
     MP_TRY(mp::nccl_load());
@@ -212,6 +224,9 @@ int mp_comm_init(mp_ctx *c, int nranks, int rank, const uint8_t *id128) {
     MP_NCCL(mp::g_nccl.CommInitRank(&c->nccl_comm, nranks, id, rank));
     c->nranks = nranks;
     c->rank = rank;
+    // reductions now land in the rank-local scalar block (see grid_reduce in krylov.cu)
+    const unsigned int off = nranks > 1 ? (unsigned int)mp::kLocalOff : 0u;
+    MP_CUDA(cudaMemcpy(c->d_counter + 1, &off, sizeof(off), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -221,6 +236,7 @@ int mp_comm_destroy(mp_ctx *c) {
         mp::g_nccl.CommDestroy(c->nccl_comm);
         c->nccl_comm = nullptr;
         c->nranks = 1; c->rank = 0;
+        cudaMemset(c->d_counter + 1, 0, sizeof(unsigned int));
     }
     return 0;
 }

@@ -35,9 +35,12 @@ __device__ __forceinline__ double safe_div(double a, double b) { return b == 0.0
 
 // Block-level sum of NR accumulators, partials to global, the last block to arrive adds the partials in a
 // fixed order and stores the results: no floating-point atomics => bitwise reproducible for a given grid.
+// Multi-GPU: rank-local sums go to the LOCAL copy of the scalar block (offset counter[1] = kLocalOff) and an out-of-place
+// ncclAllReduce(local -> global) follows; kernels only ever READ the global copy.  This keeps the allreduce idempotent when the
+// producing kernel has become a no-op after convergence (an in-place allreduce would multiply the stale value by nranks).
 template <int NR>
 __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restrict__ partials, unsigned int *counter,
-                                            double *__restrict__ scal, const int (&slots)[NR], bool bump_iter) {
+                                            double *__restrict__ scal, const int (&slots)[NR], bool bump_iter, bool use_off = true) {
     __shared__ double sm[NR][kThreads / 32];
     __shared__ bool last;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -75,7 +78,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restric
         if (threadIdx.x == 0) {
             double s = 0.0;
             for (int k = 0; k < kThreads / 32; ++k) s += sm[r][k];
-            scal[slots[r]] = s;
+            scal[slots[r] + (use_off ? (int)counter[1] : 0)] = s;
         }
     }
     if (threadIdx.x == 0) {
@@ -516,6 +519,12 @@ int nnz_of(mp_ctx *ctx, const mp_csr *A, int64_t *nnz) {
     return 0;
 }
 
+// rank-local slot values (written at +kLocalOff by grid_reduce) -> global slots on every rank; no-op on one GPU
+int reduce_slots(mp_ctx *ctx, int slot, int count) {
+    if (ctx->nranks <= 1) return 0;
+    return mp::allreduce_oop(ctx, ctx->d_scalars + mp::kLocalOff + slot, ctx->d_scalars + slot, count);
+}
+
 int poll(mp_ctx *ctx) {
     MP_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -532,8 +541,8 @@ int check_csr(const mp_csr *A, bool for_solver = true) {
 // first == true: set the tolerance from ||b|| and zero the iteration counter (one synchronising poll per solve);
 // first == false (restart): only test the freshly evaluated TRUE residual against the stored tolerance.
 int start_solve(mp_ctx *ctx, mp_solve_info *info, bool first, bool *done) {
-    MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_BB, 1));
-    MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RR, 1));
+    MP_TRY(reduce_slots(ctx, S_BB, 1));
+    MP_TRY(reduce_slots(ctx, S_RR, 1));
     MP_TRY(poll(ctx));
     const double bb = ctx->h_scalars[S_BB], rr = ctx->h_scalars[S_RR];
     if (!first) {
@@ -570,7 +579,7 @@ namespace {
 // Small dense data of one cycle, all on the device: R (upper triangular, column major, ld = m+1), Givens (cs, sn),
 // rotated rhs g, solution y, and the two Gram-Schmidt coefficient columns h1, h2 (classical GS applied twice).
 struct GmresSmall {
-    double *R, *cs, *sn, *g, *y, *h1, *h2;
+    double *R, *cs, *sn, *g, *y, *h1, *h2, *h1loc, *h2loc;
     int m;
 };
 
@@ -606,7 +615,7 @@ __global__ void __launch_bounds__(kThreads) k_multidot8(int64_t n, const double 
             if (v < cnt) acc[v] += V[(int64_t)(k0 + v) * ld + i] * wi;
     }
     const int sl_[8] = {k0, k0 + 1, k0 + 2, k0 + 3, k0 + 4, k0 + 5, k0 + 6, k0 + 7};
-    grid_reduce<8>(acc, partials, counter, out, sl_, false);
+    grid_reduce<8>(acc, partials, counter, out, sl_, false, false);
 }
 
 // w -= sum_{k<=j} h[k] V_k ; optionally slot S_TMP0 = ||w||^2
@@ -707,13 +716,13 @@ extern "C" int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv
     double *wk = nullptr, *sm = nullptr;
     MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)((m + 3) * n + nc + 8), (void **)&wk));
     const int pad = m + 16;  // k_multidot8 always stores 8 slots
-    const size_t nsmall = (size_t)(m + 1) * m + 7 * (size_t)pad;
+    const size_t nsmall = (size_t)(m + 1) * m + 9 * (size_t)pad;
     MP_TRY(mp::ws_get(ctx, 1, sizeof(double) * nsmall, (void **)&sm));
     double *V = wk, *w = wk + (int64_t)(m + 1) * n, *r = w + n, *z = r + n;  // z has ghost entries
     GmresSmall S;
     S.m = m;
     S.R = sm; S.cs = S.R + (size_t)(m + 1) * m; S.sn = S.cs + pad; S.g = S.sn + pad; S.y = S.g + pad;
-    S.h1 = S.y + pad; S.h2 = S.h1 + pad;
+    S.h1 = S.y + pad; S.h2 = S.h1 + pad; S.h1loc = S.h2 + pad; S.h2loc = S.h1loc + pad;
     const int g1 = grid_for(ctx, n);
     const int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 5 : 25);
     int total = 0;
@@ -735,17 +744,18 @@ extern "C" int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv
             MP_TRY((launch_spmv<0, true>(ctx, A, lanes, z, w, nullptr, 0, 0)));
             for (int pass = 0; pass < 2; ++pass) {   // classical Gram-Schmidt, applied twice
                 double *h = pass == 0 ? S.h1 : S.h2;
+                double *hl = ctx->nranks > 1 ? (pass == 0 ? S.h1loc : S.h2loc) : h;   // rank-local dots, then out-of-place allreduce
                 for (int k0 = 0; k0 <= j; k0 += 8) {
                     const int cnt = (j + 1 - k0) < 8 ? (j + 1 - k0) : 8;
-                    k_multidot8<<<g1, kThreads, 0, ctx->stream>>>(n, V, n, k0, cnt, w, ctx->d_partials, ctx->d_counter, h, ctx->d_scalars);
+                    k_multidot8<<<g1, kThreads, 0, ctx->stream>>>(n, V, n, k0, cnt, w, ctx->d_partials, ctx->d_counter, hl, ctx->d_scalars);
                     mp::count_launch(ctx);
                 }
-                MP_TRY(mp_allreduce_sum(ctx, h, j + 1));
+                if (ctx->nranks > 1) MP_TRY(mp::allreduce_oop(ctx, hl, h, j + 1));
                 if (pass == 0) k_gmres_orth<false><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_counter, ctx->d_scalars);
                 else k_gmres_orth<true><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_counter, ctx->d_scalars);
                 mp::count_launch(ctx);
             }
-            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_TMP0, 1));
+            MP_TRY(reduce_slots(ctx, S_TMP0, 1));
             k_gmres_normalize<<<g1, kThreads, 0, ctx->stream>>>(n, w, d_dinv, V + (int64_t)(j + 1) * n, z, ctx->d_scalars);
             k_gmres_givens<<<1, 32, 0, ctx->stream>>>(j, S, ctx->d_scalars);
             mp::count_launch(ctx, 2);
@@ -799,7 +809,7 @@ extern "C" int mp_dot(mp_ctx *ctx, int64_t n, const double *d_x, const double *d
     k_dot<<<grid_for(ctx, n > 0 ? n : 1), kThreads, 0, ctx->stream>>>(n, d_x, d_y, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_TMP0);
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
-    MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_TMP0, 1));
+    MP_TRY(reduce_slots(ctx, S_TMP0, 1));
     MP_CUDA(cudaMemcpyAsync(ctx->h_scalars + S_TMP0, ctx->d_scalars + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
     *result = ctx->h_scalars[S_TMP0];
@@ -838,7 +848,7 @@ extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, 
         k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, p, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RZ0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
-        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RZ0, 1));
+        MP_TRY(reduce_slots(ctx, S_RZ0, 1));
         bool done = false;
         MP_TRY(start_solve(ctx, info, restart == 0, &done));
         if (done || total >= info->maxit) break;
@@ -846,9 +856,9 @@ extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, 
         for (; total < info->maxit;) {
             MP_TRY(mp_halo_exchange(ctx, halo, p));
             MP_TRY((launch_spmv<1, true>(ctx, A, lanes, p, q, p, S_PQ, 0)));
-            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_PQ, 1));
+            MP_TRY(reduce_slots(ctx, S_PQ, 1));
             k_cg_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_dinv, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
-            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + (nxt < S_RR ? nxt : S_RR), 2));
+            MP_TRY(reduce_slots(ctx, (nxt < S_RR ? nxt : S_RR), 2));
             k_cg_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, r, d_dinv, p, ctx->d_scalars, cur, nxt);
             mp::count_launch(ctx, 2);
             int tmp = cur; cur = nxt; nxt = tmp;
@@ -884,7 +894,7 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
         k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, v, d_dinv, r, nullptr, rhat, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RHO0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
-        MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RHO0, 1));
+        MP_TRY(reduce_slots(ctx, S_RHO0, 1));
         bool done = false;
         MP_TRY(start_solve(ctx, info, restart == 0, &done));
         if (done || total >= info->maxit) break;
@@ -893,13 +903,13 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
             k_bicg_p<<<g1, kThreads, 0, ctx->stream>>>(n, it == 0 ? 1 : 0, r, v, d_dinv, p, y, ctx->d_scalars, cur);
             MP_TRY(mp_halo_exchange(ctx, halo, y));
             MP_TRY((launch_spmv<1, true>(ctx, A, lanes, y, v, rhat, S_RV, 0)));
-            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_RV, 1));
+            MP_TRY(reduce_slots(ctx, S_RV, 1));
             k_bicg_s<<<g1, kThreads, 0, ctx->stream>>>(n, r, v, d_dinv, s, z, ctx->d_scalars, cur);
             MP_TRY(mp_halo_exchange(ctx, halo, z));
             MP_TRY((launch_spmv<2, true>(ctx, A, lanes, z, t, s, S_TS, S_TT)));
-            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + S_TS, 2));
+            MP_TRY(reduce_slots(ctx, S_TS, 2));
             k_bicg_x<<<g1, kThreads, 0, ctx->stream>>>(n, y, z, s, t, rhat, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
-            MP_TRY(mp_allreduce_sum(ctx, ctx->d_scalars + (nxt < S_RR ? nxt : S_RR), 2));
+            MP_TRY(reduce_slots(ctx, (nxt < S_RR ? nxt : S_RR), 2));
             mp::count_launch(ctx, 3);
             int tmp = cur; cur = nxt; nxt = tmp;
             ++total;
