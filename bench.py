@@ -98,7 +98,7 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def oracle_step_time(n, rtol, steps, warm):
+def oracle_step_time(n, rtol, steps, warm, sides="noflow"):
     """The oracle's mode-F timestep (NumPy assembly + SciPy cg/bicgstab with Jacobi) on an n^3 sample."""
     from oracle import fem, forms, modef
     m = fem.box_mesh(BOX[0], BOX[1], n, n, n)
@@ -106,7 +106,10 @@ def oracle_step_time(n, rtol, steps, warm):
     prm = forms.ccs_three_component_params(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"], dt=PHYS["dt"],
                                            K=PHYS["K"], zhat=(0.0, 0.0, 1.0), gam_rho=PHYS["gam_rho"])
     top = lambda x: x[2] > 1.0 - 1e-12
-    bcs = modef.make_bcs(m, top, lambda x: np.array([0.0, 0.0, -0.5]), top, 0.1)
+    if sides == "noflow":
+        bcs = modef.make_bcs(m, lambda x: x[2] > 1e-12, lambda x: np.array([0.0, 0.0, -0.5 if x[2] > 1.0 - 1e-12 else 0.0]), top, 0.1)
+    else:
+        bcs = modef.make_bcs(m, top, lambda x: np.array([0.0, 0.0, -0.5]), top, 0.1)
     f = source_term(m.coords)
     st = modef.StateF(u=np.zeros((m.nc, 3)), p=np.zeros(m.nv), c0=np.zeros(m.nv), c1=0.1 * np.ones(m.nv), c2=np.zeros(m.nv))
     times, iters = [], []
@@ -128,7 +131,7 @@ def run_reference(args):
         return 0
     n = args.ref_n
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-    ndof, times, iters = oracle_step_time(n, args.rtol, args.steps, min(args.warmup, 1))
+    ndof, times, iters = oracle_step_time(n, args.rtol, args.steps, min(args.warmup, 1), args.sides)
     ms = 1e3 * float(np.mean(times))
     ndof_full = (args.n + 1) ** 3
     # scale the sample to the full workload linearly in dofs (optimistic for the CPU: Krylov iteration counts grow with n)
@@ -294,7 +297,7 @@ def run_b200(args):
                             "share_of_step": spmv_ms / ms_total}}
         if not args.no_cpu and nranks == 1:
             try:
-                ndof, times, oit = oracle_step_time(args.ref_n, args.rtol, 1, 0)
+                ndof, times, oit = oracle_step_time(args.ref_n, args.rtol, 1, 0, args.sides)
                 cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
                 v = 1.0 / (np.mean(times) * (args.n + 1) ** 3 / ndof)
                 out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": cores,
@@ -322,9 +325,14 @@ def main():
     ap.add_argument("--maxit", type=int, default=50000)
     ap.add_argument("--c0-method", default="gmres", choices=["gmres", "bicgstab"])
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--sides", default="natural", choices=["natural", "noflow"],
-                    help="x/y faces: natural (p=0, as CCS_3D_side_source.py) or impermeable (u.n=0)")
+    ap.add_argument("--sides", default="noflow", choices=["natural", "noflow"],
+                    help="x/y faces: impermeable u.n=0 (default; same uniform-inflow regime as the reference's periodic sides, "
+                         "CCS_3comp.py:131-143) or natural p=0 (CCS_3D_side_source.py)")
+    ap.add_argument("--hard-timeout", type=int, default=1500, help="SIGALRM kills the process after this many seconds (never hang a box)")
     args = ap.parse_args()
+    if args.hard_timeout > 0:
+        import signal
+        signal.alarm(args.hard_timeout)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -724,7 +724,7 @@ extern "C" int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv
     S.R = sm; S.cs = S.R + (size_t)(m + 1) * m; S.sn = S.cs + pad; S.g = S.sn + pad; S.y = S.g + pad;
     S.h1 = S.y + pad; S.h2 = S.h1 + pad; S.h1loc = S.h2 + pad; S.h2loc = S.h1loc + pad;
     const int g1 = grid_for(ctx, n);
-    const int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 5 : 25);
+    const int every = info->check_every > 0 ? info->check_every : 10;   // rank-independent (collective control flow)
     int total = 0;
     for (int cycle = 0; cycle < 100000; ++cycle) {
         // true residual r = b - A x at the start of every cycle
@@ -838,7 +838,7 @@ extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, 
     MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(2 * n + nc + 8), (void **)&w));
     double *r = w, *q = w + n, *p = w + 2 * n;  // p has ghost entries
     const int g1 = grid_for(ctx, n);
-    const int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 10 : 50);
+    const int every = info->check_every > 0 ? info->check_every : 20;   // must NOT depend on the rank-local size: all ranks poll together
     int total = 0;
     // outer loop = residual replacement: after the recurrence says "converged" the TRUE residual b - A x is
     // evaluated and the iteration restarted from x if it is not below the tolerance yet.
@@ -886,7 +886,7 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
     MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(6 * n + 2 * nc + 8), (void **)&w));
     double *r = w, *rhat = w + n, *p = w + 2 * n, *v = w + 3 * n, *s = w + 4 * n, *t = w + 5 * n, *y = w + 6 * n, *z = w + 6 * n + nc;
     const int g1 = grid_for(ctx, n);
-    const int every = info->check_every > 0 ? info->check_every : (n >= (1 << 20) ? 5 : 25);
+    const int every = info->check_every > 0 ? info->check_every : 10;   // rank-independent (collective control flow)
     int total = 0;
     for (int restart = 0; restart <= kMaxRestart; ++restart) {   // residual replacement, see mp_solve_pcg
         MP_TRY(mp_halo_exchange(ctx, halo, d_x));
