@@ -89,7 +89,7 @@ typedef struct {
     double Kconst;               /* used when d_K == NULL */
     int32_t reaction;            /* 0: Da*c0*c1 (CCS)   1: Da*c0*c1^2 (DarcyAdvection)   2: Da*c0 (single component, mupopp.py:650) */
     int32_t ncomp;               /* 1 (quadrature kernel only), 2 or 3 concentration fields */
-    int32_t supg;                /* 1 Sendur, 2 Codina, 3 Brooks-Hughes: mupopp.py:835-846; 4: h/(2|w|) (mupopp.py:663) */
+    int32_t supg;                /* 1 Sendur, 2 Codina, 3 Brooks-Hughes: mupopp.py:835-846; 4: h/(2|w|) (mupopp.py:663); 5: Sendur + Da*c1^n(x)/phi (mupopp.py:738, quadrature kernel only) */
     int32_t pad;
 } mp_transport_params;
 

@@ -566,6 +566,8 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport_quad(mp_mesh m, mp_tr
         if (fsrc) gather<D>(fsrc, G, f);
         if (P.ncomp >= 2) { gather<D>(c1n, G, a1); gather<D>(c1new, G, n1); }
         if (P.ncomp == 3) { gather<D>(c2n, G, a2); gather<D>(c2new, G, n2); }
+    } else if (P.supg == 5) {
+        gather<D>(c1n, G, a1);
     }
     double gc0[D], gg[D + 1][D + 1];
 #pragma unroll
@@ -613,7 +615,14 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport_quad(mp_mesh m, mp_tr
 #pragma unroll
         for (int a = 0; a < D; ++a) vn2 += u[a] * u[a];
         const double vn = sqrt(vn2);
-        const double tau = P.supg == 4 ? G.h / (2.0 * vn) : tau_supg(P.supg, P.Pe, P.Da, G.h, vn);
+        double tau;
+        if (P.supg == 4) tau = G.h / (2.0 * vn);                       // mupopp.py:663
+        else if (P.supg == 5) {                                        // mupopp.py:738: Sendur + Da*c1^n(x)/phi (np.max is a UFL no-op)
+            double c1p = 0.0;
+#pragma unroll
+            for (int i = 0; i <= D; ++i) c1p += lam[i] * a1[i];
+            tau = 1.0 / (4.0 / (P.Pe * G.h * G.h) + 2.0 * vn / G.h + P.Da * c1p / P.phi);
+        } else tau = tau_supg(P.supg, P.Pe, P.Da, G.h, vn);
         double ug[D + 1];
 #pragma unroll
         for (int i = 0; i <= D; ++i) {
@@ -791,6 +800,7 @@ extern "C" int mp_elem_p1_transport_quad(mp_ctx *ctx, const mp_mesh *mesh, const
     MP_CHECK(prm && quad && quad->nq > 0 && quad->nbv > 0 && quad->d_w && quad->d_lam && quad->d_vphi, "mp_elem_p1_transport_quad: bad quadrature");
     MP_CHECK(d_vel_dofs && d_vel0 && d_vel1 && (mesh->dim == 2 || d_vel2), "mp_elem_p1_transport_quad: velocity pointers");
     MP_CHECK(!d_elem_vec || d_c0n, "mp_elem_p1_transport_quad: rhs needs c0n");
+    MP_CHECK(prm->supg != 5 || d_c1n, "mp_elem_p1_transport_quad: supg==5 needs c1n");
     MP_CHECK(!d_elem_vec || prm->ncomp < 2 || (d_c1n && d_c1new), "mp_elem_p1_transport_quad: ncomp>=2 needs c1n,c1new");
     MP_CHECK(!d_elem_vec || prm->ncomp < 3 || (d_c2n && d_c2new), "mp_elem_p1_transport_quad: ncomp==3 needs c2n,c2new");
     QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};

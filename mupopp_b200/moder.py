@@ -296,3 +296,43 @@ class TransportSolverR:
         if three:
             self.c2 = c2new
         return dict(c0=r0, outer=outer)
+
+
+def adaptive_source(X):
+    """Hard-coded source of DarcyAdvection.advection_diffusion_two_component_adaptive (mupopp.py:693-698; `3.14`, not pi),
+    nodally interpolated as `Expression(..., degree=1)` is."""
+    s = np.zeros(X.shape[0])
+    for k in range(1, 11):
+        s += 1.0 + np.sin(k * X[:, 0] * 3.14)
+    return (1.0 - np.tanh(X[:, 1] / 0.01)) * s / 20.0
+
+
+class TwoComponentAdaptiveR:
+    """DarcyAdvection.advection_diffusion_two_component_adaptive (mupopp.py:667-749): [c0, c1] with a given velocity;
+    f = Da*c0^n*c1^n, tau = 1/(4/(Pe h^2) + 2|u|/h + Da*c1^n/phi).  The DG0 projection at :704-710 is dead code (result unused)."""
+
+    def __init__(self, ctx: Context, spaces: Spaces, Pe, Da, phi, alpha, dt, c0_isbc, c0_g, vel_degree=2, rtol=1e-13):
+        self.ctx, self.sp, self.rtol = ctx, spaces, rtol
+        d = spaces.mesh.dim
+        self.prm = transport_params(Pe, Da, phi, alpha, dt, 0.0, 0.0, 0.0, (1.0, 1.0, 0.0), (0.0,) * d, 1.0, "c0c1", 2, 5)
+        self.adr = AdrSolverR(ctx, spaces, self.prm, c0_isbc, c0_g, vel_degree=vel_degree, rtol=rtol)
+        p11 = spaces.plan(1, 1)
+        self.p11 = p11
+        self.M1 = p11.new_matrix(sell=True)
+        emat = ctx.empty(spaces.dm.ncell * (d + 1) ** 2)
+        check(ctx.lib.mp_elem_p1_mass(ctx.h, C.byref(spaces.dm.c), 1.0, ptr(emat)), "mp_elem_p1_mass")
+        p11.scatter_matrix(emat, self.M1)
+        self.M1.jacobi_setup()
+        self.evec = ctx.empty(spaces.dm.ncell * (d + 1))
+        self.rhs1 = ctx.zeros(spaces.n1)
+        self.fsrc = ctx.to_device(adaptive_source(spaces.mesh.coords))
+
+    def step(self, vel, c0n, c1n, c0_out, c1_out):
+        ctx = self.ctx
+        check(ctx.lib.mp_elem_p1_reaction_rhs(ctx.h, C.byref(self.sp.dm.c), C.byref(self.prm), ptr(c0n), ptr(c1n), None, ptr(self.evec), None),
+              "mp_elem_p1_reaction_rhs")
+        self.p11.scatter_vector(self.evec, self.rhs1)
+        c1_out.copy_(c1n)
+        self.M1.solve("pcg", self.rhs1, c1_out, rtol=self.rtol, refresh_jacobi=False)
+        c0_out.copy_(c0n)
+        return self.adr.solve(vel, c0n, c0_out, c1n=c1n, c1new=c1_out, fsrc=self.fsrc)

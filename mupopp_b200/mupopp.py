@@ -274,4 +274,18 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
         if nc == 3:
             u.blocks[dim + 3].copy_(s.c2)
         return info_
-    raise NotImplementedError("solve: form kind %r is not on the B200 path yet (SURVEY.md section 8 rows a6-a10)" % kind)
+    if kind == "two_component_adaptive":
+        Q, mesh, own = d["Q"], d["mesh"], d["owner"]
+        key = ("adaptive", id(Q), own.Pe, own.Da, own.phi, own.alpha, own.dt, _bc_key(bcs))
+        if key not in _CACHE:
+            sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+            arr = _bc_arrays(Q, bcs, [Q.sub_blocks[0][0]])
+            b0 = Q.sub_blocks[0][0]
+            _CACHE[key] = moder.TwoComponentAdaptiveR(ctx, sp, own.Pe, own.Da, own.phi, own.alpha, own.dt, arr[b0][0], arr[b0][1],
+                                                      vel_degree=d["velocity"].block_degree(0))
+        s = _CACHE[key]
+        prev = d["c_prev"]
+        c0n, c1n = prev.blocks[0].clone(), prev.blocks[1].clone()
+        res = s.step(d["velocity"].blocks, c0n, c1n, u.blocks[0], u.blocks[1])
+        return res.niter
+    raise NotImplementedError("solve: form kind %r is not on the B200 path yet (SURVEY.md section 8 rows a7-a10)" % kind)

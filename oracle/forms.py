@@ -78,8 +78,10 @@ def ccs_three_component_params(Pe=100, Da=10.0, phi=0.01, alpha=0.005, dt=0.01, 
                            SUPG=SUPG, zhat=zhat)
 
 
-def tau_supg(SUPG, Pe, Da, h, vnorm):
-    """mupopp.py:835-846 (identical at :945-956, :1245-1256)."""
+def tau_supg(SUPG, Pe, Da, h, vnorm, extra=0.0):
+    """mupopp.py:835-846 (identical at :945-956, :1245-1256); SUPG == 5: mupopp.py:738 with extra = Da*c1^n(x)/phi."""
+    if SUPG == 5:
+        return 1.0 / (4.0 / (Pe * h * h) + 2.0 * vnorm / h + extra)
     if SUPG == 1:
         return 1.0 / (4.0 / (Pe * h * h) + 2.0 * vnorm / h)
     if SUPG == 2:
@@ -178,7 +180,7 @@ class Assembler:
         return np.stack([fem.eval_at_quad(s, np.asarray(c), ph) for c in data], axis=-1)
 
     # ---- the c0 row: CN + SUPG advection-diffusion-reaction ---------------
-    def c0_row(self, prm: TransportParams, vel, qdeg):
+    def c0_row(self, prm: TransportParams, vel, qdeg, c1n=None):
         """Matrix pieces of the c0 row (mupopp.py:823-848 and twins):
            A00 = int eta*phi + dt/2 [eta u.grad(phi) + grad(eta).grad(phi)/Pe] + tau (u.grad eta)(phi + dt/2 u.grad phi)
            S   = int tau (u.grad eta) phi           (coupling to the NEW c1, c2 through r)
@@ -187,7 +189,8 @@ class Assembler:
         g = fem.phys_grads(dref, self.Jinv)                         # (C,q,b,d)
         uq = self.velocity_q(vel, qdeg)                             # (C,q,d)
         vn = np.sqrt((uq * uq).sum(-1))
-        tau = tau_supg(prm.SUPG, prm.Pe, prm.Da, self.h[:, None], vn)
+        extra = prm.Da * fem.eval_at_quad(self.P1, c1n, p1) / prm.phi if prm.SUPG == 5 else 0.0
+        tau = tau_supg(prm.SUPG, prm.Pe, prm.Da, self.h[:, None], vn, extra)
         ug = np.einsum("cqd,cqbd->cqb", uq, g, optimize=True)       # u.grad(basis)
         wd = w[None, :] * self.detJ[:, None]
         dt = prm.dt
@@ -414,3 +417,36 @@ def segregated_step(asm: Assembler, prm: TransportParams, prev: State, fsrc, bcs
     rhs_u = [-prm.sigma * prm.zhat[c] * (prm.rho0 * lK + prm.gamma * Gc0) for c in range(d)]
     u, p = solve_saddle(asm, prm, M, B, BK, rhs_u, bcs)
     return State(u=u, p=p, c0=c0, c1=c1, c2=c2)
+
+
+# --------------------------------------------------------------------------- a6: two-component adaptive form
+
+def adaptive_source(X):
+    """The hard-coded source of mupopp.py:693-698 (`3.14`, not pi), nodally interpolated (degree=1)."""
+    s = np.zeros(X.shape[0])
+    for k in range(1, 11):
+        s += 1.0 + np.sin(k * X[:, 0] * 3.14)
+    return (1.0 - np.tanh(X[:, 1] / 0.01)) * s / 20.0
+
+
+def two_component_adaptive_params(Pe, Da, phi, alpha, dt):
+    """mupopp.py:667-749: f = Da*u0*c0 (bilinear), R1 = f/phi, R2 = f/(1-phi), source alpha/phi*dt*f1, tau with Da*c1^n/phi."""
+    return TransportParams(Pe=Pe, Da=Da, phi=phi, alpha=alpha, dt=dt, K=1.0, sigma=0.0, rho0=0.0, gamma=0.0, reaction="c0c1",
+                           fracs=(1.0, 1.0, 0.0), ncomp=2, SUPG=5, zhat=(0.0, 1.0))
+
+
+def two_component_adaptive_step(asm: Assembler, prm: TransportParams, vel, c0n, c1n, fsrc, c0_dofs, c0_vals, qdeg=None):
+    """Monolithic [c0, c1] solve of DarcyAdvection.advection_diffusion_two_component_adaptive with a given velocity
+    (`project(advect_term, DG0)` at mupopp.py:704-710 is dead code: its result is unused)."""
+    qdeg = qdeg or QDEG["c0row"]
+    n1 = asm.P1.ndof
+    A00, S, qd = asm.c0_row(prm, vel, qdeg, c1n=c1n)
+    M1 = asm.mass(1, 1, QDEG["mass_p1"])
+    b0 = asm.c0_rhs(prm, qd, c0n, c1n, None, fsrc, qdeg)
+    R1, R2, R3 = asm.reaction_q(prm, c0n, c1n, QDEG["react"])
+    b1 = M1 @ c1n - prm.dt / (1 - prm.phi) * asm.load(1, QDEG["react"], R2)
+    A = sp.bmat([[A00, S], [None, M1]], format="csr")
+    b = np.concatenate([b0, b1])
+    Abc, bbc = fem.apply_dirichlet_symmetric(A, b, np.asarray(c0_dofs, dtype=np.int64), np.asarray(c0_vals, dtype=float))
+    x = spla.splu(Abc.tocsc()).solve(bbc)
+    return x[:n1], x[n1:]

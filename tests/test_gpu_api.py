@@ -86,3 +86,39 @@ def test_ccs_three_component_through_api(ctx):
         assert rel(sol.get(3), prev.c0) < 1e-8 and rel(sol.get(4), prev.c1) < 1e-8 and rel(sol.get(5), prev.c2) < 1e-8
         assert rel(sol.get(2), prev.p) < 1e-8
         assert rel(np.concatenate([sol.get(0), sol.get(1)]), np.concatenate(prev.u)) < 1e-8
+
+
+def test_two_component_adaptive_through_api(ctx):
+    """DarcyAdvection.advection_diffusion_two_component_adaptive (mupopp.py:667-749) == oracle monolithic [c0,c1] LU."""
+    from mupopp_b200.fenics import (Constant, DirichletBC, DOLFIN_EPS, FiniteElement, Function, FunctionSpace, MixedElement,
+                                    RectangleMesh, VectorFunctionSpace, solve)
+    from mupopp_b200.mupopp import DarcyAdvection
+    nx, ny = 8, 6
+    mesh = RectangleMesh((0.0, 0.0), (2.0, 1.0), nx, ny)
+    P1 = FiniteElement("Lagrange", mesh.ufl_cell(), 1)
+    Q = FunctionSpace(mesh, MixedElement([P1, P1]))
+    V = VectorFunctionSpace(mesh, "CG", 2)
+    om = fem.rectangle_mesh(0, 0, 2, 1, nx, ny)
+    asm = forms.Assembler(om)
+    n1, n2 = asm.P1.ndof, asm.P2.ndof
+    rng = np.random.default_rng(0)
+    vel_h = [0.3 + 0.1 * rng.random(n2), -0.5 + 0.1 * rng.random(n2)]
+    c0n, c1n = 0.1 * rng.random(n1), 0.2 + 0.1 * rng.random(n1)
+    vel = Function(V)
+    vel.vector().set_local(np.concatenate(vel_h))
+    c_prev = Function(Q)
+    c_prev.vector().set_local(np.concatenate([c0n, c1n]))
+    top = lambda x: x[1] > 1.0 - DOLFIN_EPS
+    bcs = [DirichletBC(Q.sub(0), Constant(1.0), top)]
+    model = DarcyAdvection(Pe=100, Da=10.0, phi=0.01, alpha=0.005, dt=0.01)
+    sol = Function(Q)
+    oprm = forms.two_component_adaptive_params(100.0, 10.0, 0.01, 0.005, 0.01)
+    topd = np.where(om.coords[:, 1] > 1 - 1e-12)[0]
+    for k in range(2):
+        a, L = model.advection_diffusion_two_component_adaptive(Q, c_prev, vel, mesh)
+        solve(a == L, sol, bcs)
+        o0, o1 = forms.two_component_adaptive_step(asm, oprm, ("P2", vel_h), c0n, c1n, forms.adaptive_source(om.coords), topd, np.ones(len(topd)))
+        assert rel(sol.get(1), o1) < 1e-10
+        assert rel(sol.get(0), o0) < 1e-9
+        c_prev = sol
+        c0n, c1n = o0, o1
