@@ -118,6 +118,7 @@ int mp_recover_velocity(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_par
 /* Generic affine element kernel ("tensor representation"): elem_mat[c][i][j] = scale * sum_t geo_t(c) * T0[t][i][j]
  *   kind 0 MASS  (1 tensor,  geo = |detJ|)                      kind 1 GRAD  (dim tensors, geo_a = |detJ| Jinv[a][dir]: row value x column d/dx_dir)
  *   kind 2 GRADT (as GRAD with row derivative x column value)   kind 3 STIFF (dim^2 tensors, geo_ab = |detJ| (Jinv Jinv^T)_ab)
+ *   kind 4 SYMGRAD: block (a,b) = (dir/dim, dir%dim) of 2 symgrad(u):symgrad(v) with the STIFF tensors (compaction, mupopp.py:361)
  * coef_kind 0 none | 1 nodal P1 d_coef[nvert], integrated exactly (T0 then has (dim+1) sub-tensors per t) | 2 cellwise d_coef[ncell].
  * T0 comes from mupopp_b200/reference_element.py.  Mode R operators: P2 mass u.v, K div(v) p, div(u) q (mupopp.py:620,804-807,1201-1204). */
 int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
@@ -127,6 +128,7 @@ int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int l
 typedef struct {
     int32_t nq, nbv;
     const double *d_w, *d_lam, *d_vphi;
+    const double *d_vdphi;   /* optional: reference gradients of the velocity basis [nq][nbv][dim] (porosity row: div u) */
 } mp_quad;
 /* c0 row by numerical quadrature with a Lagrange (P1/P2) lagged velocity given per component (mode R); d_vel_dofs [ncell][nbv].
  * prm->ncomp may be 1 with prm->reaction == 2 (first order Da*c) and prm->supg == 4 (tau = h/(2|w|)):
@@ -135,6 +137,28 @@ int mp_elem_p1_transport_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_transpo
                               const int32_t *d_vel_dofs, const double *d_vel0, const double *d_vel1, const double *d_vel2,
                               const double *d_c0n, const double *d_c1n, const double *d_c2n, const double *d_c1new,
                               const double *d_c2new, const double *d_fsrc, double *d_elem_mat, double *d_elem_vec);
+
+/* ------------------------------------------------------------------ compaction forms (modules/mupopp.py:125-471)
+ * Coefficient functions of the P1 porosity evaluated at the points of the shared quadrature rule (degree 8: SURVEY.md appendix B):
+ *   fn 0: dL*phi*phi^(1/phi^3)  (mupopp.py:365, reproduced literally)   fn 1: dL/phi  (mupopp.py:380)   fn 2: eta = 3 phi/(2(1-phi)(2-phi))  (:346-347) */
+typedef struct {
+    double da, R, B, theta, dL;
+    double zhat[3];
+} mp_compaction_params;
+/* d_out[c] = cell average of fn(phi): the cellwise coefficient of the P1 stiffness blocks dL..grad(p).grad(q) */
+int mp_cell_fn(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, int fn, double dL, const double *d_phi, double *d_out);
+/* elem_mat[c][i][j] = scale * int fn(phi) lambda_i lambda_j   (-eta c omega, mupopp.py:366; 0.5 eta c omega, :380) */
+int mp_elem_p1_mass_fn(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, int fn, double dL, double scale, const double *d_phi,
+                       double *d_elem_mat);
+/* L = -(h.v + da R buoy gam q/(1 - R buoy)) dx, h = dL(1-phi)(chi grad(phi)/B - R buoy zhat) + da grad(4 gam/(3 phi))  (mupopp.py:356-357,374-375);
+ * evec_u<k> [ncell][nb2] per velocity component (P2 basis values in quad->d_vphi), evec_p [ncell][dim+1] */
+int mp_elem_compaction_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, const mp_compaction_params *prm, const double *d_phi,
+                           const double *d_gam, const double *d_buoy, double *d_evec_u0, double *d_evec_u1, double *d_evec_u2,
+                           double *d_evec_p);
+/* porosity row compaction.mass_conservation (mupopp.py:217-259): P1 porosity, P2 velocity (values + reference gradients in quad) */
+int mp_elem_p1_porosity_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, double da, double dt, const int32_t *d_vel_dofs,
+                             const double *d_vel0, const double *d_vel1, const double *d_vel2, const double *d_phi0, const double *d_gam,
+                             double *d_elem_mat, double *d_elem_vec);
 
 /* ------------------------------------------------------------------ linear algebra (PETSc Mat/Vec/KSP replacement)
  * Call sites replaced: KrylovSolver(...).solve modules/mupopp.py:289-303,410-425; the LU inside solve(a==L,..). */

@@ -33,7 +33,13 @@ class MpTransportParams(C.Structure):
 
 
 class MpQuad(C.Structure):
-    _fields_ = [("nq", C.c_int32), ("nbv", C.c_int32), ("d_w", C.c_void_p), ("d_lam", C.c_void_p), ("d_vphi", C.c_void_p)]
+    _fields_ = [("nq", C.c_int32), ("nbv", C.c_int32), ("d_w", C.c_void_p), ("d_lam", C.c_void_p), ("d_vphi", C.c_void_p),
+                ("d_vdphi", C.c_void_p)]
+
+
+class MpCompactionParams(C.Structure):
+    _fields_ = [("da", C.c_double), ("R", C.c_double), ("B", C.c_double), ("theta", C.c_double), ("dL", C.c_double),
+                ("zhat", C.c_double * 3)]
 
 
 class MpCsr(C.Structure):
@@ -79,6 +85,12 @@ SIGNATURES = {
     "mp_elem_reftensor": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int, C.c_double, _VP]),
     "mp_elem_p1_transport_quad": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), C.POINTER(MpQuad), _VP, _VP, _VP, _VP,
                                             _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
+    "mp_cell_fn": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.c_int, C.c_double, _VP, _VP]),
+    "mp_elem_p1_mass_fn": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.c_int, C.c_double, C.c_double, _VP, _VP]),
+    "mp_elem_compaction_rhs": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.POINTER(MpCompactionParams), _VP, _VP, _VP,
+                                         _VP, _VP, _VP, _VP]),
+    "mp_elem_p1_porosity_quad": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.c_double, C.c_double, _VP, _VP, _VP, _VP,
+                                           _VP, _VP, _VP, _VP]),
     "mp_spmv": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP]),
     "mp_dot": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.POINTER(C.c_double)]),
     "mp_axpby": (C.c_int, [_VP, C.c_int64, C.c_double, _VP, C.c_double, _VP]),

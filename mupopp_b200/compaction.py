@@ -1,0 +1,238 @@
+"""compaction forms on the GPU: split-field momentum system [u (P2^d), p (P1), c (P1)] and the
+CN + SUPG porosity row, for /root/reference/src/modules/mupopp.py:306-429 and :217-304.
+
+Assembly is block-wise: the viscous block 0.5(1-phi) symgrad:symgrad and the divergence blocks come from the generic reference-tensor
+kernel (exact for the P1 coefficient 1-phi); the blocks whose coefficients are non-polynomial in phi (dL*phi*phi^(1/phi^3), dL/phi,
+eta(phi)) and the right-hand side use the shared degree-8 quadrature rule.  The symmetric indefinite system is solved by MINRES
+preconditioned with the diagonal of the reference's own preconditioner form `b` (mupopp.py:379-380) -- the reference applies
+hypre AMG to that form; AMG is outside this build's scope.  The Krylov recurrence is driven from the host through the
+C-ABI BLAS-1 kernels because the operator is a composition of block SpMVs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import reference_element as ref
+from ._lib import MpCompactionParams, MpQuad, check, ptr
+from .device import Context
+from .moder import Spaces
+
+QDEG_COMPACTION = 8      # shared with oracle/compaction.py
+
+
+def _quad(ctx, dim, qdeg, with_grad=False):
+    w, lam, vphi = ref.quadrature_tables(dim, qdeg, 2)
+    t = dict(w=ctx.to_device(w), lam=ctx.to_device(lam.ravel()), vphi=ctx.to_device(vphi.ravel()))
+    dv = None
+    if with_grad:
+        t["vdphi"] = ctx.to_device(ref.basis_gradient_table(dim, qdeg, 2).ravel())
+        dv = t["vdphi"].data_ptr()
+    q = MpQuad(len(w), vphi.shape[1], t["w"].data_ptr(), t["lam"].data_ptr(), t["vphi"].data_ptr(), dv)
+    return q, t
+
+
+class BlockVector:
+    """[u_0 .. u_{d-1} | p | c] in one contiguous device buffer with per-block views."""
+
+    def __init__(self, ctx, d, n2, n1):
+        self.buf = ctx.zeros(d * n2 + 2 * n1)
+        self.u = [self.buf[a * n2:(a + 1) * n2] for a in range(d)]
+        self.p = self.buf[d * n2:d * n2 + n1]
+        self.c = self.buf[d * n2 + n1:]
+
+
+class CompactionMomentumR:
+    def __init__(self, ctx: Context, spaces: Spaces, da, R, B, theta, dL, zhat, u_isbc, u_g, qdeg=QDEG_COMPACTION):
+        self.ctx, self.sp = ctx, spaces
+        d = spaces.mesh.dim
+        self.d = d
+        self.prm = MpCompactionParams(float(da), float(R), float(B), float(theta), float(dL), (C.c_double * 3)(*[float(zhat[i]) if i < len(zhat) else 0.0 for i in range(3)]))
+        self.dL = float(dL)
+        self.quad, self._qt = _quad(ctx, d, qdeg)
+        n1, n2 = spaces.n1, spaces.n2
+        self.n1, self.n2 = n1, n2
+        self.Bdiv = [spaces.assemble("grad", 1, 2, direction=a) for a in range(d)]        # int q d_a psi   (constant)
+        self.BdivT = [spaces.assemble("gradT", 2, 1, direction=a) for a in range(d)]
+        self.mask = [ctx.to_device(1.0 - np.asarray(u_isbc[a], dtype=np.float64)) for a in range(d)]   # 0 on Dirichlet dofs
+        self.isbc = [ctx.to_device(np.asarray(u_isbc[a], dtype=np.uint8), torch.uint8) for a in range(d)]
+        self.g = [ctx.to_device(np.asarray(u_g[a], dtype=np.float64)) for a in range(d)]
+        self.p22, self.p11 = spaces.plan(2, 2), spaces.plan(1, 1)
+        self.Auu = [[self.p22.new_matrix(sell=True) for _ in range(d)] for _ in range(d)]
+        self.App, self.Acc = self.p11.new_matrix(sell=True), self.p11.new_matrix(sell=True)
+        self.Puu, self.Ppp, self.Pcc = self.p22.new_matrix(sell=False), self.p11.new_matrix(sell=False), self.p11.new_matrix(sell=False)
+        self.M1 = spaces.assemble("mass", 1, 1)
+        self.omp = ctx.zeros(n1)
+        self.ones1 = torch.ones(n1, dtype=torch.float64, device=ctx.device)
+        self.ccoef = ctx.zeros(spaces.dm.ncell)
+        self.emat2 = ctx.empty(spaces.dm.ncell * spaces.nb2 * spaces.nb2)
+        self.emat1 = ctx.empty(spaces.dm.ncell * spaces.nb1 * spaces.nb1)
+        self.evu = [ctx.empty(spaces.dm.ncell * spaces.nb2) for _ in range(d)]
+        self.evp = ctx.empty(spaces.dm.ncell * spaces.nb1)
+        self.T_stiff22 = spaces.tensor("stiff", 2, 2, True)
+        self.T_stiff11 = spaces.tensor("stiff", 1, 1, False)
+        self.rhs = BlockVector(ctx, d, n2, n1)
+        self.dinv = BlockVector(ctx, d, n2, n1)
+        self.t2, self.t1, self.s1 = ctx.zeros(n2), ctx.zeros(n1), ctx.zeros(n1)
+        self.xm = BlockVector(ctx, d, n2, n1)
+
+    # ---- assembly -------------------------------------------------------------
+    def assemble(self, phi, gam, buoy):
+        ctx, lib, sp, m, d = self.ctx, self.ctx.lib, self.sp, self.sp.dm.c, self.d
+        nb1, nb2 = sp.nb1, sp.nb2
+        self.omp.copy_(self.ones1)
+        ctx.axpby(-1.0, phi, 1.0, self.omp)                                   # 1 - phi (nodal: exact P1 coefficient)
+        for a in range(d):
+            for b in range(d):
+                check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 4, a * d + b, nb2, nb2, ptr(self.T_stiff22), ptr(self.omp), 1, 0.25, ptr(self.emat2)),
+                      "mp_elem_reftensor(symgrad)")
+                self.p22.scatter_matrix(self.emat2, self.Auu[a][b])
+        # preconditioner viscous block (1-phi) grad u:grad v
+        check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 3, 0, nb2, nb2, ptr(self.T_stiff22), ptr(self.omp), 1, 1.0, ptr(self.emat2)), "mp_elem_reftensor(stiff)")
+        self.p22.scatter_matrix(self.emat2, self.Puu)
+        # (q,p): dL phi phi^(1/phi^3) grad p.grad q ;  P: dL/phi grad p.grad q + p q
+        check(lib.mp_cell_fn(ctx.h, C.byref(m), C.byref(self.quad), 0, self.dL, ptr(phi), ptr(self.ccoef)), "mp_cell_fn")
+        check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 3, 0, nb1, nb1, ptr(self.T_stiff11), ptr(self.ccoef), 2, 1.0, ptr(self.emat1)), "mp_elem_reftensor(App)")
+        self.p11.scatter_matrix(self.emat1, self.App)
+        check(lib.mp_cell_fn(ctx.h, C.byref(m), C.byref(self.quad), 1, self.dL, ptr(phi), ptr(self.ccoef)), "mp_cell_fn")
+        check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 3, 0, nb1, nb1, ptr(self.T_stiff11), ptr(self.ccoef), 2, 1.0, ptr(self.emat1)), "mp_elem_reftensor(Ppp)")
+        self.p11.scatter_matrix(self.emat1, self.Ppp)
+        ctx.axpby(1.0, self.M1.vals, 1.0, self.Ppp.vals)
+        # (omega,c): -eta c omega ; P: 0.5 eta c omega
+        check(lib.mp_elem_p1_mass_fn(ctx.h, C.byref(m), C.byref(self.quad), 2, self.dL, -1.0, ptr(phi), ptr(self.emat1)), "mp_elem_p1_mass_fn")
+        self.p11.scatter_matrix(self.emat1, self.Acc)
+        self.Pcc.vals.copy_(self.Acc.vals)
+        ctx.axpby(0.0, self.Acc.vals, -0.5, self.Pcc.vals)
+        # rhs
+        check(lib.mp_elem_compaction_rhs(ctx.h, C.byref(m), C.byref(self.quad), C.byref(self.prm), ptr(phi), ptr(gam), ptr(buoy),
+                                         ptr(self.evu[0]), ptr(self.evu[1]), ptr(self.evu[2]) if d == 3 else None, ptr(self.evp)), "mp_elem_compaction_rhs")
+        for a in range(d):
+            self.p22.scatter_vector(self.evu[a], self.rhs.u[a])
+        self.p11.scatter_vector(self.evp, self.rhs.p)
+        self.rhs.c.zero_()
+        # Jacobi of the preconditioner form, Dirichlet rows -> 1
+        du = self.Puu.jacobi_setup()
+        for a in range(d):
+            ctx.vmul(1.0, du, self.mask[a], self.dinv.u[a])                   # dinv on free dofs, 0 on Dirichlet dofs ...
+            ctx.axpby(-1.0, self.mask[a], 1.0, self.dinv.u[a])                # ... minus mask, plus 1  => 1 on Dirichlet dofs
+            self.dinv.u[a].add_(1.0)
+        self.dinv.p.copy_(self.Ppp.jacobi_setup())
+        self.dinv.c.copy_(self.Pcc.jacobi_setup())
+
+    # ---- operator ---------------------------------------------------------------
+    def _apply_raw(self, x: BlockVector, y: BlockVector):
+        ctx, d = self.ctx, self.d
+        self.s1.copy_(x.p)
+        ctx.axpby(1.0, x.c, 1.0, self.s1)                                     # p + c multiplies div v
+        y.p.zero_()
+        for a in range(d):
+            ya = y.u[a]
+            self.BdivT[a].spmv(self.s1, self.t2)
+            ctx.axpby(-1.0, self.t2, 0.0, ya)                                 # -(p + c) div v
+            for b in range(d):
+                self.Auu[a][b].spmv(x.u[b], self.t2)
+                ctx.axpby(1.0, self.t2, 1.0, ya)
+            self.Bdiv[a].spmv(x.u[a], self.t1)
+            ctx.axpby(-1.0, self.t1, 1.0, y.p)
+        y.c.copy_(y.p)
+        self.App.spmv(x.p, self.t1)
+        ctx.axpby(1.0, self.t1, 1.0, y.p)
+        self.Acc.spmv(x.c, self.t1)
+        ctx.axpby(1.0, self.t1, 1.0, y.c)
+
+    def apply(self, x: BlockVector, y: BlockVector):
+        """y = (P A P + (I - P)) x with P zeroing the Dirichlet velocity dofs (== symmetric elimination of assemble_system)."""
+        ctx, d = self.ctx, self.d
+        self.xm.buf.copy_(x.buf)
+        for a in range(d):
+            ctx.vmul(1.0, self.mask[a], x.u[a], self.xm.u[a])
+        self._apply_raw(self.xm, y)
+        for a in range(d):
+            ctx.vmul(1.0, self.mask[a], y.u[a], y.u[a])
+            ctx.axpby(1.0, x.u[a], 1.0, y.u[a])
+            ctx.axpby(-1.0, self.xm.u[a], 1.0, y.u[a])                        # + (1 - mask) x
+
+    # ---- MINRES -------------------------------------------------------------------
+    def solve(self, x: BlockVector, rtol=1e-6, maxit=3000):
+        """Preconditioned MINRES (M = diag of the reference's preconditioner form).  x: initial guess in, solution out.
+        Returns the iteration count (compaction.momentum_solver returns niter too, mupopp.py:424-429)."""
+        ctx, d = self.ctx, self.d
+        n2, n1 = self.n2, self.n1
+        new = lambda: BlockVector(ctx, d, n2, n1)
+        # right-hand side with Dirichlet lifting: b <- mask (b - A g), b[D] = g
+        gfull, b, tmp = new(), new(), new()
+        for a in range(d):
+            gfull.u[a].copy_(self.g[a])
+        self._apply_raw(gfull, tmp)
+        b.buf.copy_(self.rhs.buf)
+        ctx.axpby(-1.0, tmp.buf, 1.0, b.buf)
+        for a in range(d):
+            ctx.vmul(1.0, self.mask[a], b.u[a], b.u[a])
+            ctx.axpby(1.0, self.g[a], 1.0, b.u[a])
+            self.Auu[a][a].apply_dirichlet(x.u[a], self.isbc[a], self.g[a], matrix=False)     # x[D] = g
+        v_old, v, v_new, z, z_new, w_old, w, w_new, Az = new(), new(), new(), new(), new(), new(), new(), new(), new()
+        self.apply(x, Az)
+        v.buf.copy_(b.buf)
+        ctx.axpby(-1.0, Az.buf, 1.0, v.buf)
+        ctx.vmul(1.0, self.dinv.buf, v.buf, z.buf)
+        gamma = np.sqrt(max(ctx.dot(z.buf, v.buf), 0.0))
+        ctx.vmul(1.0, self.dinv.buf, b.buf, tmp.buf)
+        bnorm = np.sqrt(max(ctx.dot(tmp.buf, b.buf), 1e-300))
+        eta, s_old, s, c_old, c, gamma_old = gamma, 0.0, 0.0, 1.0, 1.0, 1.0
+        it = 0
+        while it < maxit and abs(eta) > rtol * bnorm and gamma > 0.0:
+            ctx.axpby(0.0, z.buf, 1.0 / gamma, z.buf)                          # z <- z / gamma
+            self.apply(z, Az)
+            delta = ctx.dot(Az.buf, z.buf)
+            v_new.buf.copy_(Az.buf)
+            ctx.axpby(-delta / gamma, v.buf, 1.0, v_new.buf)
+            ctx.axpby(-gamma / gamma_old, v_old.buf, 1.0, v_new.buf)
+            ctx.vmul(1.0, self.dinv.buf, v_new.buf, z_new.buf)
+            gamma_new = np.sqrt(max(ctx.dot(z_new.buf, v_new.buf), 0.0))
+            a0 = c * delta - c_old * s * gamma
+            a1 = np.sqrt(a0 * a0 + gamma_new * gamma_new)
+            a2 = s * delta + c_old * c * gamma
+            a3 = s_old * gamma
+            c_new, s_new = a0 / a1, gamma_new / a1
+            w_new.buf.copy_(z.buf)
+            ctx.axpby(-a3, w_old.buf, 1.0, w_new.buf)
+            ctx.axpby(-a2, w.buf, 1.0, w_new.buf)
+            ctx.axpby(0.0, w_new.buf, 1.0 / a1, w_new.buf)
+            ctx.axpby(c_new * eta, w_new.buf, 1.0, x.buf)
+            eta = -s_new * eta
+            v_old, v, v_new = v, v_new, v_old
+            w_old, w, w_new = w, w_new, w_old
+            z, z_new = z_new, z
+            gamma_old, gamma = gamma, gamma_new
+            s_old, s, c_old, c = s, s_new, c, c_new
+            it += 1
+        self.last_relres = abs(eta) / bnorm
+        return it
+
+
+class PorosityR:
+    """compaction.mass_conservation / mass_solver (mupopp.py:217-304) with X = P1: assemble by quadrature, solve with Jacobi-GMRES
+    (the reference runs MINRES on this non-symmetric matrix to rtol 1e-6)."""
+
+    def __init__(self, ctx: Context, spaces: Spaces, da, qdeg=QDEG_COMPACTION):
+        self.ctx, self.sp, self.da = ctx, spaces, float(da)
+        self.quad, self._qt = _quad(ctx, spaces.mesh.dim, qdeg, with_grad=True)
+        self.plan = spaces.plan(1, 1)
+        self.A = self.plan.new_matrix(sell=True)
+        l = spaces.nb1
+        self.emat = ctx.empty(spaces.dm.ncell * l * l)
+        self.evec = ctx.empty(spaces.dm.ncell * l)
+        self.rhs = ctx.zeros(spaces.n1)
+
+    def solve(self, phi0, u, dt, gam, phi1, rtol=1e-6, maxit=100, method="gmres"):
+        ctx = self.ctx
+        u2 = u[2] if len(u) > 2 else None
+        check(ctx.lib.mp_elem_p1_porosity_quad(ctx.h, C.byref(self.sp.dm.c), C.byref(self.quad), self.da, float(dt), ptr(self.sp.cd2),
+                                               ptr(u[0]), ptr(u[1]), ptr(u2), ptr(phi0), ptr(gam), ptr(self.emat), ptr(self.evec)),
+              "mp_elem_p1_porosity_quad")
+        self.plan.scatter_matrix(self.emat, self.A)
+        self.plan.scatter_vector(self.evec, self.rhs)
+        phi1.copy_(phi0)
+        return self.A.solve(method, self.rhs, phi1, rtol=rtol, maxit=maxit)

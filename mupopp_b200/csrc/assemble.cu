@@ -495,7 +495,7 @@ __global__ void __launch_bounds__(kThreads) k_reftensor(mp_mesh m, int kind, int
         nT = D;
 #pragma unroll
         for (int a = 0; a < D; ++a) geo[a] = detJ * G.g[a + 1][dir];
-    } else {
+    } else if (kind == 3) {
         nT = D * D;
 #pragma unroll
         for (int a = 0; a < D; ++a)
@@ -504,6 +504,22 @@ __global__ void __launch_bounds__(kThreads) k_reftensor(mp_mesh m, int kind, int
                 double t = 0.0;
 #pragma unroll
                 for (int i = 0; i < D; ++i) t += G.g[a + 1][i] * G.g[b + 1][i];
+                geo[a * D + b] = detJ * t;
+            }
+    } else {
+        // kind 4, SYMGRAD block (ca, cb) = (dir / D, dir % D) of  2 symgrad(u):symgrad(v) = delta_ab grad psi_i.grad psi_j + d_b psi_i d_a psi_j
+        // (compaction.momentum_conservation, mupopp.py:361), contracted with the STIFF reference tensors
+        nT = D * D;
+        const int ca = dir / D, cb = dir % D;
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+                double t = G.g[a + 1][cb] * G.g[b + 1][ca];
+                if (ca == cb) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) t += G.g[a + 1][i] * G.g[b + 1][i];
+                }
                 geo[a * D + b] = detJ * t;
             }
     }
@@ -668,6 +684,216 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport_quad(mp_mesh m, mp_tr
     if (evec) store_vec<D>(evec, c, b);
 }
 
+
+// ------------------------------------------------------------------ compaction forms (mupopp.py:206-382), coefficient kernels
+__device__ __forceinline__ double compaction_fn(int fn, double phi, double dL) {
+    if (fn == 0) return dL * phi * pow(phi, 1.0 / (phi * phi * phi));   // dL*phi*phi**m3, mupopp.py:365 (precedence quirk, ~0)
+    if (fn == 1) return dL / phi;                                       // dL*phi*phi*m3, mupopp.py:380
+    return 3.0 * phi / (2.0 * (1.0 - phi) * (2.0 - phi));               // eta = 1/alpha, mupopp.py:346-347
+}
+
+// out[c] = (1/|K|) int_K f(phi): cellwise coefficient of the P1 stiffness blocks (grad p.grad q is constant per cell)
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_cell_fn(mp_mesh m, QuadView Q, int fn, double dL, const double *__restrict__ phi,
+                                                      double *__restrict__ out) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    double ph[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) ph[i] = phi[m.d_cells[(D + 1) * c + i]];
+    double s = 0.0;
+    for (int q = 0; q < Q.nq; ++q) {
+        double pq = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) pq += Q.lam[q * (D + 1) + i] * ph[i];
+        s += Q.w[q] * compaction_fn(fn, pq, dL);
+    }
+    double fac = 1.0;
+#pragma unroll
+    for (int k = 2; k <= D; ++k) fac *= k;
+    out[c] = s * fac;
+}
+
+// emat[c][i][j] = scale * int f(phi) lambda_i lambda_j
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_mass_fn(mp_mesh m, QuadView Q, int fn, double dL, double scale,
+                                                         const double *__restrict__ phi, double *__restrict__ emat) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double detJ = G.vol;
+#pragma unroll
+    for (int k = 2; k <= D; ++k) detJ *= k;
+    double ph[D + 1], A[D + 1][D + 1];
+    gather<D>(phi, G, ph);
+#pragma unroll
+    for (int i = 0; i <= D; ++i)
+#pragma unroll
+        for (int j = 0; j <= D; ++j) A[i][j] = 0.0;
+    for (int q = 0; q < Q.nq; ++q) {
+        double lam[D + 1], pq = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) { lam[i] = Q.lam[q * (D + 1) + i]; pq += lam[i] * ph[i]; }
+        const double w = scale * Q.w[q] * detJ * compaction_fn(fn, pq, dL);
+#pragma unroll
+        for (int i = 0; i <= D; ++i)
+#pragma unroll
+            for (int j = 0; j <= D; ++j) A[i][j] += w * lam[i] * lam[j];
+    }
+    store_mat<D>(emat, c, A);
+}
+
+// rhs of the momentum form (mupopp.py:356-357, 374-375):  evec_u[a][c][i] = -int h_a psi_i,  evec_p[c][i] = -int da R buoy gam/(1 - R buoy) lambda_i
+//   h = dL (1-phi) (chi(phi) grad(phi)/B - R buoy zhat) + da grad(4 gam / (3 phi))
+struct CompactionPrm { double da, R, B, costerm, dL, zhat[3]; };
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_compaction_rhs(mp_mesh m, QuadView Q, CompactionPrm P, const double *__restrict__ phi,
+                                                             const double *__restrict__ gam, const double *__restrict__ buoy,
+                                                             double *__restrict__ evu0, double *__restrict__ evu1, double *__restrict__ evu2,
+                                                             double *__restrict__ evp) {
+    constexpr int NB2 = D == 2 ? 6 : 10;
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double detJ = G.vol;
+#pragma unroll
+    for (int k = 2; k <= D; ++k) detJ *= k;
+    double ph[D + 1], ga[D + 1], bu[D + 1], gphi[D], ggam[D];
+    gather<D>(phi, G, ph);
+    gather<D>(gam, G, ga);
+    gather<D>(buoy, G, bu);
+#pragma unroll
+    for (int a = 0; a < D; ++a) {
+        gphi[a] = 0.0; ggam[a] = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) { gphi[a] += ph[i] * G.g[i][a]; ggam[a] += ga[i] * G.g[i][a]; }
+    }
+    double bvec[D][NB2], bp[D + 1];
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int i = 0; i < NB2; ++i) bvec[a][i] = 0.0;
+#pragma unroll
+    for (int i = 0; i <= D; ++i) bp[i] = 0.0;
+    for (int q = 0; q < Q.nq; ++q) {
+        double lam[D + 1], pq = 0.0, gq = 0.0, bq = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) { lam[i] = Q.lam[q * (D + 1) + i]; pq += lam[i] * ph[i]; gq += lam[i] * ga[i]; bq += lam[i] * bu[i]; }
+        const double w = Q.w[q] * detJ;
+        const double chi = P.costerm * (2.0 * 249.0 + 20.0 * (-8065.0) * pq * pq * pq + 12.0 * 6149.0 * pq * pq + 6.0 * (-1778.0) * pq);
+        double h[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a)
+            h[a] = P.dL * (1.0 - pq) * (chi * gphi[a] / P.B - P.R * bq * P.zhat[a]) + P.da * (4.0 / 3.0) * (ggam[a] / pq - gq * gphi[a] / (pq * pq));
+#pragma unroll
+        for (int i = 0; i < NB2; ++i) {
+            const double psi = Q.vphi[q * NB2 + i];
+#pragma unroll
+            for (int a = 0; a < D; ++a) bvec[a][i] -= w * h[a] * psi;
+        }
+        const double fq = P.da * P.R * bq * gq / (1.0 - P.R * bq);
+#pragma unroll
+        for (int i = 0; i <= D; ++i) bp[i] -= w * fq * lam[i];
+    }
+    double *dst[3] = {evu0, evu1, evu2};
+#pragma unroll
+    for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int i = 0; i < NB2; ++i) dst[a][c * NB2 + i] = bvec[a][i];
+    store_vec<D>(evp, c, bp);
+}
+
+// porosity row (compaction.mass_conservation, mupopp.py:217-259) with a P1 porosity and a P2 velocity:
+//   w (phi1 - phi0 + dt (u.grad(phi_mid) - (1 - phi_mid) div u) - dt da gam) + (keff/|u|^2) (u.grad w) (phi1 - phi0 + dt (u.grad(phi_mid) - da gam))
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_porosity_quad(mp_mesh m, QuadView Q, const double *__restrict__ vdphi, double da, double dt,
+                                                               const int32_t *__restrict__ vdofs, const double *__restrict__ v0,
+                                                               const double *__restrict__ v1, const double *__restrict__ v2,
+                                                               const double *__restrict__ phi0, const double *__restrict__ gam,
+                                                               double *__restrict__ emat, double *__restrict__ evec) {
+    constexpr int NB2 = D == 2 ? 6 : 10;
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    double detJ = G.vol;
+#pragma unroll
+    for (int k = 2; k <= D; ++k) detJ *= k;
+    double p0[D + 1], ga[D + 1];
+    gather<D>(phi0, G, p0);
+    gather<D>(gam, G, ga);
+    double uc[D][NB2];
+    const int32_t *vd = vdofs + c * (int64_t)NB2;
+#pragma unroll
+    for (int k = 0; k < NB2; ++k) {
+        const int32_t dk = vd[k];
+        uc[0][k] = v0[dk];
+        uc[1][k] = v1[dk];
+        if (D == 3) uc[D - 1][k] = v2[dk];
+    }
+    double A[D + 1][D + 1], b[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) {
+        b[i] = 0.0;
+#pragma unroll
+        for (int j = 0; j <= D; ++j) A[i][j] = 0.0;
+    }
+    for (int q = 0; q < Q.nq; ++q) {
+        const double w = Q.w[q] * detJ;
+        double lam[D + 1], u[D], divu = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) lam[i] = Q.lam[q * (D + 1) + i];
+#pragma unroll
+        for (int a = 0; a < D; ++a) u[a] = 0.0;
+        for (int k = 0; k < NB2; ++k) {
+            const double ph = Q.vphi[q * NB2 + k];
+            double gk[D];   // physical gradient of the P2 basis function k: sum_alpha dpsi/dxi_alpha * Jinv[alpha][.]
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                double t = 0.0;
+#pragma unroll
+                for (int al = 0; al < D; ++al) t += vdphi[(q * NB2 + k) * D + al] * G.g[al + 1][a];
+                gk[a] = t;
+            }
+#pragma unroll
+            for (int a = 0; a < D; ++a) { u[a] += ph * uc[a][k]; divu += gk[a] * uc[a][k]; }
+        }
+        double un2 = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) un2 += u[a] * u[a];
+        const double keff = fmax(0.5 * G.h * sqrt(un2) - 1.0, 0.0);
+        const double st = keff > 0.0 ? keff / un2 : 0.0;
+        double ug[D + 1], ph0 = 0.0, gq = 0.0, ugp0 = 0.0;
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            double t = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) t += u[a] * G.g[i][a];
+            ug[i] = t;
+            ph0 += lam[i] * p0[i]; gq += lam[i] * ga[i]; ugp0 += t * p0[i];
+        }
+        if (emat) {
+#pragma unroll
+            for (int i = 0; i <= D; ++i)
+#pragma unroll
+                for (int j = 0; j <= D; ++j)
+                    A[i][j] += w * (lam[i] * lam[j] + 0.5 * dt * lam[i] * ug[j] + 0.5 * dt * divu * lam[i] * lam[j] +
+                                    st * ug[i] * (lam[j] + 0.5 * dt * ug[j]));
+        }
+        if (evec) {
+            const double gal = ph0 - 0.5 * dt * ugp0 + dt * divu - 0.5 * dt * ph0 * divu + dt * da * gq;
+            const double rk = -ph0 + 0.5 * dt * ugp0 - dt * da * gq;
+#pragma unroll
+            for (int i = 0; i <= D; ++i) b[i] += w * (lam[i] * gal - st * ug[i] * rk);
+        }
+    }
+    if (emat) store_mat<D>(emat, c, A);
+    if (evec) store_vec<D>(evec, c, b);
+}
+
 // Symmetric Dirichlet elimination, 8 lanes per row, fixed reduction order.
 __global__ void __launch_bounds__(256) k_dirichlet(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                                                    double *__restrict__ vals, double *__restrict__ rhs,
@@ -786,7 +1012,8 @@ extern "C" int mp_apply_dirichlet_sym(mp_ctx *ctx, int64_t nrow, const int32_t *
 extern "C" int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
                                  const double *d_coef, int coef_kind, double scale, double *d_elem_mat) {
     MP_TRY(check_mesh(ctx, mesh));
-    MP_CHECK(kind >= 0 && kind <= 3 && dir >= 0 && dir < mesh->dim && lr > 0 && lc > 0 && d_T0 && d_elem_mat, "mp_elem_reftensor: bad argument");
+    MP_CHECK(kind >= 0 && kind <= 4 && dir >= 0 && dir < (kind == 4 ? mesh->dim * mesh->dim : mesh->dim) && lr > 0 && lc > 0 && d_T0 && d_elem_mat,
+             "mp_elem_reftensor: bad argument");
     MP_CHECK(coef_kind == 0 || d_coef, "mp_elem_reftensor: coefficient pointer is null");
     DISPATCH_DIM(mesh, k_reftensor, kind, dir, lr * lc, d_T0, d_coef, coef_kind, scale, d_elem_mat);
     return 0;
@@ -806,5 +1033,57 @@ extern "C" int mp_elem_p1_transport_quad(mp_ctx *ctx, const mp_mesh *mesh, const
     QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
     DISPATCH_DIM(mesh, k_p1_transport_quad, *prm, Q, d_vel_dofs, d_vel0, d_vel1, d_vel2 ? d_vel2 : d_vel1, d_c0n, d_c1n, d_c2n, d_c1new,
                  d_c2new, d_fsrc, d_elem_mat, d_elem_vec);
+    return 0;
+}
+
+static int check_quad(const mp_quad *q, bool need_v, bool need_dv) {
+    MP_CHECK(q && q->nq > 0 && q->d_w && q->d_lam, "quadrature tables missing");
+    MP_CHECK(!need_v || (q->nbv > 0 && q->d_vphi), "quadrature: velocity basis table missing");
+    MP_CHECK(!need_dv || q->d_vdphi, "quadrature: velocity basis gradient table missing");
+    return 0;
+}
+
+extern "C" int mp_cell_fn(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, int fn, double dL, const double *d_phi, double *d_out) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_TRY(check_quad(quad, false, false));
+    MP_CHECK(fn >= 0 && fn <= 2 && d_phi && d_out, "mp_cell_fn: bad argument");
+    QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
+    DISPATCH_DIM(mesh, k_cell_fn, Q, fn, dL, d_phi, d_out);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_mass_fn(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, int fn, double dL, double scale,
+                                  const double *d_phi, double *d_elem_mat) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_TRY(check_quad(quad, false, false));
+    MP_CHECK(fn >= 0 && fn <= 2 && d_phi && d_elem_mat, "mp_elem_p1_mass_fn: bad argument");
+    QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
+    DISPATCH_DIM(mesh, k_p1_mass_fn, Q, fn, dL, scale, d_phi, d_elem_mat);
+    return 0;
+}
+
+extern "C" int mp_elem_compaction_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, const mp_compaction_params *prm,
+                                      const double *d_phi, const double *d_gam, const double *d_buoy, double *d_evec_u0,
+                                      double *d_evec_u1, double *d_evec_u2, double *d_evec_p) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_TRY(check_quad(quad, true, false));
+    MP_CHECK(prm && d_phi && d_gam && d_buoy && d_evec_u0 && d_evec_u1 && (mesh->dim == 2 || d_evec_u2) && d_evec_p, "mp_elem_compaction_rhs: null argument");
+    MP_CHECK(quad->nbv == (mesh->dim == 2 ? 6 : 10), "mp_elem_compaction_rhs: velocity basis must be P2");
+    CompactionPrm P{prm->da, prm->R, prm->B, 2.0 * cos(prm->theta) - 1.0, prm->dL, {prm->zhat[0], prm->zhat[1], prm->zhat[2]}};
+    QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
+    DISPATCH_DIM(mesh, k_compaction_rhs, Q, P, d_phi, d_gam, d_buoy, d_evec_u0, d_evec_u1, d_evec_u2 ? d_evec_u2 : d_evec_u1, d_evec_p);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_porosity_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, double da, double dt,
+                                        const int32_t *d_vel_dofs, const double *d_vel0, const double *d_vel1, const double *d_vel2,
+                                        const double *d_phi0, const double *d_gam, double *d_elem_mat, double *d_elem_vec) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_TRY(check_quad(quad, true, true));
+    MP_CHECK(quad->nbv == (mesh->dim == 2 ? 6 : 10), "mp_elem_p1_porosity_quad: velocity basis must be P2");
+    MP_CHECK(d_vel_dofs && d_vel0 && d_vel1 && (mesh->dim == 2 || d_vel2) && d_phi0 && d_gam, "mp_elem_p1_porosity_quad: null argument");
+    QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
+    DISPATCH_DIM(mesh, k_p1_porosity_quad, Q, quad->d_vdphi, da, dt, d_vel_dofs, d_vel0, d_vel1, d_vel2 ? d_vel2 : d_vel1, d_phi0, d_gam,
+                 d_elem_mat, d_elem_vec);
     return 0;
 }

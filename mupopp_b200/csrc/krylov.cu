@@ -253,13 +253,13 @@ k_spmv_sell(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *_
 }
 
 // ------------------------------------------------------------------ BLAS-1
-__global__ void __launch_bounds__(kThreads) k_axpby(int64_t n, double a, const double *__restrict__ x, double b, double *__restrict__ y) {
+// x, y (and z below) may alias: no __restrict__ here
+__global__ void __launch_bounds__(kThreads) k_axpby(int64_t n, double a, const double *x, double b, double *y) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x)
         y[i] = (b == 0.0) ? a * x[i] : a * x[i] + b * y[i];
 }
 
-__global__ void __launch_bounds__(kThreads) k_vmul(int64_t n, double a, const double *__restrict__ x, const double *__restrict__ y,
-                                                   double *__restrict__ z) {
+__global__ void __launch_bounds__(kThreads) k_vmul(int64_t n, double a, const double *x, const double *y, double *z) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) z[i] = a * x[i] * y[i];
 }
 

@@ -192,7 +192,7 @@ class AdrSolverR:
         d = spaces.mesh.dim
         w, lam, vphi = ref.quadrature_tables(d, qdeg, vel_degree)
         self.qw, self.qlam, self.qvphi = ctx.to_device(w), ctx.to_device(lam.ravel()), ctx.to_device(vphi.ravel())
-        self.quad = MpQuad(len(w), vphi.shape[1], self.qw.data_ptr(), self.qlam.data_ptr(), self.qvphi.data_ptr())
+        self.quad = MpQuad(len(w), vphi.shape[1], self.qw.data_ptr(), self.qlam.data_ptr(), self.qvphi.data_ptr(), None)
         self.vdofs = spaces.cd2 if vel_degree == 2 else spaces.cd1
         self.plan = spaces.plan(1, 1)
         self.A = self.plan.new_matrix(sell=True)

@@ -131,7 +131,7 @@ class StokesAdvection:
 
 
 class compaction:
-    """mupopp.py:125-471: parameters come from a `key = value` file; forms are rows a8-a10 of SURVEY.md section 8 (not built yet)."""
+    """mupopp.py:125-471: parameters come from a `key = value` file; forms are rows a8-a10 of SURVEY.md section 8."""
 
     def __init__(self, param_file, ksp="minres"):
         param = parse_param_file(param_file)
@@ -150,17 +150,64 @@ class compaction:
         return a, L, Form("compaction_mass", "b", **a.data)
 
     def mass_solver(self, X, a_phi, L_phi, bb_phi, nits=100, tol=1.0e-6, monitor=False):
-        raise NotImplementedError("compaction.mass_solver: SURVEY.md section 8 row a10 is not on the B200 path yet")
+        """mupopp.py:261-304: assemble the porosity row and solve it (Jacobi-GMRES on the GPU; the reference runs `krylov_method`
+        with AMG on this non-symmetric matrix).  Returns the new porosity Function."""
+        from . import compaction as _c, moder
+        d = a_phi.data
+        if d["V"].blocks[0][0] != 1:
+            raise NotImplementedError("compaction.mass_solver: only a P1 porosity space is on the B200 path (P2 needs div(grad(phi)))")
+        ctx = default_context()
+        mesh = d["mesh"]
+        sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+        key = ("porosity", id(mesh), float(self.da))
+        if key not in _CACHE:
+            _CACHE[key] = _c.PorosityR(ctx, sp, self.da)
+        sol = Function(X)
+        dt = float(getattr(d["dt"], "dt", d["dt"]))
+        res = _CACHE[key].solve(d["phi0"].blocks[0].clone(), d["u"].blocks, dt, d["gam"].blocks[0], sol.blocks[0], rtol=tol, maxit=max(nits, 1))
+        if monitor:
+            info("mass_solver: %s" % (res,))
+        return sol
 
     def momentum_conservation(self, W, phi, gam, buyoancy, zh=Constant((0.0, 0.0, 1.0))):
         a, L = _pair("compaction_momentum", W=W, phi=phi, gam=gam, buoyancy=buyoancy, zh=zh, owner=self)
         return a, L, Form("compaction_momentum", "b", **a.data)
 
     def momentum_solver(self, W, a, L, b, bcs, pc="amg", tol=1.0e-6, max_its=3000, monitor=False):
-        raise NotImplementedError("compaction.momentum_solver: SURVEY.md section 8 rows a8-a9 are not on the B200 path yet")
+        """mupopp.py:383-429: assemble_system(a, L, bcs), assemble_system(b, L, bcs), MINRES -> (u, p, c, niter).
+        On the GPU the preconditioner is the diagonal of the form `b` (the reference hands `b` to hypre AMG)."""
+        from . import compaction as _c, moder
+        d = a.data
+        ctx = default_context()
+        mesh = W.mesh
+        dim = mesh.dim
+        if d["phi"].space.blocks[0][0] != 1:
+            raise NotImplementedError("compaction.momentum_solver: only P1 phi/gam/buoyancy coefficients are on the B200 path")
+        bcs = list(bcs) if isinstance(bcs, (list, tuple)) else [bcs]
+        sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+        key = ("compaction", id(W), _bc_key(bcs), self.da, self.R, self.B, self.theta, self.dL, tuple(_zhat(d["zh"], dim)))
+        if key not in _CACHE:
+            ub = W.sub_blocks[0]
+            arr = _bc_arrays(W, bcs, list(ub))
+            _CACHE[key] = _c.CompactionMomentumR(ctx, sp, self.da, self.R, self.B, self.theta, self.dL, _zhat(d["zh"], dim),
+                                                 [arr[k][0] for k in ub], [arr[k][1] for k in ub])
+        s = _CACHE[key]
+        s.assemble(d["phi"].blocks[0], d["gam"].blocks[0], d["buoyancy"].blocks[0])
+        x = _c.BlockVector(ctx, dim, sp.n2, sp.n1)
+        niter = s.solve(x, rtol=tol, maxit=max_its)
+        if monitor:
+            info("momentum_solver: %d MINRES iterations, relative residual %.3e" % (niter, s.last_relres))
+        sol = Function(W)
+        for k in range(dim):
+            sol.blocks[k].copy_(x.u[k])
+        sol.blocks[dim].copy_(x.p)
+        sol.blocks[dim + 1].copy_(x.c)
+        u, p, c = sol.split()
+        return u, p, c, niter
 
     def momentum_solver_direct(self, W, a, L, b, bcs, pc="amg", tol=1.0e-6, max_its=3000, monitor=False):
-        raise NotImplementedError("compaction.momentum_solver_direct: SURVEY.md section 8 rows a8-a9 are not on the B200 path yet")
+        """mupopp.py:430-471 solves the same system with LU (quadrature_degree=3); here: the same MINRES driven to a tight tolerance."""
+        return self.momentum_solver(W, a, L, b, bcs, pc=pc, tol=1.0e-11, max_its=max(max_its, 50000), monitor=monitor)
 
 
 # ------------------------------------------------------------------ solve dispatch (called by fenics.solve)

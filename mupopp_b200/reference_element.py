@@ -132,3 +132,9 @@ def quadrature_tables(dim, qdeg, vel_degree):
     else:
         vphi, _ = tabulate(vel_degree, pts)
     return np.ascontiguousarray(w), np.ascontiguousarray(lam), np.ascontiguousarray(vphi)
+
+
+def basis_gradient_table(dim, qdeg, degree):
+    """Reference gradients (nq, nb, dim) of the Lagrange basis at the points of the degree-`qdeg` rule."""
+    pts, _ = simplex_quadrature(dim, qdeg)
+    return np.ascontiguousarray(tabulate(degree, pts)[1])

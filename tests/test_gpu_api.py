@@ -122,3 +122,43 @@ def test_two_component_adaptive_through_api(ctx):
         assert rel(sol.get(0), o0) < 1e-9
         c_prev = sol
         c0n, c1n = o0, o1
+
+
+def test_compaction_through_api(ctx, tmp_path):
+    """compaction(param_file).momentum_conservation / momentum_solver / mass_conservation / mass_solver (time_test1.py:179-237 flow)."""
+    from mupopp_b200.fenics import (BoxMesh, Constant, DirichletBC, DOLFIN_EPS, Expression, FiniteElement, Function, FunctionSpace,
+                                    MixedElement, Point, VectorElement, near)
+    from mupopp_b200.mupopp import compaction
+    from oracle import compaction as oc
+    cfg = tmp_path / "t.cfg"
+    cfg.write_text("# test\nout_freq = 5\nT = 5.0\ndt = 0.1   # step\nda = 0.01\nR = 0.2\nB = 1e3\ntheta = 10\ndL = 1.0\n")
+    model = compaction(str(cfg))
+    assert model.da == 0.01 and model.theta == 10 and model.krylov_method == "minres"
+    mesh = BoxMesh(Point(-1, -1, 0), Point(1, 1, 2), 3, 3, 4)
+    cell = mesh.ufl_cell()
+    W = FunctionSpace(mesh, MixedElement([VectorElement("Lagrange", cell, 2), FiniteElement("Lagrange", cell, 1), FiniteElement("Lagrange", cell, 1)]))
+    X = FunctionSpace(mesh, "CG", 1)
+    walls = lambda x, on_boundary: on_boundary and (near(abs(x[0]), 1.0, 1e-12) or near(abs(x[1]), 1.0, 1e-12))
+    bcs = [DirichletBC(W.sub(0), Constant((0.0, 0.0, 0.0)), walls)]
+    phi0, gam, buoy = Function(X), Function(X), Function(X)
+    phi0.interpolate(Expression("0.05*(exp(-x[0]*x[0]-x[1]*x[1]-(x[2]-0.5)*(x[2]-0.5))/0.5)+0.1", degree=2))
+    gam.interpolate(Expression("0.0", degree=1))
+    buoy.interpolate(Expression("1.0", degree=1))
+    a, L, b = model.momentum_conservation(W, phi0, gam, buoy)
+    u, p, c, niter = model.momentum_solver(W, a, L, b, bcs, tol=1e-11, max_its=20000)
+    om = fem.box_mesh((-1, -1, 0), (1, 1, 2), 3, 3, 4)
+    asm = forms.Assembler(om)
+    X2 = asm.P2.dof_coords()
+    side = np.where((np.abs(X2[:, 0]) > 1 - 1e-12) | (np.abs(X2[:, 1]) > 1 - 1e-12))[0]
+    prm = oc.CompactionParams(da=0.01, R=0.2, B=1e3, theta=10.0, dL=1.0)
+    Xv = om.coords
+    phi_h = 0.05 * np.exp(-Xv[:, 0] ** 2 - Xv[:, 1] ** 2 - (Xv[:, 2] - 0.5) ** 2) / 0.5 + 0.1
+    assert rel(phi0.get(), phi_h) < 1e-15
+    uo, po, co = oc.momentum_solve(asm, prm, phi_h, np.zeros(om.nv), np.ones(om.nv), [side] * 3, [np.zeros(len(side))] * 3)
+    assert niter > 0
+    assert rel(np.concatenate([u.get(0), u.get(1), u.get(2)]), np.concatenate(uo)) < 1e-6
+    assert rel(p.get(), po) < 1e-6
+    a_phi, L_phi, bb = model.mass_conservation(X, phi0, u, 0.1, gam, mesh)
+    phi1 = model.mass_solver(X, a_phi, L_phi, bb, nits=500, tol=1e-13)
+    Ao, bo = oc.porosity_system(asm, 0.01, 0.1, phi_h, uo, np.zeros(om.nv))
+    assert rel(phi1.get(), spla.splu(Ao.tocsc()).solve(bo)) < 1e-7
