@@ -37,11 +37,17 @@ def _quad(ctx, dim, qdeg, with_grad=False):
 class BlockVector:
     """[u_0 .. u_{d-1} | p | c] in one contiguous device buffer with per-block views."""
 
-    def __init__(self, ctx, d, n2, n1):
-        self.buf = ctx.zeros(d * n2 + 2 * n1)
-        self.u = [self.buf[a * n2:(a + 1) * n2] for a in range(d)]
-        self.p = self.buf[d * n2:d * n2 + n1]
-        self.c = self.buf[d * n2 + n1:]
+    def __init__(self, ctx, d, n2, n1, buf="new"):
+        self.d, self.n2, self.n1 = d, n2, n1
+        if buf == "new":
+            self.rebind(ctx.zeros(d * n2 + 2 * n1))
+
+    def rebind(self, buf):
+        d, n2, n1 = self.d, self.n2, self.n1
+        self.buf = buf
+        self.u = [buf[a * n2:(a + 1) * n2] for a in range(d)]
+        self.p = buf[d * n2:d * n2 + n1]
+        self.c = buf[d * n2 + n1:]
 
 
 class CompactionMomentumR:
@@ -158,11 +164,11 @@ class CompactionMomentumR:
     def solve(self, x: BlockVector, rtol=1e-6, maxit=3000):
         """Preconditioned MINRES (M = diag of the reference's preconditioner form).  x: initial guess in, solution out.
         Returns the iteration count (compaction.momentum_solver returns niter too, mupopp.py:424-429)."""
+        from .minres import minres
         ctx, d = self.ctx, self.d
         n2, n1 = self.n2, self.n1
-        new = lambda: BlockVector(ctx, d, n2, n1)
         # right-hand side with Dirichlet lifting: b <- mask (b - A g), b[D] = g
-        gfull, b, tmp = new(), new(), new()
+        gfull, b, tmp = BlockVector(ctx, d, n2, n1), BlockVector(ctx, d, n2, n1), BlockVector(ctx, d, n2, n1)
         for a in range(d):
             gfull.u[a].copy_(self.g[a])
         self._apply_raw(gfull, tmp)
@@ -172,43 +178,14 @@ class CompactionMomentumR:
             ctx.vmul(1.0, self.mask[a], b.u[a], b.u[a])
             ctx.axpby(1.0, self.g[a], 1.0, b.u[a])
             self.Auu[a][a].apply_dirichlet(x.u[a], self.isbc[a], self.g[a], matrix=False)     # x[D] = g
-        v_old, v, v_new, z, z_new, w_old, w, w_new, Az = new(), new(), new(), new(), new(), new(), new(), new(), new()
-        self.apply(x, Az)
-        v.buf.copy_(b.buf)
-        ctx.axpby(-1.0, Az.buf, 1.0, v.buf)
-        ctx.vmul(1.0, self.dinv.buf, v.buf, z.buf)
-        gamma = np.sqrt(max(ctx.dot(z.buf, v.buf), 0.0))
-        ctx.vmul(1.0, self.dinv.buf, b.buf, tmp.buf)
-        bnorm = np.sqrt(max(ctx.dot(tmp.buf, b.buf), 1e-300))
-        eta, s_old, s, c_old, c, gamma_old = gamma, 0.0, 0.0, 1.0, 1.0, 1.0
-        it = 0
-        while it < maxit and abs(eta) > rtol * bnorm and gamma > 0.0:
-            ctx.axpby(0.0, z.buf, 1.0 / gamma, z.buf)                          # z <- z / gamma
-            self.apply(z, Az)
-            delta = ctx.dot(Az.buf, z.buf)
-            v_new.buf.copy_(Az.buf)
-            ctx.axpby(-delta / gamma, v.buf, 1.0, v_new.buf)
-            ctx.axpby(-gamma / gamma_old, v_old.buf, 1.0, v_new.buf)
-            ctx.vmul(1.0, self.dinv.buf, v_new.buf, z_new.buf)
-            gamma_new = np.sqrt(max(ctx.dot(z_new.buf, v_new.buf), 0.0))
-            a0 = c * delta - c_old * s * gamma
-            a1 = np.sqrt(a0 * a0 + gamma_new * gamma_new)
-            a2 = s * delta + c_old * c * gamma
-            a3 = s_old * gamma
-            c_new, s_new = a0 / a1, gamma_new / a1
-            w_new.buf.copy_(z.buf)
-            ctx.axpby(-a3, w_old.buf, 1.0, w_new.buf)
-            ctx.axpby(-a2, w.buf, 1.0, w_new.buf)
-            ctx.axpby(0.0, w_new.buf, 1.0 / a1, w_new.buf)
-            ctx.axpby(c_new * eta, w_new.buf, 1.0, x.buf)
-            eta = -s_new * eta
-            v_old, v, v_new = v, v_new, v_old
-            w_old, w, w_new = w, w_new, w_old
-            z, z_new = z_new, z
-            gamma_old, gamma = gamma, gamma_new
-            s_old, s, c_old, c = s, s_new, c, c_new
-            it += 1
-        self.last_relres = abs(eta) / bnorm
+        xv, yv = BlockVector(ctx, d, n2, n1, buf=None), BlockVector(ctx, d, n2, n1, buf=None)
+
+        def op(xb, yb):
+            xv.rebind(xb)
+            yv.rebind(yb)
+            self.apply(xv, yv)
+
+        it, self.last_relres = minres(ctx, op, self.dinv.buf, b.buf, x.buf, rtol=rtol, maxit=maxit)
         return it
 
 

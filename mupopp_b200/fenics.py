@@ -175,9 +175,13 @@ class FunctionSpace:
         off = 0
         for e in subs:
             idx = []
-            nd = mesh.num_vertices() + (mesh.num_edges() if e.degree == 2 else 0)
-            if e.degree not in (1, 2):
+            if e.degree not in (1, 2, 3):
                 raise NotImplementedError("Lagrange degree %d" % e.degree)
+            nd = mesh.num_vertices()
+            if e.degree == 2:
+                nd += mesh.num_edges()
+            elif e.degree == 3:
+                nd += 2 * mesh.num_edges() + (mesh.num_cells() if mesh.dim == 2 else mesh.faces.shape[0])
             for _ in range(e.ncomp):
                 idx.append(len(self.blocks))
                 self.blocks.append((e.degree, off, nd))
@@ -197,10 +201,16 @@ class FunctionSpace:
         return len(self.sub_elements)
 
     def dof_coords(self, degree):
+        m = self.mesh
         if degree == 1:
-            return self.mesh.coords
-        e = self.mesh.edges
-        return np.concatenate([self.mesh.coords, 0.5 * (self.mesh.coords[e[:, 0]] + self.mesh.coords[e[:, 1]])], axis=0)
+            return m.coords
+        e = m.edges
+        a, b = m.coords[e[:, 0]], m.coords[e[:, 1]]
+        if degree == 2:
+            return np.concatenate([m.coords, 0.5 * (a + b)], axis=0)
+        ed = np.stack([(2.0 * a + b) / 3.0, (a + 2.0 * b) / 3.0], axis=1).reshape(-1, m.dim)
+        inner = m.coords[m.cells].mean(1) if m.dim == 2 else m.coords[m.faces].mean(1)
+        return np.concatenate([m.coords, ed, inner], axis=0)
 
 
 class _SubSpace:
@@ -434,14 +444,20 @@ class DirichletBC:
             c, k = int(owner[f]), int(oloc[f])
             for v in fv[f]:
                 seen.setdefault(int(v), (vx[v], c, k))
-            if degree == 2:
+            if degree >= 2:
                 ce = mesh.cell_edges[c]
                 for e, (a, b) in enumerate(le):
                     if a != k and b != k:            # edge lies on the facet opposite local vertex k
-                        gid = nv + int(ce[e])
-                        if gid not in seen:
-                            va, vb = mesh.cells[c][a], mesh.cells[c][b]
-                            seen[gid] = (0.5 * (vx[va] + vx[vb]), c, k)
+                        va, vb = mesh.cells[c][a], mesh.cells[c][b]
+                        if degree == 2:
+                            seen.setdefault(nv + int(ce[e]), (0.5 * (vx[va] + vx[vb]), c, k))
+                        else:                        # P3: two dofs per edge, the one nearer the lower vertex first
+                            lo, hi = (va, vb) if va < vb else (vb, va)
+                            seen.setdefault(nv + 2 * int(ce[e]), ((2.0 * vx[lo] + vx[hi]) / 3.0, c, k))
+                            seen.setdefault(nv + 2 * int(ce[e]) + 1, ((vx[lo] + 2.0 * vx[hi]) / 3.0, c, k))
+                if degree == 3 and d == 3:           # the face dof of the boundary facet itself
+                    gid = nv + 2 * mesh.num_edges() + int(mesh.cell_faces[c][k])
+                    seen.setdefault(gid, (vx[fv[f]].mean(0), c, k))
         if not seen:
             return {b: (np.zeros(0, dtype=np.int64), np.zeros(0)) for b in self.block_ids}
         dofs = np.array(sorted(seen), dtype=np.int64)

@@ -88,6 +88,33 @@ class Mesh:
     def num_edges(self):
         return self.edges.shape[0]
 
+    # -- faces of tetrahedra (needed by P3 spaces) -----------------------------------
+    def init_faces(self):
+        """Face ids in first-seen order over (cell, UFC local facet k = the facet opposite local vertex k)."""
+        if getattr(self, "_faces", None) is not None:
+            return
+        nv = self.num_vertices()
+        loc = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])
+        fv = self.cells[:, loc].astype(np.int64)
+        keys = ((fv[..., 0] * nv + fv[..., 1]) * nv + fv[..., 2]).ravel()
+        uniq, first, inv = np.unique(keys, return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        rank = np.empty(order.size, dtype=np.int64)
+        rank[order] = np.arange(order.size)
+        self._cell_faces = rank[inv].reshape(fv.shape[:2]).astype(np.int32)
+        u = uniq[order]
+        self._faces = np.stack([u // (nv * nv), (u // nv) % nv, u % nv], 1).astype(np.int32)
+
+    @property
+    def faces(self):
+        self.init_faces()
+        return self._faces
+
+    @property
+    def cell_faces(self):
+        self.init_faces()
+        return self._cell_faces
+
     # -- boundary facets -----------------------------------------------------------
     def boundary_facets(self):
         """(facet vertices (F,d), outward unit normals (F,d), measures (F,), owning cell (F,)).

@@ -23,7 +23,7 @@ QDEG_C0ROW = 6    # shared with oracle/forms.py::QDEG["c0row"]; part of the pari
 
 
 class Spaces:
-    """P1 and P2 scalar dofmaps of one mesh (UFC numbering: vertices, then V + edge id) on host and device."""
+    """P1 / P2 / P3 scalar Lagrange dofmaps of one mesh (UFC numbering: vertices, then edge dofs, then face/cell dofs) on host and device."""
 
     def __init__(self, ctx: Context, mesh):
         self.ctx, self.mesh = ctx, mesh
@@ -36,21 +36,58 @@ class Spaces:
         self.cd1 = self.dm.cells
         self.cd2 = ctx.to_device(self.cd2_host, torch.int32)
         self.nb1, self.nb2 = d + 1, self.cd2_host.shape[1]
+        self._cd3 = None
         self._plans = {}
         self._tens = {}
 
+    # ---- P3: 2 dofs per edge (nearer the lower vertex first), 1 per face (tets) / per cell (triangles)
+    def _init_p3(self):
+        if self._cd3 is not None:
+            return
+        m = self.mesh
+        ce = m.cell_edges.astype(np.int64)
+        ed = np.stack([self.n1 + 2 * ce, self.n1 + 2 * ce + 1], axis=2).reshape(m.num_cells(), -1)
+        base = self.n1 + 2 * m.num_edges()
+        if m.dim == 2:
+            inner = base + np.arange(m.num_cells(), dtype=np.int64)[:, None]
+            self.n3 = base + m.num_cells()
+        else:
+            inner = base + m.cell_faces.astype(np.int64)
+            self.n3 = base + m.faces.shape[0]
+        self.cd3_host = np.ascontiguousarray(np.concatenate([m.cells.astype(np.int64), ed, inner], axis=1).astype(np.int32))
+        self._cd3 = self.ctx.to_device(self.cd3_host, torch.int32)
+        self.nb3 = self.cd3_host.shape[1]
+
+    def ndof(self, degree):
+        if degree == 3:
+            self._init_p3()
+        return {1: self.n1, 2: self.n2}[degree] if degree < 3 else self.n3
+
+    def cell_dofs(self, degree):
+        if degree == 3:
+            self._init_p3()
+            return self._cd3
+        return self.cd1 if degree == 1 else self.cd2
+
+    def nb(self, degree):
+        return ref.nbasis(degree, self.mesh.dim)
+
     def dof_coords(self, degree):
+        m = self.mesh
         if degree == 1:
-            return self.mesh.coords
-        e = self.mesh.edges
-        return np.concatenate([self.mesh.coords, 0.5 * (self.mesh.coords[e[:, 0]] + self.mesh.coords[e[:, 1]])], axis=0)
+            return m.coords
+        e = m.edges
+        a, b = m.coords[e[:, 0]], m.coords[e[:, 1]]
+        if degree == 2:
+            return np.concatenate([m.coords, 0.5 * (a + b)], axis=0)
+        ed = np.stack([(2.0 * a + b) / 3.0, (a + 2.0 * b) / 3.0], axis=1).reshape(-1, m.dim)
+        inner = m.coords[m.cells].mean(1) if m.dim == 2 else m.coords[m.faces].mean(1)
+        return np.concatenate([m.coords, ed, inner], axis=0)
 
     def plan(self, deg_r, deg_c):
         key = (deg_r, deg_c)
         if key not in self._plans:
-            cr = self.cd1 if deg_r == 1 else self.cd2
-            cc = self.cd1 if deg_c == 1 else self.cd2
-            self._plans[key] = Plan(self.ctx, cr, cc, self.n1 if deg_r == 1 else self.n2, self.n1 if deg_c == 1 else self.n2)
+            self._plans[key] = Plan(self.ctx, self.cell_dofs(deg_r), self.cell_dofs(deg_c), self.ndof(deg_r), self.ndof(deg_c))
         return self._plans[key]
 
     def tensor(self, kind, deg_r, deg_c, p1coef=False):
@@ -63,8 +100,7 @@ class Spaces:
         """CSR matrix of one reference-tensor block; coef: None | float (folded into scale) | nodal P1 device tensor."""
         ctx = self.ctx
         plan = self.plan(deg_r, deg_c)
-        lr = self.nb1 if deg_r == 1 else self.nb2
-        lc = self.nb1 if deg_c == 1 else self.nb2
+        lr, lc = self.nb(deg_r), self.nb(deg_c)
         kid = {"mass": 0, "grad": 1, "gradT": 2, "stiff": 3}[kind]
         nodal = coef is not None and not np.isscalar(coef)
         if coef is not None and np.isscalar(coef):
@@ -193,7 +229,7 @@ class AdrSolverR:
         w, lam, vphi = ref.quadrature_tables(d, qdeg, vel_degree)
         self.qw, self.qlam, self.qvphi = ctx.to_device(w), ctx.to_device(lam.ravel()), ctx.to_device(vphi.ravel())
         self.quad = MpQuad(len(w), vphi.shape[1], self.qw.data_ptr(), self.qlam.data_ptr(), self.qvphi.data_ptr(), None)
-        self.vdofs = spaces.cd2 if vel_degree == 2 else spaces.cd1
+        self.vdofs = spaces.cell_dofs(vel_degree)
         self.plan = spaces.plan(1, 1)
         self.A = self.plan.new_matrix(sell=True)
         l = d + 1

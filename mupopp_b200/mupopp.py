@@ -121,7 +121,7 @@ class CCS:
 
 
 class StokesAdvection:
-    """mupopp.py:965-1099 (P3 velocity Stokes + ADR + precipitation): API kept; kernels are SURVEY.md section 8 row a7 (not built yet)."""
+    """mupopp.py:965-1099 (P3 velocity Stokes + ADR + precipitation), SURVEY.md section 8 row a7."""
 
     def __init__(self, Pe=100, Da=10.0, alpha=0.005, cfl=1.0e-2, dt=1.0e-2):
         self.Pe, self.Da, self.cfl, self.dt, self.alpha = Pe, Da, cfl, dt, alpha
@@ -335,4 +335,35 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
         c0n, c1n = prev.blocks[0].clone(), prev.blocks[1].clone()
         res = s.step(d["velocity"].blocks, c0n, c1n, u.blocks[0], u.blocks[1])
         return res.niter
-    raise NotImplementedError("solve: form kind %r is not on the B200 path yet (SURVEY.md section 8 rows a7-a10)" % kind)
+    if kind == "stokes_adr":
+        from . import stokes as _st
+        W, mesh, own = d["W"], d["mesh"], d["owner"]
+        dim = mesh.dim
+        vdeg = W.blocks[W.sub_blocks[0][0]][0]
+        dt = float(getattr(d["dt"], "dt", d["dt"]))
+        key = ("stokes", id(W), _bc_key(bcs), own.Pe, own.Da, dt, d["SUPG"])
+        if key not in _CACHE:
+            ub = W.sub_blocks[0]
+            c0b = W.sub_blocks[2][0]
+            arr = _bc_arrays(W, bcs, list(ub) + [c0b])
+            _CACHE[key] = _st.StokesAdrR(ctx, mesh, own.Pe, own.Da, dt, d["SUPG"], [arr[k][0] for k in ub], [arr[k][1] for k in ub],
+                                         arr[c0b][0], arr[c0b][1], vdeg=vdeg)
+        s = _CACHE[key]
+        prev = d["sol_prev"]
+        uv = s.u_views()
+        for c in range(dim):
+            uv[c].copy_(prev.blocks[c])
+        s.p.copy_(prev.blocks[dim])
+        s.c0.copy_(prev.blocks[dim + 1])
+        s.c1.copy_(prev.blocks[dim + 2])
+        s.c2.copy_(prev.blocks[dim + 3])
+        info_ = s.step()
+        uv = s.u_views()
+        for c in range(dim):
+            u.blocks[c].copy_(uv[c])
+        u.blocks[dim].copy_(s.p)
+        u.blocks[dim + 1].copy_(s.c0)
+        u.blocks[dim + 2].copy_(s.c1)
+        u.blocks[dim + 3].copy_(s.c2)
+        return info_
+    raise NotImplementedError("solve: unknown form kind %r" % kind)

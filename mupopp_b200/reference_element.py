@@ -68,9 +68,31 @@ def tabulate(degree, pts):
     dlam = np.concatenate([-np.ones((1, d)), np.eye(d)], axis=0)
     if degree == 1:
         return lam.copy(), np.broadcast_to(dlam, (nq, d + 1, d)).copy()
+    edges = TRI_EDGES if d == 2 else TET_EDGES
+    if degree == 3:
+        faces = [(0, 1, 2)] if d == 2 else [(1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2)]
+        nb = d + 1 + 2 * len(edges) + len(faces)
+        phi = np.empty((nq, nb))
+        dphi = np.empty((nq, nb, d))
+        for i in range(d + 1):
+            l = lam[:, i]
+            phi[:, i] = 0.5 * l * (3.0 * l - 1.0) * (3.0 * l - 2.0)
+            dphi[:, i] = (13.5 * l * l - 9.0 * l + 1.0)[:, None] * dlam[i]
+        k = d + 1
+        for (a, b) in edges:
+            for (ia, ib) in ((a, b), (b, a)):                 # the dof nearer the first (lower) vertex comes first
+                p_, q_ = lam[:, ia], lam[:, ib]
+                phi[:, k] = 4.5 * p_ * q_ * (3.0 * p_ - 1.0)
+                dphi[:, k] = 4.5 * ((6.0 * p_ * q_ - q_)[:, None] * dlam[ia] + (3.0 * p_ * p_ - p_)[:, None] * dlam[ib])
+                k += 1
+        for (a, b, c) in faces:
+            la, lb, lc = lam[:, a], lam[:, b], lam[:, c]
+            phi[:, k] = 27.0 * la * lb * lc
+            dphi[:, k] = 27.0 * ((lb * lc)[:, None] * dlam[a] + (la * lc)[:, None] * dlam[b] + (la * lb)[:, None] * dlam[c])
+            k += 1
+        return phi, dphi
     if degree != 2:
         raise NotImplementedError("Lagrange degree %d" % degree)
-    edges = TRI_EDGES if d == 2 else TET_EDGES
     nb = d + 1 + len(edges)
     phi = np.empty((nq, nb))
     dphi = np.empty((nq, nb, d))
@@ -84,7 +106,7 @@ def tabulate(degree, pts):
 
 
 def nbasis(degree, dim):
-    return dim + 1 if degree == 1 else (6 if dim == 2 else 10)
+    return {1: dim + 1, 2: 6 if dim == 2 else 10, 3: 10 if dim == 2 else 20}[degree]
 
 
 # ---- reference tensors for mp_elem_reftensor: A_e[i,j] = sum_t geo_t(cell) * T0[t][i][j] -------------------------------

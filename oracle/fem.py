@@ -71,6 +71,20 @@ class Mesh:
         self.init_edges()
         return self.edges.shape[0]
 
+    def init_faces(self):
+        """Global face numbering of a tetrahedral mesh: first-seen order over (cell, UFC local facet k = opposite vertex k)."""
+        if getattr(self, "faces", None) is not None:
+            return
+        fv = self.cells[:, TET_FACES]                 # (C, 4, 3) ascending
+        keys = (fv[..., 0].astype(np.int64) * self.nv + fv[..., 1]) * self.nv + fv[..., 2]
+        uniq, first, inv = np.unique(keys.ravel(), return_index=True, return_inverse=True)
+        order = np.argsort(first, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(order.size)
+        self.cell_faces = rank[inv].reshape(keys.shape)
+        u = uniq[order]
+        self.faces = np.stack([u // (self.nv * self.nv), (u // self.nv) % self.nv, u % self.nv], axis=1)
+
     def hmax_cells(self):
         """UFL CellDiameter: max vertex-vertex distance per cell (mupopp.py:797)."""
         le = TRI_EDGES if self.dim == 2 else TET_EDGES
@@ -209,6 +223,30 @@ def tabulate(degree, pts):
             phi[:, d + 1 + k] = 4 * lam[:, a] * lam[:, b]
             dphi[:, d + 1 + k, :] = 4 * (lam[:, a][:, None] * dlam[b][None, :] + lam[:, b][:, None] * dlam[a][None, :])
         return phi, dphi
+    if degree == 3:
+        le = TRI_EDGES if d == 2 else TET_EDGES
+        nint = 1 if d == 2 else 4
+        nb = d + 1 + 2 * len(le) + nint
+        phi = np.empty((nq, nb))
+        dphi = np.empty((nq, nb, d))
+        for i in range(d + 1):
+            l = lam[:, i]
+            phi[:, i] = 0.5 * l * (3 * l - 1) * (3 * l - 2)
+            dphi[:, i, :] = (0.5 * (27 * l * l - 18 * l + 2))[:, None] * dlam[i][None, :]
+        k = d + 1
+        for (a, b) in le:
+            la, lb = lam[:, a], lam[:, b]
+            for (p, q, ip, iq) in ((la, lb, a, b), (lb, la, b, a)):    # dof nearer vertex a first, then nearer b
+                phi[:, k] = 4.5 * p * q * (3 * p - 1)
+                dphi[:, k, :] = 4.5 * ((6 * p * q - q)[:, None] * dlam[ip][None, :] + (3 * p * p - p)[:, None] * dlam[iq][None, :])
+                k += 1
+        tris = [(0, 1, 2)] if d == 2 else [tuple(f) for f in TET_FACES]
+        for (a, b, c) in tris:
+            la, lb, lc = lam[:, a], lam[:, b], lam[:, c]
+            phi[:, k] = 27 * la * lb * lc
+            dphi[:, k, :] = 27 * ((lb * lc)[:, None] * dlam[a][None, :] + (la * lc)[:, None] * dlam[b][None, :] + (la * lb)[:, None] * dlam[c][None, :])
+            k += 1
+        return phi, dphi
     raise NotImplementedError(degree)
 
 
@@ -230,6 +268,20 @@ class ScalarSpace:
             m.init_edges()
             self.ndof = m.nv + m.ne
             self.cell_dofs = np.concatenate([m.cells, m.nv + m.cell_edges], axis=1)
+        elif self.degree == 3:
+            # vertices | 2 dofs per edge (nearer the lower vertex first; cells are UFC-ordered so local == global direction)
+            # | 1 dof per face (tets) or per cell (triangles)
+            m.init_edges()
+            ed = np.stack([m.nv + 2 * m.cell_edges, m.nv + 2 * m.cell_edges + 1], axis=2).reshape(m.nc, -1)
+            base = m.nv + 2 * m.ne
+            if m.dim == 2:
+                inner = base + np.arange(m.nc)[:, None]
+                self.ndof = base + m.nc
+            else:
+                m.init_faces()
+                inner = base + m.cell_faces
+                self.ndof = base + m.faces.shape[0]
+            self.cell_dofs = np.concatenate([m.cells, ed, inner], axis=1)
         else:
             raise NotImplementedError
 
@@ -237,6 +289,14 @@ class ScalarSpace:
         m = self.mesh
         if self.degree == 1:
             return m.coords.copy()
+        if self.degree == 3:
+            a, b = m.coords[m.edges[:, 0]], m.coords[m.edges[:, 1]]
+            ed = np.stack([(2 * a + b) / 3.0, (a + 2 * b) / 3.0], axis=1).reshape(-1, m.dim)
+            if m.dim == 2:
+                inner = m.coords[m.cells].mean(1)
+            else:
+                inner = m.coords[m.faces].mean(1)
+            return np.concatenate([m.coords, ed, inner], axis=0)
         mid = 0.5 * (m.coords[m.edges[:, 0]] + m.coords[m.edges[:, 1]])
         return np.concatenate([m.coords, mid], axis=0)
 

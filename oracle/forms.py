@@ -100,6 +100,7 @@ class Assembler:
         self.h = mesh.hmax_cells()
         self.P1 = fem.ScalarSpace(mesh, 1)
         self._P2 = None
+        self._P3 = None
         self._tab = {}
 
     @property
@@ -108,8 +109,14 @@ class Assembler:
             self._P2 = fem.ScalarSpace(self.mesh, 2)
         return self._P2
 
+    @property
+    def P3(self):
+        if self._P3 is None:
+            self._P3 = fem.ScalarSpace(self.mesh, 3)
+        return self._P3
+
     def space(self, degree):
-        return self.P1 if degree == 1 else self.P2
+        return {1: self.P1, 2: self.P2, 3: self.P3}[degree] if degree != 1 else self.P1
 
     def quad(self, qdeg):
         return fem.simplex_quadrature(self.mesh.dim, qdeg)
@@ -174,7 +181,7 @@ class Assembler:
         w = self.tab(1, qdeg)[0]
         if kind == "DG0":
             return np.broadcast_to(np.asarray(data)[:, None, :], (self.mesh.nc, len(w), self.mesh.dim)).copy()
-        deg = 2 if kind == "P2" else 1
+        deg = {"P1": 1, "P2": 2, "P3": 3}[kind]
         _, ph, _ = self.tab(deg, qdeg)
         s = self.space(deg)
         return np.stack([fem.eval_at_quad(s, np.asarray(c), ph) for c in data], axis=-1)

@@ -162,3 +162,44 @@ def test_compaction_through_api(ctx, tmp_path):
     phi1 = model.mass_solver(X, a_phi, L_phi, bb, nits=500, tol=1e-13)
     Ao, bo = oc.porosity_system(asm, 0.01, 0.1, phi_h, uo, np.zeros(om.nv))
     assert rel(phi1.get(), spla.splu(Ao.tocsc()).solve(bo)) < 1e-7
+
+
+def test_stokes_adr_through_api(ctx):
+    """StokesAdvection.stokes_ADR_precipitation + solve(a == L, sol, bc) on [P3^2, P1, P1, P1, P1] == oracle monolithic LU
+    (master_advective_stokes.py:94-130,208-218 with callable markers instead of the enGrid facet ids)."""
+    from mupopp_b200.fenics import (Constant, DirichletBC, FiniteElement, Function, FunctionSpace, MixedElement, RectangleMesh,
+                                    VectorElement, near, solve)
+    from mupopp_b200.mupopp import StokesAdvection
+    from oracle import stokes as os_
+    nx, ny = 6, 3
+    mesh = RectangleMesh((0.0, 0.0), (2.0, 1.0), nx, ny)
+    cell = mesh.ufl_cell()
+    Qc = FiniteElement("Lagrange", cell, 1)
+    W = FunctionSpace(mesh, MixedElement([VectorElement("Lagrange", cell, 3), FiniteElement("Lagrange", cell, 1), Qc, Qc, Qc]))
+    inflow = lambda x, on_boundary: on_boundary and near(x[0], 0.0, 1e-12)
+    walls = lambda x, on_boundary: on_boundary and (near(x[1], 0.0, 1e-12) or near(x[1], 1.0, 1e-12))
+    # facet-wise (topological) marking; the inflow condition is listed last so that it wins at the two corners
+    bcs = [DirichletBC(W.sub(0), Constant((0.0, 0.0)), walls), DirichletBC(W.sub(0), Constant((1.0, 0.0)), inflow),
+           DirichletBC(W.sub(2), Constant(0.1), inflow)]
+    stokes = StokesAdvection(Pe=0.1, Da=0.1)
+    sol_prev, sol = Function(W), Function(W)
+    sol_prev.blocks[4].fill_(0.1)          # An(0) = 0.1; blocks [ux, uy, p, c0, c1, c2]
+    om = fem.rectangle_mesh(0, 0, 2, 1, nx, ny)
+    asm = forms.Assembler(om)
+    X3, X1 = asm.P3.dof_coords(), om.coords
+    n3, n1 = asm.P3.ndof, asm.P1.ndof
+    inf3 = np.where(X3[:, 0] < 1e-12)[0]
+    wal3 = np.where(((X3[:, 1] < 1e-12) | (X3[:, 1] > 1 - 1e-12)) & (X3[:, 0] > 1e-12))[0]
+    D = np.unique(np.concatenate([inf3, wal3]))
+    g = [np.zeros(n3), np.zeros(n3)]
+    g[0][inf3] = 1.0
+    cin = np.where(X1[:, 0] < 1e-12)[0]
+    oprm = os_.stokes_adr_params(Pe=0.1, Da=0.1, dt=100.0, SUPG=2)
+    prev = forms.State(u=[np.zeros(n3), np.zeros(n3)], p=np.zeros(n1), c0=np.zeros(n1), c1=0.1 * np.ones(n1), c2=np.zeros(n1))
+    for k in range(2):
+        a, L = stokes.stokes_ADR_precipitation(W, mesh, sol_prev, 100.0)
+        solve(a == L, sol, bcs)
+        sol_prev = sol
+        prev = os_.monolithic_step(asm, oprm, prev, [D, D], [g[0][D], g[1][D]], cin, 0.1 * np.ones(len(cin)))
+        assert rel(np.concatenate([sol.get(0), sol.get(1)]), np.concatenate(prev.u)) < 1e-7
+        assert rel(sol.get(3), prev.c0) < 1e-8 and rel(sol.get(4), prev.c1) < 1e-9 and rel(sol.get(5), prev.c2) < 1e-8

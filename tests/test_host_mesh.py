@@ -56,3 +56,21 @@ def test_boundary_data_matches_oracle(dim):
     f1 = a.boundary_facets()[0]
     f2 = a2.boundary_facets()[0]
     assert sorted(map(tuple, f1.tolist())) == sorted(map(tuple, f2.tolist()))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_face_numbering_and_p3_tables_match_oracle(dim):
+    from mupopp_b200 import reference_element as ref
+    a = mp.RectangleMesh((0, 0), (2, 1), 4, 3) if dim == 2 else mp.BoxMesh((0, 0, 0), (2, 1, 1), 3, 2, 2)
+    b = fem.rectangle_mesh(0, 0, 2, 1, 4, 3) if dim == 2 else fem.box_mesh((0, 0, 0), (2, 1, 1), 3, 2, 2)
+    if dim == 3:
+        b.init_faces()
+        assert np.array_equal(a.faces, b.faces) and np.array_equal(a.cell_faces, b.cell_faces)
+    for deg in (1, 2, 3):
+        for q in (2, 4, 6, 8):
+            pts, w = ref.simplex_quadrature(dim, q)
+            po, wo = fem.simplex_quadrature(dim, q)
+            assert np.allclose(pts, po, rtol=0, atol=1e-15) and np.allclose(w, wo, rtol=0, atol=1e-15)
+            t1, d1 = ref.tabulate(deg, pts)
+            t2, d2 = fem.tabulate(deg, pts)
+            assert np.allclose(t1, t2, rtol=0, atol=1e-15) and np.allclose(d1, d2, rtol=0, atol=1e-14)
