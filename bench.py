@@ -106,23 +106,33 @@ def oracle_step_time(n, rtol, steps, warm, sides="noflow"):
     prm = forms.ccs_three_component_params(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"], dt=PHYS["dt"],
                                            K=PHYS["K"], zhat=(0.0, 0.0, 1.0), gam_rho=PHYS["gam_rho"])
     top = lambda x: x[2] > 1.0 - 1e-12
-    if sides == "noflow":
+    P = None
+    if sides == "periodic":
+        P, dof = modef.periodic_prolongation(m, (0, 1), BOX[0], BOX[1])
+        bcs = modef.make_bcs_periodic(m, (0, 1), dof, top, lambda x: np.array([0.0, 0.0, -0.5]), top, 0.1)
+    elif sides == "noflow":
         bcs = modef.make_bcs(m, lambda x: x[2] > 1e-12, lambda x: np.array([0.0, 0.0, -0.5 if x[2] > 1.0 - 1e-12 else 0.0]), top, 0.1)
     else:
         bcs = modef.make_bcs(m, top, lambda x: np.array([0.0, 0.0, -0.5]), top, 0.1)
     f = source_term(m.coords)
-    st = modef.StateF(u=np.zeros((m.nc, 3)), p=np.zeros(m.nv), c0=np.zeros(m.nv), c1=0.1 * np.ones(m.nv), c2=np.zeros(m.nv))
+    nd = m.nv
+    if P is not None:
+        nd = P.shape[1]
+        first = np.full(nd, -1, dtype=np.int64)
+        first[dof[::-1]] = np.arange(m.nv)[::-1]
+        f = f[first]
+    st = modef.StateF(u=np.zeros((m.nc, 3)), p=np.zeros(nd), c0=np.zeros(nd), c1=0.1 * np.ones(nd), c2=np.zeros(nd))
     times, iters = [], []
     for k in range(warm + steps):
         info = {}
         t0 = time.perf_counter()
-        st = modef.step(asm, prm, st, f, bcs, solver="krylov", rtol=rtol, info=info)
+        st = modef.step(asm, prm, st, f, bcs, solver="krylov", rtol=rtol, info=info, P=P)
         dt = time.perf_counter() - t0
         if k >= warm:
             times.append(dt)
             iters.append(dict(info))
         log("[oracle] n=%d step %d: %.2f s iters %s" % (n, k, dt, info))
-    return m.nv, times, iters
+    return nd, times, iters
 
 
 def run_reference(args):
@@ -173,19 +183,24 @@ def build_problem(ctx, args, rank, nranks):
         uval = lambda x: np.stack([0 * x[..., 0], 0 * x[..., 0], np.where(x[..., 2] > 1.0 - 1e-12, -0.5, 0.0)], -1)
     else:
         umark, uval = top, (0.0, 0.0, -0.5)
+    per = args.sides == "periodic"
     if nranks == 1:
+        from mupopp_b200.mesh import box_periodic_map
         mesh = mp.BoxMesh(BOX[0], BOX[1], n, n, n)
-        bd = make_boundary_data(mesh, umark, uval, top, 0.1)
-        solver = TransportSolverF(ctx, mesh, model, bd, f_source=source_term(mesh.coords), rtol=args.rtol, maxit=args.maxit,
-                                  c0_method=args.c0_method)
-        c1 = 0.1 * np.ones(mesh.num_vertices())
+        pmap = box_periodic_map(mesh, (0, 1)) if per else None
+        bd = make_boundary_data(mesh, umark, uval, top, 0.1, periodic=pmap)
+        fs = source_term(mesh.coords)
+        solver = TransportSolverF(ctx, mesh, model, bd, f_source=pmap.restrict(fs) if per else fs, rtol=args.rtol, maxit=args.maxit,
+                                  c0_method=args.c0_method, vert2dof=pmap.vert2dof if per else None)
+        c1 = 0.1 * np.ones(solver.dm.ndof)
     else:
-        part = partition.slab_partition(BOX, (n, n, n), rank, nranks)
+        part = partition.slab_partition(BOX, (n, n, n), rank, nranks, periodic_xy=per)
         bd = partition.slab_boundary_data(part, umark, uval, top, 0.1)
         halo = partition.make_halo(ctx, part)
-        solver = TransportSolverF(ctx, part.mesh, model, bd, f_source=source_term(part.mesh.coords), rtol=args.rtol,
-                                  maxit=args.maxit, c0_method=args.c0_method, halo=halo, n_owned=part.n_owned)
-        c1 = 0.1 * np.ones(part.mesh.num_vertices())
+        fs = source_term(part.mesh.coords)
+        solver = TransportSolverF(ctx, part.mesh, model, bd, f_source=part.periodic.restrict(fs) if per else fs, rtol=args.rtol,
+                                  maxit=args.maxit, c0_method=args.c0_method, halo=halo, n_owned=part.n_owned, vert2dof=part.vert2dof)
+        c1 = 0.1 * np.ones(part.n_local)
     solver.set_state(c1=c1)
     return solver
 
@@ -290,9 +305,11 @@ def run_b200(args):
                "krylov_iterations_per_step": iters,
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out},
-               "roofline": {"bound": "hbm", "kernel": "k_spmv (CSR SpMV inside PCG/GMRES, per-rank operator)", "achieved": achieved,
+               "roofline": {"bound": "hbm", "kernel": "k_spmv_sell (SELL-32 SpMV inside PCG/GMRES, per-rank operator)", "achieved": achieved,
                             "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-                            "frac": (achieved / peak) if achieved else None, "traffic": None,
+                            "frac": (achieved / peak) if achieved else None,
+                            # dram__bytes_read.sum + dram__bytes_write.sum of k_spmv_sell at this size, profiles/r1_ncu_full_production_kernels.md
+                            "traffic": 1.585e9 if (args.n == 200 and nranks == 1 and args.sides != "periodic") else None,
                             "algorithmic_bytes_per_launch": spmv_bytes, "launches_timed": n_spmv, "avg_launch_ms": avg_ms,
                             "share_of_step": spmv_ms / ms_total}}
         if not args.no_cpu and nranks == 1:
@@ -325,10 +342,10 @@ def main():
     ap.add_argument("--maxit", type=int, default=50000)
     ap.add_argument("--c0-method", default="gmres", choices=["gmres", "bicgstab"])
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--sides", default="noflow", choices=["natural", "noflow"],
+    ap.add_argument("--sides", default="noflow", choices=["natural", "noflow", "periodic"],
                     help="x/y faces: impermeable u.n=0 (default; same uniform-inflow regime as the reference's periodic sides, "
                          "CCS_3comp.py:131-143) or natural p=0 (CCS_3D_side_source.py)")
-    ap.add_argument("--hard-timeout", type=int, default=1500, help="SIGALRM kills the process after this many seconds (never hang a box)")
+    ap.add_argument("--hard-timeout", type=int, default=900, help="SIGALRM kills the process after this many seconds (never hang a box)")
     args = ap.parse_args()
     if args.hard_timeout > 0:
         import signal

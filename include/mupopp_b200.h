@@ -49,6 +49,9 @@ typedef struct {
     int64_t nvert;
     const int32_t *d_cells; /* [ncell][dim+1] vertex ids, ascending per cell (UFC ordering) */
     const double *d_coords; /* [nvert][dim] */
+    /* optional [ncell][dim+1] P1 dof ids when they differ from the vertex ids (periodic `constrained_domain`,
+     * run/CCS/CCS_3D_top_source.py:134-158,211): geometry comes from d_cells, nodal fields are gathered through d_cell_dofs */
+    const int32_t *d_cell_dofs;
 } mp_mesh;
 
 /* ------------------------------------------------------------------ scatter plan

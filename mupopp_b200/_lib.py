@@ -22,7 +22,7 @@ class MpError(RuntimeError):
 
 class MpMesh(C.Structure):
     _fields_ = [("dim", C.c_int32), ("ncell", C.c_int64), ("nvert", C.c_int64),
-                ("d_cells", C.c_void_p), ("d_coords", C.c_void_p)]
+                ("d_cells", C.c_void_p), ("d_coords", C.c_void_p), ("d_cell_dofs", C.c_void_p)]
 
 
 class MpTransportParams(C.Structure):

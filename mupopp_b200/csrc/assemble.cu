@@ -15,15 +15,17 @@ inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 template <int D>
 struct Geom {
-    int32_t v[D + 1];
+    int32_t v[D + 1];     // vertex ids (geometry)
+    int32_t dof[D + 1];   // P1 dof ids (== v unless the space is periodic)
     double g[D + 1][D];  // physical gradients of the barycentric (P1) basis
     double vol;
     double h;            // UFL CellDiameter: max vertex distance (mupopp.py:797,828)
 };
 
 template <int D>
-__device__ __forceinline__ void load_geom(const int32_t *__restrict__ cells, const double *__restrict__ coords, int64_t c,
-                                          Geom<D> &G) {
+__device__ __forceinline__ void load_geom(const mp_mesh &m, int64_t c, Geom<D> &G) {
+    const int32_t *__restrict__ cells = m.d_cells;
+    const double *__restrict__ coords = m.d_coords;
     double x[D + 1][D];
     if (D == 3) {
         const int4 q = *reinterpret_cast<const int4 *>(cells + 4 * c);
@@ -31,6 +33,13 @@ __device__ __forceinline__ void load_geom(const int32_t *__restrict__ cells, con
     } else {
 #pragma unroll
         for (int i = 0; i <= D; ++i) G.v[i] = cells[(D + 1) * c + i];
+    }
+    if (m.d_cell_dofs) {
+#pragma unroll
+        for (int i = 0; i <= D; ++i) G.dof[i] = m.d_cell_dofs[(D + 1) * c + i];
+    } else {
+#pragma unroll
+        for (int i = 0; i <= D; ++i) G.dof[i] = G.v[i];
     }
 #pragma unroll
     for (int i = 0; i <= D; ++i)
@@ -90,7 +99,7 @@ __device__ __forceinline__ void load_geom(const int32_t *__restrict__ cells, con
 
 template <int D> __device__ __forceinline__ void gather(const double *__restrict__ f, const Geom<D> &G, double (&out)[D + 1]) {
 #pragma unroll
-    for (int i = 0; i <= D; ++i) out[i] = f[G.v[i]];
+    for (int i = 0; i <= D; ++i) out[i] = f[G.dof[i]];
 }
 template <int D> __device__ __forceinline__ double sum(const double (&a)[D + 1]) {
     double s = 0.0;
@@ -205,7 +214,7 @@ __device__ __forceinline__ double cell_K(const double *__restrict__ K, double Kc
     if (!K) return Kconst;
     double s = 0.0;
 #pragma unroll
-    for (int i = 0; i <= D; ++i) s += K[G.v[i]];
+    for (int i = 0; i <= D; ++i) s += K[G.dof[i]];
     return s * (1.0 / (D + 1));
 }
 
@@ -216,7 +225,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_mass(mp_mesh m, double scale, d
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double A[D + 1][D + 1];
     const double w = scale * G.vol * Coef<D>::c2;
 #pragma unroll
@@ -232,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_stiffness(mp_mesh m, const doub
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     const double w = scale * cell_K<D>(K, Kconst, G) * G.vol;
     double A[D + 1][D + 1];
 #pragma unroll
@@ -256,7 +265,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_reaction_rhs(mp_mesh m, mp_tran
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double a0[D + 1], a1[D + 1], Ti[D + 1], mean;
     gather<D>(c0n, G, a0);
     gather<D>(c1n, G, a1);
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport(mp_mesh m, mp_transpo
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double u[D], vn2 = 0.0;
 #pragma unroll
     for (int a = 0; a < D; ++a) { u[a] = ucell[c * D + a]; vn2 += u[a] * u[a]; }
@@ -373,7 +382,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_adr_single(mp_mesh m, double Pe
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double u[D], vn2 = 0.0;
 #pragma unroll
     for (int a = 0; a < D; ++a) { u[a] = ucell[c * D + a]; vn2 += u[a] * u[a]; }
@@ -433,7 +442,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_pressure_rhs(mp_mesh m, mp_tran
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double a0[D + 1];
     gather<D>(c0, G, a0);
     const double rho = P.rho0 + P.gamma * sum<D>(a0) * (1.0 / (D + 1));
@@ -457,7 +466,7 @@ __global__ void __launch_bounds__(kThreads) k_recover_velocity(mp_mesh m, mp_tra
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double a0[D + 1], pp[D + 1];
     gather<D>(c0, G, a0);
     gather<D>(p, G, pp);
@@ -484,7 +493,7 @@ __global__ void __launch_bounds__(kThreads) k_reftensor(mp_mesh m, int kind, int
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double detJ = G.vol;
 #pragma unroll
     for (int k = 2; k <= D; ++k) detJ *= k;
@@ -527,7 +536,7 @@ __global__ void __launch_bounds__(kThreads) k_reftensor(mp_mesh m, int kind, int
     if (coef_kind == 1) {
         double Kv[D + 1];
 #pragma unroll
-        for (int v = 0; v <= D; ++v) Kv[v] = coef[G.v[v]];
+        for (int v = 0; v <= D; ++v) Kv[v] = coef[G.dof[v]];
         for (int e = 0; e < L; ++e) {
             double sum = 0.0;
             for (int t = 0; t < nT; ++t) {
@@ -569,7 +578,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport_quad(mp_mesh m, mp_tr
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double detJ = G.vol;
 #pragma unroll
     for (int k = 2; k <= D; ++k) detJ *= k;
@@ -700,7 +709,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_fn(mp_mesh m, QuadView Q, int
     if (c >= m.ncell) return;
     double ph[D + 1];
 #pragma unroll
-    for (int i = 0; i <= D; ++i) ph[i] = phi[m.d_cells[(D + 1) * c + i]];
+    for (int i = 0; i <= D; ++i) ph[i] = phi[(m.d_cell_dofs ? m.d_cell_dofs : m.d_cells)[(D + 1) * c + i]];
     double s = 0.0;
     for (int q = 0; q < Q.nq; ++q) {
         double pq = 0.0;
@@ -721,7 +730,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_mass_fn(mp_mesh m, QuadView Q, 
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double detJ = G.vol;
 #pragma unroll
     for (int k = 2; k <= D; ++k) detJ *= k;
@@ -757,7 +766,7 @@ __global__ void __launch_bounds__(kThreads) k_compaction_rhs(mp_mesh m, QuadView
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double detJ = G.vol;
 #pragma unroll
     for (int k = 2; k <= D; ++k) detJ *= k;
@@ -818,7 +827,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_porosity_quad(mp_mesh m, QuadVi
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= m.ncell) return;
     Geom<D> G;
-    load_geom<D>(m.d_cells, m.d_coords, c, G);
+    load_geom<D>(m, c, G);
     double detJ = G.vol;
 #pragma unroll
     for (int k = 2; k <= D; ++k) detJ *= k;

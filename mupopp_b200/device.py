@@ -95,7 +95,10 @@ class Context:
 
 
 class DeviceMesh:
-    def __init__(self, ctx: Context, mesh):
+    """Mesh on the device.  `vert2dof` (int array, one P1 dof per vertex) identifies vertices of a periodic space; then
+    `cell_dofs` differs from `cells`, `ndof < nvert`, and nodal fields live in dof numbering."""
+
+    def __init__(self, ctx: Context, mesh, vert2dof=None):
         self.ctx = ctx
         self.host = mesh
         self.dim = mesh.dim
@@ -103,7 +106,14 @@ class DeviceMesh:
         self.nvert = mesh.num_vertices()
         self.cells = ctx.to_device(mesh.cells, torch.int32)
         self.coords = ctx.to_device(mesh.coords, torch.float64)
-        self.c = MpMesh(self.dim, self.ncell, self.nvert, self.cells.data_ptr(), self.coords.data_ptr())
+        if vert2dof is None:
+            self.cell_dofs, self.ndof, dp = self.cells, self.nvert, None
+        else:
+            v2d = np.asarray(vert2dof, dtype=np.int32)
+            self.cell_dofs = ctx.to_device(np.ascontiguousarray(v2d[mesh.cells]), torch.int32)
+            self.ndof = int(v2d.max()) + 1
+            dp = self.cell_dofs.data_ptr()
+        self.c = MpMesh(self.dim, self.ncell, self.nvert, self.cells.data_ptr(), self.coords.data_ptr(), dp)
 
 
 class Plan:

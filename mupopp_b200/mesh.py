@@ -116,9 +116,16 @@ class Mesh:
         return self._cell_faces
 
     # -- boundary facets -----------------------------------------------------------
-    def boundary_facets(self):
+    def boundary_facets(self, exclude_axes=()):
         """(facet vertices (F,d), outward unit normals (F,d), measures (F,), owning cell (F,)).
-        A boundary facet belongs to exactly one cell; order = ascending (local facet, cell)."""
+        A boundary facet belongs to exactly one cell; order = ascending (local facet, cell).
+        `exclude_axes`: faces normal to these axes are periodic images of one another, not boundary (result not cached)."""
+        if exclude_axes:
+            fv, n, meas, owner = self.boundary_facets()
+            keep = np.ones(fv.shape[0], dtype=bool)
+            for a in exclude_axes:
+                keep &= np.abs(n[:, a]) < 0.5
+            return fv[keep], n[keep], meas[keep], owner[keep]
         if self._bfacets is not None:
             return self._bfacets
         d = self.dim
@@ -249,3 +256,53 @@ def BoxMesh(p0, p1, nx, ny, nz, z_range=None):
 
 def UnitCubeMesh(nx, ny, nz):
     return BoxMesh((0.0, 0.0, 0.0), (1.0, 1.0, 1.0), nx, ny, nz)
+
+
+class PeriodicMap:
+    """P1 dof identification of a periodic `constrained_domain` (the reference: run/CCS/CCS_3D_top_source.py:134-158,
+    run/CCS2D/CCS_3comp.py:131-143): slave vertices share the dof of their master; dofs are numbered compactly in master order.
+    `vert2dof[v]` = dof of vertex v, `dof2vert[j]` = the master vertex of dof j, `axes` = periodic coordinate directions."""
+
+    def __init__(self, vert2dof, axes, box):
+        self.vert2dof = np.asarray(vert2dof, dtype=np.int32)
+        self.ndof = int(self.vert2dof.max()) + 1          # need not be "master order" (slab partitions put owned planes first)
+        self.axes = tuple(axes)
+        self.box = box
+        d2v = np.full(self.ndof, -1, dtype=np.int64)
+        # masters are the lowest-numbered vertex of each class
+        order = np.arange(self.vert2dof.size)[::-1]
+        d2v[self.vert2dof[order]] = order
+        self.dof2vert = d2v
+
+    def fold_sum(self, a):
+        return np.bincount(self.vert2dof, weights=np.asarray(a, dtype=float), minlength=self.ndof)
+
+    def fold_any(self, a):
+        out = np.zeros(self.ndof, dtype=np.uint8)
+        np.maximum.at(out, self.vert2dof, np.asarray(a, dtype=np.uint8))
+        return out
+
+    def restrict(self, a):
+        """Vertex array -> dof array taking the master's value."""
+        return np.asarray(a)[self.dof2vert]
+
+
+def box_periodic_map(mesh, axes):
+    """Identify the max-face of each periodic axis with its min-face on an axis-aligned box mesh (any simplicial mesh whose
+    boundary vertices on the two faces match up to a translation)."""
+    if mesh.box is None:
+        raise ValueError("box_periodic_map needs a mesh with a known bounding box")
+    lo, hi = mesh.box
+    X = mesh.coords
+    tol = 1e-9 * float(np.max(hi - lo))
+    img = X.copy()
+    for a in axes:
+        on_hi = np.abs(X[:, a] - hi[a]) <= tol
+        img[on_hi, a] = lo[a]
+    scale = 1.0 / (1e-7 * float(np.max(hi - lo)))
+    key = np.round((img - lo) * scale).astype(np.int64)
+    _, first, inv = np.unique(key, axis=0, return_index=True, return_inverse=True)
+    master = first[inv.ravel()]                       # lowest vertex id with the same image
+    is_master = master == np.arange(X.shape[0])
+    dof_of_master = np.cumsum(is_master) - 1
+    return PeriodicMap(dof_of_master[master], axes, (lo, hi))

@@ -24,8 +24,10 @@ class SlabPartition:
     mesh: Mesh             # local mesh in local numbering
     n_owned: int
     n_local: int
-    global_ids: np.ndarray  # local vertex -> global vertex id
+    global_ids: np.ndarray  # local dof -> global dof id (== vertex ids unless periodic)
     neigh: list            # [(rank, send_local_idx ndarray, recv_start, recv_count), ...]
+    vert2dof: np.ndarray = None   # periodic x/y: local P1 dof of every local vertex
+    periodic: object = None       # mesh.PeriodicMap of the local mesh (periodic x/y)
 
 
 def plane_ranges(nz, nranks):
@@ -40,7 +42,11 @@ def plane_ranges(nz, nranks):
     return out
 
 
-def slab_partition(box, grid, rank, nranks):
+def slab_partition(box, grid, rank, nranks, periodic_xy=False):
+    """`periodic_xy`: the x and y faces are periodic (constrained_domain of run/CCS/CCS_3D_top_source.py:134-158): each
+    vertex plane then carries nx*ny dofs; the z-slab structure and the halo pattern are unchanged."""
+    if periodic_xy:
+        return _slab_partition_periodic(box, grid, rank, nranks)
     nx, ny, nz = grid
     if nranks > nz + 1:
         raise ValueError("more ranks than vertex planes")
@@ -86,9 +92,48 @@ def slab_partition(box, grid, rank, nranks):
     return SlabPartition(rank, nranks, grid, (a, b), loc, n_owned, nplanes * npl, gids, neigh)
 
 
+def _slab_partition_periodic(box, grid, rank, nranks):
+    from .mesh import PeriodicMap
+    nx, ny, nz = grid
+    if nranks > nz + 1:
+        raise ValueError("more ranks than vertex planes")
+    a, b = plane_ranges(nz, nranks)[rank]
+    k0, k1 = max(a - 1, 0), min(b, nz)
+    m = BoxMesh(box[0], box[1], nx, ny, nz, z_range=(k0, k1))
+    m.box = (np.array(box[0], dtype=float), np.array(box[1], dtype=float))
+    npd = nx * ny                                   # dofs per plane
+    has_lo, has_hi = a > 0, b <= nz
+    start, pos = {}, 0
+    for k in range(a, b):
+        start[k] = pos
+        pos += npd
+    n_owned = pos
+    if has_lo:
+        start[a - 1] = pos
+        pos += npd
+    if has_hi:
+        start[b] = pos
+        pos += npd
+    n_local = pos
+    ix = np.tile(np.arange(nx + 1), ny + 1) % nx
+    iy = np.repeat(np.arange(ny + 1), nx + 1) % ny
+    inplane = iy * nx + ix
+    v2d = np.concatenate([start[k] + inplane for k in range(k0, k1 + 1)]).astype(np.int32)
+    gids = np.empty(n_local, dtype=np.int64)
+    for k in range(k0, k1 + 1):
+        gids[start[k]:start[k] + npd] = k * npd + np.arange(npd)
+    neigh = []
+    if has_lo:
+        neigh.append((rank - 1, np.arange(0, npd, dtype=np.int32), start[a - 1], npd))
+    if has_hi:
+        neigh.append((rank + 1, np.arange(n_owned - npd, n_owned, dtype=np.int32), start[b], npd))
+    pmap = PeriodicMap(v2d, (0, 1), m.box)
+    return SlabPartition(rank, nranks, grid, (a, b), m, n_owned, n_local, gids, neigh, v2d, pmap)
+
+
 def slab_boundary_data(part: SlabPartition, u_marker, u_value, c0_marker=None, c0_value=0.0):
     from .transport import make_boundary_data
-    return make_boundary_data(part.mesh, u_marker, u_value, c0_marker, c0_value)
+    return make_boundary_data(part.mesh, u_marker, u_value, c0_marker, c0_value, periodic=part.periodic)
 
 
 def make_halo(ctx, part: SlabPartition):

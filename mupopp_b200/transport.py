@@ -85,10 +85,11 @@ def _eval_value(value, x, ncomp):
     return np.broadcast_to(np.atleast_1d(np.asarray(value, dtype=float)), (x.shape[0], ncomp)).copy()
 
 
-def make_boundary_data(mesh, u_marker, u_value, c0_marker=None, c0_value=0.0):
+def make_boundary_data(mesh, u_marker, u_value, c0_marker=None, c0_value=0.0, periodic=None):
     """Host setup of the Dirichlet/Neumann data (DOLFIN 'topological' facet marking: a facet is on Gamma_u if
-    all its vertices and its midpoint satisfy the marker).  One-time; not part of the timestep."""
-    fv, n, meas, _ = mesh.boundary_facets()
+    all its vertices and its midpoint satisfy the marker).  One-time; not part of the timestep.
+    `periodic`: a mesh.PeriodicMap -- its faces are not boundary and the result is returned in dof numbering."""
+    fv, n, meas, _ = mesh.boundary_facets(periodic.axes if periodic is not None else ())
     d = mesh.dim
     V = mesh.num_vertices()
     bverts = np.unique(fv.ravel())
@@ -115,6 +116,11 @@ def make_boundary_data(mesh, u_marker, u_value, c0_marker=None, c0_value=0.0):
         sel = bverts[_eval_marker(c0_marker, mesh.coords[bverts])]
         c0_isbc[sel] = 1
         c0_g[sel] = _eval_value(c0_value, mesh.coords[sel], 1)[:, 0]
+    if periodic is not None:
+        c0m = periodic.fold_any(c0_isbc)
+        g = np.zeros(periodic.ndof)
+        g[periodic.vert2dof[c0_isbc.astype(bool)]] = c0_g[c0_isbc.astype(bool)]
+        return BoundaryDataF(periodic.fold_any(p_isbc), periodic.fold_sum(flux), c0m, g)
     return BoundaryDataF(p_isbc, flux, c0_isbc, c0_g)
 
 
@@ -122,22 +128,24 @@ class TransportSolverF:
     """GPU state + operators of one mode-F problem.  Fields are torch fp64 tensors on the device."""
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
-                 rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="gmres", gmres_restart=50):
+                 rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="gmres", gmres_restart=50,
+                 vert2dof=None):
+        """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
         self.halo = halo
-        self.dm = DeviceMesh(ctx, mesh)
-        V, Cn, d = self.dm.nvert, self.dm.ncell, self.dm.dim
+        self.dm = DeviceMesh(ctx, mesh, vert2dof)
+        V, Cn, d = self.dm.ndof, self.dm.ncell, self.dm.dim
         self.nloc = V
         self.nown = V if n_owned is None else int(n_owned)
         self.K_dev = None if np.isscalar(model.K) else ctx.to_device(np.asarray(model.K, dtype=np.float64))
         self.prm = transport_params(model.Pe, model.Da, model.phi, model.alpha, model.dt, model.sigma, model.rho0, model.gamma,
                                     model.fracs, model.zhat, model.K, model.reaction, model.ncomp, model.SUPG)
         # row dofmap: rows of ghost vertices (>= nown) are not assembled (owner-computes)
-        rows = self.dm.cells
+        rows = self.dm.cell_dofs
         if self.nown < V:
-            rows = torch.where(self.dm.cells < self.nown, self.dm.cells, torch.full_like(self.dm.cells, -1))
-        self.plan = Plan(ctx, rows, self.dm.cells, self.nown, V)
+            rows = torch.where(rows < self.nown, rows, torch.full_like(rows, -1))
+        self.plan = Plan(ctx, rows, self.dm.cell_dofs, self.nown, V)
         l = d + 1
         self.emat = ctx.empty(Cn * l * l)
         self.evec = ctx.empty(Cn * l)

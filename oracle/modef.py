@@ -133,9 +133,56 @@ def recover_velocity(asm, prm, p, c0):
     return -kc[:, None] * (gp + prm.sigma * rho[:, None] * np.asarray(prm.zhat, dtype=float)[None, :])
 
 
-def step(asm: Assembler, prm: TransportParams, prev: StateF, fsrc, bcs: BCsF, solver="lu", rtol=1e-13, info=None):
+def periodic_prolongation(mesh, axes, lo, hi):
+    """P (V x ndof), P[v, dof(v)] = 1: vertices on the max-face of each periodic axis share the dof of their image on the
+    min-face; dofs numbered compactly in master-vertex order (constrained_domain of run/CCS/CCS_3D_top_source.py:134-158)."""
+    X = mesh.coords
+    ext = float(np.max(np.asarray(hi) - np.asarray(lo)))
+    img = X.copy()
+    for a in axes:
+        img[np.abs(X[:, a] - hi[a]) <= 1e-9 * ext, a] = lo[a]
+    key = [tuple(np.round((p - np.asarray(lo)) / (1e-7 * ext)).astype(np.int64)) for p in img]
+    first = {}
+    master = np.empty(mesh.nv, dtype=np.int64)
+    for v, k in enumerate(key):
+        master[v] = first.setdefault(k, v)
+    ism = master == np.arange(mesh.nv)
+    dof = (np.cumsum(ism) - 1)[master]
+    P = sp.csr_matrix((np.ones(mesh.nv), (np.arange(mesh.nv), dof)), shape=(mesh.nv, int(dof.max()) + 1))
+    return P, dof
+
+
+def make_bcs_periodic(mesh, axes, dof, u_pred, u_value, c0_pred=None, c0_value=0.0):
+    """make_bcs on the non-periodic part of the boundary, folded to dof numbering."""
+    fv, owner, opp = boundary_facets(mesh)
+    area, n = facet_measure_normal(mesh, fv, opp)
+    keep = np.ones(len(fv), dtype=bool)
+    for a in axes:
+        keep &= np.abs(n[:, a]) < 0.5
+    fv, area, n = fv[keep], area[keep], n[keep]
+    d = mesh.dim
+    x = mesh.coords[fv]
+    inside = np.array([[bool(u_pred(p)) for p in f] for f in x]).all(1) & np.array([bool(u_pred(p)) for p in x.mean(1)])
+    ndof = int(dof.max()) + 1
+    flux = np.zeros(ndof)
+    mloc = (np.ones((d, d)) + np.eye(d)) / (d * (d + 1))
+    for f in np.where(inside)[0]:
+        g = np.array([np.dot(u_value(p), n[f]) for p in x[f]])
+        np.add.at(flux, dof[fv[f]], area[f] * (mloc @ g))
+    p_dofs = np.unique(dof[fv[~inside].ravel()])
+    c0_dofs, c0_vals = np.zeros(0, dtype=np.int64), np.zeros(0)
+    if c0_pred is not None:
+        vs = np.array([i for i in np.unique(fv.ravel()) if c0_pred(mesh.coords[i])], dtype=np.int64)
+        c0_dofs, idx = np.unique(dof[vs], return_index=True)
+        c0_vals = np.array([c0_value(mesh.coords[i]) if callable(c0_value) else c0_value for i in vs[idx]], dtype=float)
+    return BCsF(p_dofs=p_dofs.astype(np.int64), flux_load=flux, c0_dofs=c0_dofs.astype(np.int64), c0_vals=c0_vals)
+
+
+def step(asm: Assembler, prm: TransportParams, prev: StateF, fsrc, bcs: BCsF, solver="lu", rtol=1e-13, info=None, P=None):
     """One mode-F timestep; `solver='lu'` (splu) or 'krylov' (SciPy cg/bicgstab + Jacobi,
-    the CPU baseline leg of bench.py)."""
+    the CPU baseline leg of bench.py).  `P`: periodic prolongation (V x ndof); fields, fsrc and bcs are then in dof numbering."""
+    if P is not None:
+        return _step_periodic(asm, prm, prev, fsrc, bcs, P, solver, rtol, info)
     nc = prm.ncomp
     M1 = asm.mass(1, 1, QDEG["mass_p1"])
     R1, R2, R3 = asm.reaction_q(prm, prev.c0, prev.c1, QDEG_F)
@@ -174,4 +221,42 @@ def step(asm: Assembler, prm: TransportParams, prev: StateF, fsrc, bcs: BCsF, so
     Lbc, bpbc = fem.apply_dirichlet_symmetric(L, bp, bcs.p_dofs, np.zeros(len(bcs.p_dofs)))
     p = spd_solve(Lbc, bpbc, prev.p, "p")
     u = recover_velocity(asm, prm, p, c0)
+    return StateF(u=u, p=p, c0=c0, c1=c1, c2=c2)
+
+
+def _step_periodic(asm, prm, prev, fsrc, bcs, P, solver, rtol, info):
+    """Mode-F step on a periodic P1 space: every vertex-level operator A becomes P^T A P, every load P^T b."""
+    nc = prm.ncomp
+    PT = P.T.tocsr()
+    v = lambda x: P @ x                      # dof vector -> vertex values
+    fold = lambda A: (PT @ A @ P).tocsr()
+
+    def solve_(A, b, x0, spd, tag):
+        if solver == "lu":
+            return spla.splu(A.tocsc()).solve(b)
+        Dinv = sp.diags(1.0 / A.diagonal())
+        it = [0]
+        fn = spla.cg if spd else spla.bicgstab
+        x, _ = fn(A, b, x0=x0, rtol=rtol, atol=0.0, M=Dinv, maxiter=20000, callback=lambda xk: it.__setitem__(0, it[0] + 1))
+        if info is not None:
+            info[tag] = it[0]
+        return x
+
+    c0v, c1v = v(prev.c0), v(prev.c1)
+    c2v = v(prev.c2) if nc == 3 else None
+    M1 = asm.mass(1, 1, QDEG["mass_p1"])
+    M1p = fold(M1)
+    R1, R2, R3 = asm.reaction_q(prm, c0v, c1v, QDEG_F)
+    c1 = solve_(M1p, PT @ (M1 @ c1v - prm.dt / (1 - prm.phi) * asm.load(1, QDEG_F, R2)), prev.c1, True, "c1")
+    c2 = None
+    if nc == 3:
+        c2 = solve_(M1p, PT @ (M1 @ c2v + prm.dt / (1 - prm.phi) * asm.load(1, QDEG_F, R3)), prev.c2, True, "c2")
+    A00, S, qd = asm.c0_row(prm, ("DG0", prev.u), QDEG_F)
+    b = asm.c0_rhs(prm, qd, c0v, c1v, c2v, v(fsrc), QDEG_F) - S @ (v(c1) + (v(c2) if nc == 3 else 0.0))
+    Abc, bbc = fem.apply_dirichlet_symmetric(fold(A00), PT @ b, bcs.c0_dofs, bcs.c0_vals)
+    c0 = solve_(Abc, bbc, prev.c0, False, "c0")
+    L, bp = pressure_system(asm, prm, v(c0))
+    Lbc, bpbc = fem.apply_dirichlet_symmetric(fold(L), PT @ bp - bcs.flux_load, bcs.p_dofs, np.zeros(len(bcs.p_dofs)))
+    p = solve_(Lbc, bpbc, prev.p, True, "p")
+    u = recover_velocity(asm, prm, v(p), v(c0))
     return StateF(u=u, p=p, c0=c0, c1=c1, c2=c2)

@@ -193,3 +193,53 @@ def test_krylov_solvers_against_direct(ctx, method):
     xo = spla.splu(Ao.tocsc()).solve(bo)
     assert res.converged, res
     assert rel(x.cpu().numpy(), xo) < 1e-10
+
+
+@pytest.mark.parametrize("dim,n", [(2, 10), (3, 5)])
+def test_periodic_constrained_domain_matches_oracle(ctx, dim, n):
+    """periodic side faces (constrained_domain of run/CCS/CCS_3D_top_source.py:134-158,211) in mode F:
+    dof identification changes the dofmap and the CSR pattern; fields must match the oracle's folded (P^T A P) systems."""
+    import mupopp_b200 as mp
+    from mupopp_b200.mesh import box_periodic_map
+    from mupopp_b200.transport import TransportModel, TransportSolverF, make_boundary_data
+    if dim == 2:
+        pm, om = mp.RectangleMesh((0, 0), (2, 1), n, n), fem.rectangle_mesh(0, 0, 2, 1, n, n)
+        axes, lo, hi, zh = (0,), (0.0, 0.0), (2.0, 1.0), (0.0, 1.0)
+    else:
+        pm, om = mp.BoxMesh((0, 0, 0), (2, 2, 1), n, n, n), fem.box_mesh((0, 0, 0), (2, 2, 1), n, n, n)
+        axes, lo, hi, zh = (0, 1), (0.0, 0.0, 0.0), (2.0, 2.0, 1.0), (0.0, 0.0, 1.0)
+    pmap = box_periodic_map(pm, axes)
+    P, dof = modef.periodic_prolongation(om, axes, lo, hi)
+    assert np.array_equal(pmap.vert2dof, dof)
+    nd = pmap.ndof
+    assert nd == (n ** (dim - 1)) * (n + 1)
+    model = TransportModel.ccs_three_component(Pe=500, Da=0.1, phi=0.05, alpha=1e-3, dt=0.1, K=1.0, zh=zh)
+    oprm = forms.ccs_three_component_params(Pe=500, Da=0.1, phi=0.05, alpha=1e-3, dt=0.1, K=1.0, zhat=zh)
+    uval = np.zeros(dim)
+    uval[-1] = -0.5
+    top = lambda x: x[..., -1] > 1.0 - 1e-12
+    bd = make_boundary_data(pm, top, uval, top, 0.1, periodic=pmap)
+    obc = modef.make_bcs_periodic(om, axes, dof, lambda x: x[-1] > 1.0 - 1e-12, lambda x: uval, lambda x: x[-1] > 1.0 - 1e-12, 0.1)
+    assert np.array_equal(bd.p_isbc.nonzero()[0], obc.p_dofs) and np.allclose(bd.flux_load, obc.flux_load, rtol=0, atol=1e-15)
+    X = om.coords
+    fv = np.abs(np.sin(np.pi * X[:, 0])) * (1 - np.tanh((1.0 - X[:, -1]) / 0.1))        # periodic in x with period 2... (|sin(pi x)|)
+    f = pmap.restrict(fv)
+    asm = forms.Assembler(om)
+    rng = np.random.default_rng(0)
+    c1_0, c2_0, c0_0 = 0.1 + 0.01 * rng.random(nd), 0.01 * rng.random(nd), 0.05 * rng.random(nd)
+    st = modef.StateF(u=np.zeros((om.nc, dim)), p=np.zeros(nd), c0=c0_0.copy(), c1=c1_0.copy(), c2=c2_0.copy())
+    s = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-14, vert2dof=pmap.vert2dof)
+    # the periodic CSR pattern is the pattern of P^T A P
+    rp, ci = s.plan.csr_pattern()
+    Mo = (P.T @ asm.mass(1, 1, 2) @ P).tocsr()
+    Mo.sort_indices()
+    assert np.array_equal(rp.cpu().numpy(), Mo.indptr) and np.array_equal(ci.cpu().numpy(), Mo.indices)
+    assert abs(s.M.to_scipy() - Mo).max() <= 1e-15 * abs(Mo).max() * 10
+    s.set_state(c0=c0_0, c1=c1_0, c2=c2_0)
+    for k in range(3):
+        st = modef.step(asm, oprm, st, f, obc, P=P)
+        res = s.step()
+        assert all(r is None or r.converged for r in res.values()), res
+    for nm in ("c0", "c1", "c2", "p"):
+        assert rel(getattr(s, nm).cpu().numpy(), getattr(st, nm)) < 1e-8, nm
+    assert rel(s.u.cpu().numpy().reshape(-1, dim), st.u) < 1e-8

@@ -16,6 +16,7 @@ from mupopp_b200.transport import TransportModel, TransportSolverF, make_boundar
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 nz = int(sys.argv[3]) if len(sys.argv) > 3 else n          # nz != n gives ranks of different size (collective control-flow check)
+per = len(sys.argv) > 4 and sys.argv[4] == "periodic"      # periodic x/y faces
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -29,10 +30,14 @@ top = lambda x: x[..., 2] > 1.0 - 1e-12
 umark = lambda x: x[..., 2] > 1e-12
 uval = lambda x: np.stack([0 * x[..., 0], 0 * x[..., 0], np.where(x[..., 2] > 1.0 - 1e-12, -0.5, 0.0)], -1)
 src = lambda X: np.abs(np.sin(3 * np.pi * X[:, 0])) * (1 - np.tanh((1.0 - X[:, 2]) / 0.1))
-part = partition.slab_partition(BOX, (n, n, nz), rank, world)
+if per:
+    umark, uval = top, (0.0, 0.0, -0.5)
+part = partition.slab_partition(BOX, (n, n, nz), rank, world, periodic_xy=per)
 bd = partition.slab_boundary_data(part, umark, uval, top, 0.1)
 halo = partition.make_halo(ctx, part)
-s = TransportSolverF(ctx, part.mesh, model, bd, f_source=src(part.mesh.coords), rtol=1e-13, halo=halo, n_owned=part.n_owned)
+fs = src(part.mesh.coords)
+s = TransportSolverF(ctx, part.mesh, model, bd, f_source=part.periodic.restrict(fs) if per else fs, rtol=1e-13, halo=halo,
+                     n_owned=part.n_owned, vert2dof=part.vert2dof)
 s.set_state(c1=0.1 * np.ones(part.n_local))
 its = []
 for k in range(nsteps):
@@ -40,7 +45,7 @@ for k in range(nsteps):
     its.append({a: (b.niter if b else 0) for a, b in r.items()})
 torch.cuda.synchronize()
 # gather owned parts on rank 0
-nglob = (n + 1) ** 2 * (nz + 1)
+nglob = (n * n if per else (n + 1) ** 2) * (nz + 1)
 out = {}
 for name in ("c0", "c1", "c2", "p"):
     full = torch.zeros(nglob, dtype=torch.float64, device=ctx.device)
@@ -52,9 +57,13 @@ ok = True
 if rank == 0:
     ctx1 = Context(local)
     mesh = mp.BoxMesh(BOX[0], BOX[1], n, n, nz)
-    bd1 = make_boundary_data(mesh, umark, uval, top, 0.1)
-    s1 = TransportSolverF(ctx1, mesh, model, bd1, f_source=src(mesh.coords), rtol=1e-13)
-    s1.set_state(c1=0.1 * np.ones(mesh.num_vertices()))
+    from mupopp_b200.mesh import box_periodic_map
+    pm1 = box_periodic_map(mesh, (0, 1)) if per else None
+    bd1 = make_boundary_data(mesh, umark, uval, top, 0.1, periodic=pm1)
+    fs1 = src(mesh.coords)
+    s1 = TransportSolverF(ctx1, mesh, model, bd1, f_source=pm1.restrict(fs1) if per else fs1, rtol=1e-13,
+                          vert2dof=pm1.vert2dof if per else None)
+    s1.set_state(c1=0.1 * np.ones(s1.dm.ndof))
     its1 = []
     for k in range(nsteps):
         r = s1.step()
