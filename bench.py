@@ -98,7 +98,7 @@ def measured_peak():
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
-def oracle_step_time(n, rtol, steps, warm, sides="noflow"):
+def oracle_step_time(n, rtol, steps, warm, sides="periodic"):
     """The oracle's mode-F timestep (NumPy assembly + SciPy cg/bicgstab with Jacobi) on an n^3 sample."""
     from oracle import fem, forms, modef
     m = fem.box_mesh(BOX[0], BOX[1], n, n, n)
@@ -143,7 +143,7 @@ def run_reference(args):
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
     ndof, times, iters = oracle_step_time(n, args.rtol, args.steps, min(args.warmup, 1), args.sides)
     ms = 1e3 * float(np.mean(times))
-    ndof_full = (args.n + 1) ** 3
+    ndof_full = ndofs_field(args)
     # scale the sample to the full workload linearly in dofs (optimistic for the CPU: Krylov iteration counts grow with n)
     value = 1.0 / (np.mean(times) * ndof_full / ndof)
     sample = ("oracle mode-F timestep (NumPy assembly + SciPy cg/bicgstab+Jacobi, rtol %g) on a %d^3 sample (%d dofs/field), "
@@ -159,11 +159,17 @@ def run_reference(args):
     return 0
 
 
+def ndofs_field(args):
+    """P1 dofs per scalar field: (n+1)^3 vertices, n^2 (n+1) when the x/y faces are periodic."""
+    n = args.n
+    return n * n * (n + 1) if args.sides == "periodic" else (n + 1) ** 3
+
+
 def workload_config(args, nranks):
     return {"workload": "CCS 3-component reactive transport (mupopp CCS.advection_diffusion_three_component), mode F, "
-                        "BoxMesh [0,4]x[0,4]x[0,1] %d^3 x 6 tets, P1, %d dofs/field" % (args.n, (args.n + 1) ** 3),
-            "n": args.n, "dofs_per_field": (args.n + 1) ** 3, "cells": 6 * args.n ** 3,
-            "physics": PHYS, "krylov_rtol": args.rtol, "c0_solver": args.c0_method, "preconditioner": "jacobi", "side_walls": args.sides,
+                        "BoxMesh [0,4]x[0,4]x[0,1] %d^3 x 6 tets, P1, %d dofs/field" % (args.n, ndofs_field(args)),
+            "n": args.n, "dofs_per_field": ndofs_field(args), "cells": 6 * args.n ** 3,
+            "physics": PHYS, "krylov_rtol": args.rtol, "c0_solver": args.c0_method + ("(%d)" % args.gmres_restart if args.c0_method == "gmres" else ""), "preconditioner": "jacobi", "side_walls": args.sides,
             "partition": "z-slabs x%d" % nranks if nranks > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (CSR operators 1.6 GB each at n=200 vs 126 MB L2)"}
 
@@ -191,7 +197,7 @@ def build_problem(ctx, args, rank, nranks):
         bd = make_boundary_data(mesh, umark, uval, top, 0.1, periodic=pmap)
         fs = source_term(mesh.coords)
         solver = TransportSolverF(ctx, mesh, model, bd, f_source=pmap.restrict(fs) if per else fs, rtol=args.rtol, maxit=args.maxit,
-                                  c0_method=args.c0_method, vert2dof=pmap.vert2dof if per else None)
+                                  c0_method=args.c0_method, gmres_restart=args.gmres_restart, vert2dof=pmap.vert2dof if per else None)
         c1 = 0.1 * np.ones(solver.dm.ndof)
     else:
         part = partition.slab_partition(BOX, (n, n, n), rank, nranks, periodic_xy=per)
@@ -199,7 +205,8 @@ def build_problem(ctx, args, rank, nranks):
         halo = partition.make_halo(ctx, part)
         fs = source_term(part.mesh.coords)
         solver = TransportSolverF(ctx, part.mesh, model, bd, f_source=part.periodic.restrict(fs) if per else fs, rtol=args.rtol,
-                                  maxit=args.maxit, c0_method=args.c0_method, halo=halo, n_owned=part.n_owned, vert2dof=part.vert2dof)
+                                  maxit=args.maxit, c0_method=args.c0_method, gmres_restart=args.gmres_restart, halo=halo, n_owned=part.n_owned,
+                                  vert2dof=part.vert2dof)
         c1 = 0.1 * np.ones(part.n_local)
     solver.set_state(c1=c1)
     return solver
@@ -309,14 +316,14 @@ def run_b200(args):
                             "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                             "frac": (achieved / peak) if achieved else None,
                             # dram__bytes_read.sum + dram__bytes_write.sum of k_spmv_sell at this size, profiles/r1_ncu_full_production_kernels.md
-                            "traffic": 1.585e9 if (args.n == 200 and nranks == 1 and args.sides != "periodic") else None,
+                            "traffic": 1.585e9 if (args.n == 200 and nranks == 1) else None,
                             "algorithmic_bytes_per_launch": spmv_bytes, "launches_timed": n_spmv, "avg_launch_ms": avg_ms,
                             "share_of_step": spmv_ms / ms_total}}
         if not args.no_cpu and nranks == 1:
             try:
                 ndof, times, oit = oracle_step_time(args.ref_n, args.rtol, 1, 0, args.sides)
                 cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()
-                v = 1.0 / (np.mean(times) * (args.n + 1) ** 3 / ndof)
+                v = 1.0 / (np.mean(times) * ndofs_field(args) / ndof)
                 out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "host_cores_available": cores,
                                        "sample": "1 oracle mode-F timestep (NumPy assembly + SciPy cg/bicgstab+Jacobi, same rtol) on a %d^3 "
                                                  "sample (%d dofs/field, %.1f s), scaled to %d^3 linearly in dofs (iteration growth "
@@ -340,11 +347,13 @@ def main():
     ap.add_argument("--ref-n", type=int, default=40, help="sample size of the CPU oracle leg")
     ap.add_argument("--rtol", type=float, default=1e-12)
     ap.add_argument("--maxit", type=int, default=50000)
-    ap.add_argument("--c0-method", default="gmres", choices=["gmres", "bicgstab"])
+    ap.add_argument("--c0-method", default="bicgstab", choices=["gmres", "bicgstab"],
+                    help="transport-row solver; bicgstab falls back to GMRES if it breaks down (TransportSolverF._solve_c0)")
+    ap.add_argument("--gmres-restart", type=int, default=30)
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--sides", default="noflow", choices=["natural", "noflow", "periodic"],
-                    help="x/y faces: impermeable u.n=0 (default; same uniform-inflow regime as the reference's periodic sides, "
-                         "CCS_3comp.py:131-143) or natural p=0 (CCS_3D_side_source.py)")
+    ap.add_argument("--sides", default="periodic", choices=["natural", "noflow", "periodic"],
+                    help="x/y faces: periodic constrained_domain (default; what the reference's CCS scripts use, CCS_3comp.py:131-143,212), "
+                         "impermeable u.n=0, or natural p=0 (CCS_3D_side_source.py)")
     ap.add_argument("--hard-timeout", type=int, default=900, help="SIGALRM kills the process after this many seconds (never hang a box)")
     args = ap.parse_args()
     if args.hard_timeout > 0:

@@ -52,6 +52,10 @@ typedef struct {
     /* optional [ncell][dim+1] P1 dof ids when they differ from the vertex ids (periodic `constrained_domain`,
      * run/CCS/CCS_3D_top_source.py:134-158,211): geometry comes from d_cells, nodal fields are gathered through d_cell_dofs */
     const int32_t *d_cell_dofs;
+    /* optional [ncell][dim+1]: position of each local row in the ROW-ORDERED element storage of a P1xP1 plan
+     * (mp_plan_row_positions); when set, the P1 element kernels store row i of cell c at elem[pos[c][i]] so that
+     * mp_scatter_*_ordered stream their input (negative position = row not assembled on this rank) */
+    const int32_t *d_row_pos;
 } mp_mesh;
 
 /* ------------------------------------------------------------------ scatter plan
@@ -76,6 +80,13 @@ int mp_csr_to_sell(mp_ctx *ctx, const mp_plan *plan, const double *d_csr_vals, d
 int mp_scatter_matrix(mp_ctx *ctx, const mp_plan *plan, const double *d_elem_mat, double *d_vals);
 /* out[r] = beta*out[r] + sum over incident (cell,i) of elem_vec[cell][i] */
 int mp_scatter_vector(mp_ctx *ctx, const mp_plan *plan, const double *d_elem_vec, double beta, double *d_out);
+
+/* Row-ordered element storage: elem_mat[e][lc] / elem_vec[e] with e the incidence index (row-major, ascending cell id inside a row),
+ * written directly by the P1 element kernels when mp_mesh.d_row_pos is set.  The scatter then reads contiguous memory
+ * (the cell-ordered variant reads one random 32-byte sector per (cell,row) pair, 3.5x DRAM amplification: profiles/). */
+int mp_plan_row_positions(const mp_plan *plan, const int32_t **d_pos);
+int mp_scatter_matrix_ordered(mp_ctx *ctx, const mp_plan *plan, const double *d_elem_mat_ordered, double *d_vals);
+int mp_scatter_vector_ordered(mp_ctx *ctx, const mp_plan *plan, const double *d_elem_vec_ordered, double beta, double *d_out);
 
 /* DOLFIN assemble_system semantics (symmetric elimination): rhs -= A[:,D] g; zero rows/cols D;
  * A[D,D] = 1; rhs[D] = g.  d_isbc[ncol] flags, d_g[ncol] values (ignored where isbc == 0). */

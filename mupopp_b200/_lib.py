@@ -22,7 +22,8 @@ class MpError(RuntimeError):
 
 class MpMesh(C.Structure):
     _fields_ = [("dim", C.c_int32), ("ncell", C.c_int64), ("nvert", C.c_int64),
-                ("d_cells", C.c_void_p), ("d_coords", C.c_void_p), ("d_cell_dofs", C.c_void_p)]
+                ("d_cells", C.c_void_p), ("d_coords", C.c_void_p), ("d_cell_dofs", C.c_void_p),
+                ("d_row_pos", C.c_void_p)]
 
 
 class MpTransportParams(C.Structure):
@@ -73,6 +74,9 @@ SIGNATURES = {
     "mp_plan_sell_info": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_VP), C.POINTER(_VP)]),
     "mp_csr_to_sell": (C.c_int, [_VP, _VP, _VP, _VP]),
     "mp_scatter_matrix": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "mp_scatter_matrix_ordered": (C.c_int, [_VP, _VP, _VP, _VP]),
+    "mp_scatter_vector_ordered": (C.c_int, [_VP, _VP, _VP, C.c_double, _VP]),
+    "mp_plan_row_positions": (C.c_int, [_VP, C.POINTER(_VP)]),
     "mp_scatter_vector": (C.c_int, [_VP, _VP, _VP, C.c_double, _VP]),
     "mp_apply_dirichlet_sym": (C.c_int, [_VP, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mp_elem_p1_mass": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_double, _VP]),

@@ -182,7 +182,23 @@ __device__ __forceinline__ double tau_supg(int supg, double Pe, double Da, doubl
 }
 
 template <int D>
-__device__ __forceinline__ void store_mat(double *__restrict__ emat, int64_t c, const double (&A)[D + 1][D + 1]) {
+__device__ __forceinline__ void store_mat(const mp_mesh &m, double *__restrict__ emat, int64_t c, const double (&A)[D + 1][D + 1]) {
+    if (m.d_row_pos) {   // row-ordered element storage: row i of this cell goes to its incidence slot (skipped if not assembled here)
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            const int32_t e = m.d_row_pos[c * (D + 1) + i];
+            if (e < 0) continue;
+            double *dst = emat + (int64_t)e * (D + 1);
+            if (D == 3) {
+                reinterpret_cast<double2 *>(dst)[0] = make_double2(A[i][0], A[i][1]);
+                reinterpret_cast<double2 *>(dst)[1] = make_double2(A[i][2], A[i][3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j <= D; ++j) dst[j] = A[i][j];
+            }
+        }
+        return;
+    }
     double *dst = emat + c * (D + 1) * (D + 1);
     if (D == 3) {
 #pragma unroll
@@ -198,7 +214,15 @@ __device__ __forceinline__ void store_mat(double *__restrict__ emat, int64_t c, 
     }
 }
 template <int D>
-__device__ __forceinline__ void store_vec(double *__restrict__ evec, int64_t c, const double (&b)[D + 1]) {
+__device__ __forceinline__ void store_vec(const mp_mesh &m, double *__restrict__ evec, int64_t c, const double (&b)[D + 1]) {
+    if (m.d_row_pos) {
+#pragma unroll
+        for (int i = 0; i <= D; ++i) {
+            const int32_t e = m.d_row_pos[c * (D + 1) + i];
+            if (e >= 0) evec[e] = b[i];
+        }
+        return;
+    }
     double *dst = evec + c * (D + 1);
     if (D == 3) {
         reinterpret_cast<double2 *>(dst)[0] = make_double2(b[0], b[1]);
@@ -232,7 +256,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_mass(mp_mesh m, double scale, d
     for (int i = 0; i <= D; ++i)
 #pragma unroll
         for (int j = 0; j <= D; ++j) A[i][j] = (i == j) ? 2.0 * w : w;
-    store_mat<D>(emat, c, A);
+    store_mat<D>(m, emat, c, A);
 }
 
 template <int D>
@@ -253,7 +277,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_stiffness(mp_mesh m, const doub
             for (int a = 0; a < D; ++a) s += G.g[i][a] * G.g[j][a];
             A[i][j] = w * s;
         }
-    store_mat<D>(emat, c, A);
+    store_mat<D>(m, emat, c, A);
 }
 
 // c1 / c2 rows: qc*(cc-c0)*dx + dt*f21/(1-phi)*qc*dx ; qc1*(cc1-c1)*dx - dt*f31/(1-phi)*qc1*dx
@@ -275,7 +299,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_reaction_rhs(mp_mesh m, mp_tran
     const double k2 = P.dt * P.frac[1] * P.Da / (1.0 - P.phi);
 #pragma unroll
     for (int i = 0; i <= D; ++i) b[i] = G.vol * (Coef<D>::c2 * (S1 + a1[i]) - k2 * Ti[i]);
-    store_vec<D>(eb1, c, b);
+    store_vec<D>(m, eb1, c, b);
     if (P.ncomp == 3 && eb2) {
         double a2[D + 1];
         gather<D>(c2n, G, a2);
@@ -283,7 +307,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_reaction_rhs(mp_mesh m, mp_tran
         const double k3 = P.dt * P.frac[2] * P.Da / (1.0 - P.phi);
 #pragma unroll
         for (int i = 0; i <= D; ++i) b[i] = G.vol * (Coef<D>::c2 * (S2 + a2[i]) + k3 * Ti[i]);
-        store_vec<D>(eb2, c, b);
+        store_vec<D>(m, eb2, c, b);
     }
 }
 
@@ -326,7 +350,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport(mp_mesh m, mp_transpo
                 A[i][j] = vol * Coef<D>::c2 * (i == j ? 2.0 : 1.0) + 0.5 * dt * m1 * ug[j] + 0.5 * dt / P.Pe * vol * gg +
                           tau * ug[i] * m1 + 0.5 * dt * tau * vol * ug[i] * ug[j];
             }
-        store_mat<D>(emat, c, A);
+        store_mat<D>(m, emat, c, A);
     }
     if (evec) {
         double a0[D + 1], a1[D + 1], f[D + 1], Ti[D + 1], meanR;
@@ -370,7 +394,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport(mp_mesh m, mp_transpo
             const double gal = Coef<D>::c2 * (S0 + a0[i]) - 0.5 * dt * ugc0 * inv - kR1 * Ti[i] + P.beta * dt * Coef<D>::c2 * (Sf + f[i]);
             b[i] = vol * (gal - 0.5 * dt / P.Pe * gg - tau * ug[i] * (rk + cpl));
         }
-        store_vec<D>(evec, c, b);
+        store_vec<D>(m, evec, c, b);
     }
 }
 
@@ -408,7 +432,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_adr_single(mp_mesh m, double Pe
                 A[i][j] = vol * Coef<D>::c2 * (i == j ? 2.0 : 1.0) + 0.5 * dt * m1 * ug[j] + 0.5 * dt / Pe * vol * gg +
                           tau * ug[i] * m1 + 0.5 * dt * tau * vol * ug[i] * ug[j];
             }
-        store_mat<D>(emat, c, A);
+        store_mat<D>(m, emat, c, A);
     }
     if (evec) {
         double a0[D + 1];
@@ -432,7 +456,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_adr_single(mp_mesh m, double Pe
             for (int a = 0; a < D; ++a) gg += G.g[i][a] * gc[a];
             b[i] = vol * (Coef<D>::c2 * (S0 + a0[i]) * (1.0 - dt * Da) - 0.5 * dt * ugc * inv - 0.5 * dt / Pe * gg - tau * ug[i] * rk);
         }
-        store_vec<D>(evec, c, b);
+        store_vec<D>(m, evec, c, b);
     }
 }
 
@@ -455,7 +479,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_pressure_rhs(mp_mesh m, mp_tran
         for (int a = 0; a < D; ++a) s += P.zhat[a] * G.g[i][a];
         b[i] = w * s;
     }
-    store_vec<D>(evec, c, b);
+    store_vec<D>(m, evec, c, b);
 }
 
 // u = -(K/phi)(grad p + sigma rho zhat): DarcyAdvection (sigma=-1) gives u = -k(grad p - drho zhat)/phi (mupopp.py:563)
@@ -689,8 +713,8 @@ __global__ void __launch_bounds__(kThreads) k_p1_transport_quad(mp_mesh m, mp_tr
             }
         }
     }
-    if (emat) store_mat<D>(emat, c, A);
-    if (evec) store_vec<D>(evec, c, b);
+    if (emat) store_mat<D>(m, emat, c, A);
+    if (evec) store_vec<D>(m, evec, c, b);
 }
 
 
@@ -750,7 +774,7 @@ __global__ void __launch_bounds__(kThreads) k_p1_mass_fn(mp_mesh m, QuadView Q, 
 #pragma unroll
             for (int j = 0; j <= D; ++j) A[i][j] += w * lam[i] * lam[j];
     }
-    store_mat<D>(emat, c, A);
+    store_mat<D>(m, emat, c, A);
 }
 
 // rhs of the momentum form (mupopp.py:356-357, 374-375):  evec_u[a][c][i] = -int h_a psi_i,  evec_p[c][i] = -int da R buoy gam/(1 - R buoy) lambda_i
@@ -812,7 +836,7 @@ __global__ void __launch_bounds__(kThreads) k_compaction_rhs(mp_mesh m, QuadView
     for (int a = 0; a < D; ++a)
 #pragma unroll
         for (int i = 0; i < NB2; ++i) dst[a][c * NB2 + i] = bvec[a][i];
-    store_vec<D>(evp, c, bp);
+    store_vec<D>(m, evp, c, bp);
 }
 
 // porosity row (compaction.mass_conservation, mupopp.py:217-259) with a P1 porosity and a P2 velocity:
@@ -899,8 +923,8 @@ __global__ void __launch_bounds__(kThreads) k_p1_porosity_quad(mp_mesh m, QuadVi
             for (int i = 0; i <= D; ++i) b[i] += w * (lam[i] * gal - st * ug[i] * rk);
         }
     }
-    if (emat) store_mat<D>(emat, c, A);
-    if (evec) store_vec<D>(evec, c, b);
+    if (emat) store_mat<D>(m, emat, c, A);
+    if (evec) store_vec<D>(m, evec, c, b);
 }
 
 // Symmetric Dirichlet elimination, 8 lanes per row, fixed reduction order.

@@ -16,7 +16,8 @@ struct mp_plan {
     int32_t *d_colidx = nullptr;
     int32_t *d_inc_ptr = nullptr;  // [nrow+1]
     int32_t *d_inc = nullptr;      // [ninc]  id = cell*lr + li, ascending per row
-    uint16_t *d_slot = nullptr;    // [ncell*lr*lc] offset of (row(cell,li), col(cell,j)) inside its CSR row
+    uint16_t *d_slot = nullptr;    // [ninc*lc] (incidence order) offset of (row(cell,li), col(cell,j)) inside its CSR row
+    int32_t *d_pos = nullptr;      // [ncell*lr] incidence index of (cell,li), -1 if the row is not assembled
     int64_t ninc = 0;
     int32_t *d_sell_ptr = nullptr; // [nslice+1] SELL-32 slice offsets (entries)
     int32_t *d_sell_col = nullptr; // [nsell]
@@ -64,27 +65,31 @@ __global__ void k_unpack_unique(const uint64_t *__restrict__ ukeys, int64_t nu, 
     atomicAdd(&rowcnt[k / (uint64_t)ncol], 1);
 }
 
-__global__ void k_slots(const int32_t *__restrict__ row_dofs, const int32_t *__restrict__ col_dofs, int lr, int lc,
-                        int64_t ncell, int32_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
-                        uint16_t *slot) {
-    int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (t >= ncell * lr) return;
-    int64_t cell = t / lr;
-    int32_t r = row_dofs[t];
-    if (r < 0 || r >= nrow) {
-        for (int j = 0; j < lc; ++j) slot[t * lc + j] = 0xffff;
-        return;
-    }
-    int32_t b = rowptr[r], e = rowptr[r + 1];
+// slot map in INCIDENCE order (thread per incidence entry): the scatter kernels then stream it
+__global__ void k_slots(const int32_t *__restrict__ inc, int64_t ninc, const int32_t *__restrict__ row_dofs,
+                        const int32_t *__restrict__ col_dofs, int lr, int lc, const int32_t *__restrict__ rowptr,
+                        const int32_t *__restrict__ colidx, uint16_t *slot, int32_t *pos) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= ninc) return;
+    const int32_t id = inc[e];
+    const int64_t cell = id / lr;
+    const int32_t r = row_dofs[id];
+    pos[id] = (int32_t)e;
+    const int32_t b = rowptr[r], en = rowptr[r + 1];
     for (int j = 0; j < lc; ++j) {
-        int32_t c = col_dofs[cell * lc + j];
-        int32_t lo = b, hi = e;
+        const int32_t c = col_dofs[cell * lc + j];
+        int32_t lo = b, hi = en;
         while (lo < hi) {  // lower_bound
-            int32_t mid = (lo + hi) >> 1;
+            const int32_t mid = (lo + hi) >> 1;
             if (colidx[mid] < c) lo = mid + 1; else hi = mid;
         }
-        slot[t * lc + j] = (lo < e && colidx[lo] == c) ? (uint16_t)(lo - b) : (uint16_t)0xffff;
+        slot[e * lc + j] = (lo < en && colidx[lo] == c) ? (uint16_t)(lo - b) : (uint16_t)0xffff;
     }
+}
+
+__global__ void k_inc_pos(const int32_t *__restrict__ inc, int64_t ninc, int32_t *pos) {
+    int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e < ninc) pos[inc[e]] = (int32_t)e;
 }
 
 __global__ void k_max_rowlen(const int32_t *__restrict__ rowptr, int32_t nrow, int *out) {
@@ -125,7 +130,7 @@ __global__ void k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *_
 
 // One CTA owns a contiguous block of rows; its CSR value segment is accumulated in shared memory
 // (each thread owns one row => no conflicts, fixed summation order) and written back coalesced.
-template <int LC>
+template <int LC, bool ORDERED>
 __global__ void __launch_bounds__(kThreads)
 k_scatter_matrix(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc,
                  const uint16_t *__restrict__ slot, const double *__restrict__ emat, double *__restrict__ vals,
@@ -142,9 +147,9 @@ k_scatter_matrix(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
         double *row = sm + (rowptr[r] - base);
         int32_t e0 = inc_ptr[r], e1 = inc_ptr[r + 1];
         for (int32_t e = e0; e < e1; ++e) {
-            int64_t id = inc[e];
+            const int64_t id = ORDERED ? (int64_t)e : (int64_t)inc[e];
             const double *src = emat + id * lc;
-            const uint16_t *sl = slot + id * lc;
+            const uint16_t *sl = slot + (int64_t)e * lc;
             if (LC == 4) {
                 const double2 a = *reinterpret_cast<const double2 *>(src);
                 const double2 b = *reinterpret_cast<const double2 *>(src + 2);
@@ -166,6 +171,36 @@ k_scatter_matrix(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
     for (int k = threadIdx.x; k < seg; k += blockDim.x) vals[base + k] = sm[k];
 }
 
+
+// LC == 4 (P1 tets), row-ordered input: FOUR lanes per row, lane j owns column j of every incident local row.  A quad reads one
+// contiguous 32-byte element row and one 8-byte slot quadruple per step (8 rows -> 8 sectors per warp instruction instead of 32
+// scattered lines with a thread per row); per CSR slot the summation order is still ascending incidence index => same bits.
+__global__ void __launch_bounds__(kThreads)
+k_scatter_matrix_quad(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ inc_ptr, const uint16_t *__restrict__ slot,
+                      const double *__restrict__ emat, double *__restrict__ vals, int32_t nrow, int rows_per_block) {
+    extern __shared__ double sm[];
+    const int32_t r0 = blockIdx.x * rows_per_block;
+    const int32_t r1 = min(r0 + rows_per_block, nrow);
+    const int32_t base = rowptr[r0];
+    const int32_t seg = rowptr[r1] - base;
+    for (int k = threadIdx.x; k < seg; k += blockDim.x) sm[k] = 0.0;
+    __syncthreads();
+    const int j = threadIdx.x & 3;
+    for (int32_t r = r0 + (threadIdx.x >> 2); r < r1; r += (blockDim.x >> 2)) {
+        double *row = sm + (rowptr[r] - base);
+        const int32_t e0 = inc_ptr[r], e1 = inc_ptr[r + 1];
+#pragma unroll 4
+        for (int32_t e = e0; e < e1; ++e) {
+            const double v = emat[(int64_t)e * 4 + j];
+            const uint16_t s = slot[(int64_t)e * 4 + j];
+            if (s != 0xffff) row[s] += v;
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < seg; k += blockDim.x) vals[base + k] = sm[k];
+}
+
+template <bool ORDERED>
 __global__ void __launch_bounds__(kThreads)
 k_scatter_vector(const int32_t *__restrict__ inc_ptr, const int32_t *__restrict__ inc, const double *__restrict__ evec,
                  double beta, double *__restrict__ out, int32_t nrow) {
@@ -173,7 +208,7 @@ k_scatter_vector(const int32_t *__restrict__ inc_ptr, const int32_t *__restrict_
     if (r >= nrow) return;
     int32_t e0 = inc_ptr[r], e1 = inc_ptr[r + 1];
     double s = 0.0;
-    for (int32_t e = e0; e < e1; ++e) s += evec[inc[e]];
+    for (int32_t e = e0; e < e1; ++e) s += evec[ORDERED ? e : inc[e]];
     out[r] = (beta == 0.0) ? s : beta * out[r] + s;
 }
 
@@ -182,7 +217,7 @@ k_scatter_vector(const int32_t *__restrict__ inc_ptr, const int32_t *__restrict_
 extern "C" int mp_plan_destroy(mp_plan *p) {
     if (!p) return 0;
     cudaFree(p->d_rowptr); cudaFree(p->d_colidx); cudaFree(p->d_inc_ptr); cudaFree(p->d_inc); cudaFree(p->d_slot);
-    cudaFree(p->d_sell_ptr); cudaFree(p->d_sell_col);
+    cudaFree(p->d_sell_ptr); cudaFree(p->d_sell_col); cudaFree(p->d_pos);
     delete p;
     return 0;
 }
@@ -258,6 +293,12 @@ extern "C" int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr
     PC(cudaStreamSynchronize(st));
     cudaFree(keys); cudaFree(keys2); cudaFree(ids); cudaFree(ids2); cudaFree(cnt);
     keys = keys2 = ids = ids2 = cnt = nullptr;
+    PC(cudaMalloc(&p->d_pos, sizeof(int32_t) * (size_t)(ninc_all > 0 ? ninc_all : 1)));
+    PC(cudaMemsetAsync(p->d_pos, 0xff, sizeof(int32_t) * (size_t)(ninc_all > 0 ? ninc_all : 1), st));   // -1
+    if (ninc > 0) {
+        k_inc_pos<<<(unsigned)cdiv(ninc, kThreads), kThreads, 0, st>>>(p->d_inc, ninc, p->d_pos);
+        mp::count_launch(ctx);
+    }
 
     // ---- 2. CSR pattern: sort 64-bit (row,col) keys of every local entry, unique
     if (lc > 0) {
@@ -311,10 +352,10 @@ extern "C" int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr
         }
         cudaFree(uk); uk = nullptr;
         // ---- 3. slot map + row-block tiling of the scatter kernel
-        PC(cudaMalloc(&p->d_slot, sizeof(uint16_t) * (size_t)(nkeys > 0 ? nkeys : 1)));
-        if (ninc_all > 0) {
-            k_slots<<<(unsigned)cdiv(ninc_all, kThreads), kThreads, 0, st>>>(d_row_dofs, d_col_dofs, lr, lc, ncell, (int32_t)nrow,
-                                                                             p->d_rowptr, p->d_colidx, p->d_slot);
+        PC(cudaMalloc(&p->d_slot, sizeof(uint16_t) * (size_t)(ninc > 0 ? (int64_t)ninc * lc : 1)));
+        if (ninc > 0) {
+            k_slots<<<(unsigned)cdiv(ninc, kThreads), kThreads, 0, st>>>(p->d_inc, ninc, d_row_dofs, d_col_dofs, lr, lc, p->d_rowptr,
+                                                                         p->d_colidx, p->d_slot, p->d_pos);
             mp::count_launch(ctx);
         }
         PC(cudaMalloc(&d_max, sizeof(int)));
@@ -372,32 +413,59 @@ extern "C" int mp_plan_export_csr(mp_ctx *ctx, const mp_plan *p, int32_t *d_rowp
     return 0;
 }
 
-extern "C" int mp_scatter_matrix(mp_ctx *ctx, const mp_plan *p, const double *d_elem_mat, double *d_vals) {
+static int scatter_matrix_impl(mp_ctx *ctx, const mp_plan *p, const double *d_elem_mat, double *d_vals, bool ordered) {
     MP_CHECK(ctx && p && p->lc > 0 && d_elem_mat && d_vals, "mp_scatter_matrix: bad argument");
     if (p->nnz == 0) return 0;
     size_t smem = sizeof(double) * (size_t)p->smem_doubles;
     unsigned grid = (unsigned)cdiv(p->nrow, p->rows_per_block);
     const int kThreadsRt = p->rows_per_block >= kThreads ? kThreads : ((p->rows_per_block + 31) / 32) * 32;
-    if (p->lc == 4) {
-        MP_CUDA(cudaFuncSetAttribute(k_scatter_matrix<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_scatter_matrix<4><<<grid, kThreadsRt, smem, ctx->stream>>>(p->d_rowptr, p->d_inc_ptr, p->d_inc, p->d_slot, d_elem_mat,
-                                                                    d_vals, (int32_t)p->nrow, p->rows_per_block, p->lc);
-    } else {
-        MP_CUDA(cudaFuncSetAttribute(k_scatter_matrix<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_scatter_matrix<0><<<grid, kThreadsRt, smem, ctx->stream>>>(p->d_rowptr, p->d_inc_ptr, p->d_inc, p->d_slot, d_elem_mat,
-                                                                    d_vals, (int32_t)p->nrow, p->rows_per_block, p->lc);
-    }
+#define LAUNCH_SM(LC_, ORD_)                                                                                                          \
+    do {                                                                                                                              \
+        MP_CUDA(cudaFuncSetAttribute(k_scatter_matrix<LC_, ORD_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));           \
+        k_scatter_matrix<LC_, ORD_><<<grid, kThreadsRt, smem, ctx->stream>>>(p->d_rowptr, p->d_inc_ptr, p->d_inc, p->d_slot, d_elem_mat, \
+                                                                              d_vals, (int32_t)p->nrow, p->rows_per_block, p->lc);    \
+    } while (0)
+    if (p->lc == 4 && ordered) {
+        MP_CUDA(cudaFuncSetAttribute(k_scatter_matrix_quad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_scatter_matrix_quad<<<grid, kThreads, smem, ctx->stream>>>(p->d_rowptr, p->d_inc_ptr, p->d_slot, d_elem_mat, d_vals,
+                                                                      (int32_t)p->nrow, p->rows_per_block);
+    } else if (p->lc == 4) { LAUNCH_SM(4, false); }
+    else { if (ordered) LAUNCH_SM(0, true); else LAUNCH_SM(0, false); }
+#undef LAUNCH_SM
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp_scatter_matrix(mp_ctx *ctx, const mp_plan *p, const double *d_elem_mat, double *d_vals) {
+    return scatter_matrix_impl(ctx, p, d_elem_mat, d_vals, false);
+}
+
+extern "C" int mp_scatter_matrix_ordered(mp_ctx *ctx, const mp_plan *p, const double *d_elem_mat, double *d_vals) {
+    return scatter_matrix_impl(ctx, p, d_elem_mat, d_vals, true);
+}
+
+static int scatter_vector_impl(mp_ctx *ctx, const mp_plan *p, const double *d_elem_vec, double beta, double *d_out, bool ordered) {
+    MP_CHECK(ctx && p && d_elem_vec && d_out, "mp_scatter_vector: bad argument");
+    const unsigned grid = (unsigned)cdiv(p->nrow, kThreads);
+    if (ordered) k_scatter_vector<true><<<grid, kThreads, 0, ctx->stream>>>(p->d_inc_ptr, p->d_inc, d_elem_vec, beta, d_out, (int32_t)p->nrow);
+    else k_scatter_vector<false><<<grid, kThreads, 0, ctx->stream>>>(p->d_inc_ptr, p->d_inc, d_elem_vec, beta, d_out, (int32_t)p->nrow);
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
     return 0;
 }
 
 extern "C" int mp_scatter_vector(mp_ctx *ctx, const mp_plan *p, const double *d_elem_vec, double beta, double *d_out) {
-    MP_CHECK(ctx && p && d_elem_vec && d_out, "mp_scatter_vector: bad argument");
-    k_scatter_vector<<<(unsigned)cdiv(p->nrow, kThreads), kThreads, 0, ctx->stream>>>(p->d_inc_ptr, p->d_inc, d_elem_vec, beta,
-                                                                                       d_out, (int32_t)p->nrow);
-    mp::count_launch(ctx);
-    MP_CUDA(cudaGetLastError());
+    return scatter_vector_impl(ctx, p, d_elem_vec, beta, d_out, false);
+}
+
+extern "C" int mp_scatter_vector_ordered(mp_ctx *ctx, const mp_plan *p, const double *d_elem_vec, double beta, double *d_out) {
+    return scatter_vector_impl(ctx, p, d_elem_vec, beta, d_out, true);
+}
+
+extern "C" int mp_plan_row_positions(const mp_plan *p, const int32_t **d_pos) {
+    MP_CHECK(p && d_pos && p->d_pos, "mp_plan_row_positions: bad argument");
+    *d_pos = p->d_pos;
     return 0;
 }
 

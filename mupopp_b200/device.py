@@ -113,7 +113,15 @@ class DeviceMesh:
             self.cell_dofs = ctx.to_device(np.ascontiguousarray(v2d[mesh.cells]), torch.int32)
             self.ndof = int(v2d.max()) + 1
             dp = self.cell_dofs.data_ptr()
-        self.c = MpMesh(self.dim, self.ncell, self.nvert, self.cells.data_ptr(), self.coords.data_ptr(), dp)
+        self.c = MpMesh(self.dim, self.ncell, self.nvert, self.cells.data_ptr(), self.coords.data_ptr(), dp, None)
+
+    def use_row_ordered_storage(self, plan):
+        """Make the P1 element kernels write their output in the row order of `plan` (a P1xP1 plan of this mesh's dofmap), so
+        that the scatter kernels stream it.  Every element tensor produced with this mesh must then be scattered through `plan`."""
+        pos = C.c_void_p()
+        check(self.ctx.lib.mp_plan_row_positions(plan.h, C.byref(pos)), "mp_plan_row_positions")
+        self.c.d_row_pos = pos.value
+        plan.ordered = True
 
 
 class Plan:
@@ -130,6 +138,7 @@ class Plan:
         check(ctx.lib.mp_plan_create(ctx.h, ptr(row_dofs), self.lr, ptr(col_dofs), self.lc, ncell, nrow, ncol, C.byref(h)),
               "mp_plan_create")
         self.h = h
+        self.ordered = False
         self.nnz = int(ctx.lib.mp_plan_nnz(h)) if self.lc else 0
         self.max_row_nnz = int(ctx.lib.mp_plan_max_row_nnz(h)) if self.lc else 0
         self._csr = None
@@ -161,11 +170,13 @@ class Plan:
                          plan=self if sell else None)
 
     def scatter_matrix(self, elem_mat, A):
-        check(self.ctx.lib.mp_scatter_matrix(self.ctx.h, self.h, ptr(elem_mat), ptr(A.vals)), "mp_scatter_matrix")
+        fn = self.ctx.lib.mp_scatter_matrix_ordered if self.ordered else self.ctx.lib.mp_scatter_matrix
+        check(fn(self.ctx.h, self.h, ptr(elem_mat), ptr(A.vals)), "mp_scatter_matrix")
         A.sell_dirty = True
 
     def scatter_vector(self, elem_vec, out, beta=0.0):
-        check(self.ctx.lib.mp_scatter_vector(self.ctx.h, self.h, ptr(elem_vec), beta, ptr(out)), "mp_scatter_vector")
+        fn = self.ctx.lib.mp_scatter_vector_ordered if self.ordered else self.ctx.lib.mp_scatter_vector
+        check(fn(self.ctx.h, self.h, ptr(elem_vec), beta, ptr(out)), "mp_scatter_vector")
 
 
 class CsrMatrix:

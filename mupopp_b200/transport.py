@@ -128,8 +128,8 @@ class TransportSolverF:
     """GPU state + operators of one mode-F problem.  Fields are torch fp64 tensors on the device."""
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
-                 rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="gmres", gmres_restart=50,
-                 vert2dof=None):
+                 rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
+                 vert2dof=None, row_ordered=True):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
@@ -146,6 +146,8 @@ class TransportSolverF:
         if self.nown < V:
             rows = torch.where(rows < self.nown, rows, torch.full_like(rows, -1))
         self.plan = Plan(ctx, rows, self.dm.cell_dofs, self.nown, V)
+        if row_ordered:
+            self.dm.use_row_ordered_storage(self.plan)      # element kernels write in row order, the scatter streams
         l = d + 1
         self.emat = ctx.empty(Cn * l * l)
         self.evec = ctx.empty(Cn * l)
@@ -190,6 +192,27 @@ class TransportSolverF:
         if self.halo is not None:
             self.halo.exchange(x)
 
+    def _solve_c0(self, kw):
+        """Non-symmetric SUPG row: Jacobi-BiCGStab (2 SpMV + 3 fused vector kernels per iteration; 0.77 ms at 200^3 against
+        1.85 ms for a GMRES(50) iteration) with restarted GMRES as the safeguard when BiCGStab breaks down or stagnates
+        (it does on strongly non-normal rows, e.g. CFL ~ 400 with natural side walls).  The decision uses the allreduced
+        residual, so every rank takes the same branch."""
+        from ._lib import MpError
+        if self.c0_method == "gmres":
+            return self.A.solve("gmres", self.rhs, self.c0_new, restart=self.gmres_restart, **kw)
+        kb = dict(kw)
+        kb["maxit"] = min(kw["maxit"], 1000)
+        try:
+            r0 = self.A.solve("bicgstab", self.rhs, self.c0_new, **kb)
+            if r0.converged:
+                return r0
+        except MpError as e:
+            if "NaN" not in str(e):
+                raise
+        self.c0_new.copy_(self.c0)
+        self.fallbacks = getattr(self, "fallbacks", 0) + 1
+        return self.A.solve("gmres", self.rhs, self.c0_new, restart=max(self.gmres_restart, 100), **kw)   # long recurrences: robust
+
     def step(self):
         ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
         three = self.model.ncomp == 3
@@ -216,7 +239,7 @@ class TransportSolverF:
         self.A.apply_dirichlet(self.rhs, self.c0_isbc, self.c0_g)
         self.A.jacobi_setup()
         self.c0_new.copy_(self.c0)
-        r0 = self.A.solve(self.c0_method, self.rhs, self.c0_new, restart=self.gmres_restart, **kw)
+        r0 = self._solve_c0(kw)
         self._exchange(self.c0_new)
         # 3. pressure with the NEW c0, warm start from p^n
         check(lib.mp_elem_p1_pressure_rhs(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.c0_new), ptr(self.evec)),

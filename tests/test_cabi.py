@@ -51,7 +51,7 @@ def test_struct_sizes_match_header():
     """ctypes mirrors of the header structs (layout is what crosses the boundary)."""
     import ctypes as C
     from mupopp_b200 import _lib
-    assert C.sizeof(_lib.MpMesh) == 48
+    assert C.sizeof(_lib.MpMesh) == 56
     assert C.sizeof(_lib.MpTransportParams) == 8 * 15 + 16
     assert C.sizeof(_lib.MpCsr) == 80
     assert C.sizeof(_lib.MpSolveInfo) == 40

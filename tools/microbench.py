@@ -64,6 +64,18 @@ def main():
     rep("elem_p1_transport (mat+rhs)", ms, 16.0 * Cn + 24.0 * N + 24.0 * Cn + 6 * 8.0 * N + 160.0 * Cn)
     ms = timeit(lambda: plan.scatter_vector(evec, y))
     rep("scatter_vector", ms, 32.0 * Cn + 8.0 * N + 16.0 * Cn)
+    # row-ordered element storage (what TransportSolverF uses): element kernels write in row order, the scatter streams
+    dm.use_row_ordered_storage(plan)
+    ms = timeit(lambda: check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(dm.c), None, 1.0, 20.0, ptr(emat))))
+    rep("elem_p1_stiffness (row-ordered)", ms, 16.0 * Cn + 24.0 * N + 128.0 * Cn + 16.0 * Cn)
+    ms = timeit(lambda: plan.scatter_matrix(emat, A))
+    rep("scatter_matrix (row-ordered)", ms, 128.0 * Cn + 8.0 * nnz + 2.0 * 16 * Cn)
+    ms = timeit(lambda: check(ctx.lib.mp_elem_p1_transport(ctx.h, C.byref(dm.c), C.byref(prm), ptr(u), ptr(x), ptr(z), ptr(x), ptr(z), ptr(x), ptr(z), ptr(emat), ptr(evec))))
+    rep("elem_p1_transport (row-ordered)", ms, 16.0 * Cn + 24.0 * N + 24.0 * Cn + 6 * 8.0 * N + 160.0 * Cn + 16.0 * Cn)
+    ms = timeit(lambda: plan.scatter_vector(evec, y))
+    rep("scatter_vector (row-ordered)", ms, 32.0 * Cn + 8.0 * N)
+    check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(dm.c), None, 1.0, 20.0, ptr(emat)))
+    plan.scatter_matrix(emat, A)
     spmv_bytes = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N
     for var, name in ((2, "spmv CSR sub-warp/row"), (1, "spmv CSR CTA-stream"), (3, "spmv CSR warp-stream"), (0, "spmv SELL-32")):
         ctx.set_option("spmv_variant", var)
