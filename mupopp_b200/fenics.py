@@ -82,6 +82,72 @@ def BoxMesh(p0, p1, nx, ny, nz):
     return _mesh.BoxMesh(p0, p1, nx, ny, nz)
 
 
+def Mesh(source, cells=None):
+    """dolfin.Mesh: from a DOLFIN-XML file (optionally .gz; triangles or tetrahedra) as in
+    /root/reference/src/run/fenics_demo/demo_advection-diffusion.py:33, or from (coords, cells) arrays."""
+    if cells is not None:
+        return _mesh.Mesh(source, cells)
+    import gzip
+    import re
+    op = gzip.open if str(source).endswith(".gz") else open
+    with op(source, "rt") as f:
+        txt = f.read()
+    vs = re.findall(r'<vertex index="(\d+)" x="([^"]+)" y="([^"]+)"(?: z="([^"]+)")?', txt)
+    dim = 3 if 'celltype="tetrahedron"' in txt else 2
+    coords = np.zeros((len(vs), dim))
+    for i, x, y, z in vs:
+        coords[int(i), 0], coords[int(i), 1] = float(x), float(y)
+        if dim == 3:
+            coords[int(i), 2] = float(z)
+    if dim == 2:
+        cs = re.findall(r'<triangle index="(\d+)" v0="(\d+)" v1="(\d+)" v2="(\d+)"', txt)
+    else:
+        cs = re.findall(r'<tetrahedron index="(\d+)" v0="(\d+)" v1="(\d+)" v2="(\d+)" v3="(\d+)"', txt)
+    cl = np.zeros((len(cs), dim + 1), dtype=np.int32)
+    for row in cs:
+        cl[int(row[0])] = [int(v) for v in row[1:]]
+    return _mesh.Mesh(coords, np.sort(cl, axis=1))
+
+
+class MeshFunction:
+    """Facet markers: MeshFunction("size_t", mesh, file) for a DOLFIN-XML mesh_value_collection
+    (run/fenics_demo/dolfin_fine_subdomains.xml.gz), or built from an (n,3) array of (cell, local facet, value)."""
+
+    def __init__(self, kind, mesh, source=None, dim=None):
+        self.mesh = mesh
+        if isinstance(source, np.ndarray):
+            self.entries = np.asarray(source, dtype=np.int64)
+        elif source is not None and not isinstance(source, int):
+            import gzip
+            import re
+            op = gzip.open if str(source).endswith(".gz") else open
+            with op(source, "rt") as f:
+                txt = f.read()
+            rows = re.findall(r'<value cell_index="(\d+)" local_entity="(\d+)" value="(\d+)"', txt)
+            self.entries = np.array([[int(a), int(b), int(c)] for a, b, c in rows], dtype=np.int64)
+        else:
+            self.entries = np.zeros((0, 3), dtype=np.int64)
+
+    def facets_with(self, value):
+        e = self.entries[self.entries[:, 2] == value]
+        return e[:, 0], e[:, 1]
+
+
+def read_function_xml(path, f):
+    """`File(path) >> f` for DOLFIN-XML function data (rows `dof index, value`): UFC block numbering is assumed, which is what the
+    reference's fixture uses (tests/test_oracle_golden.py pins it)."""
+    import gzip
+    import re
+    op = gzip.open if str(path).endswith(".gz") else open
+    with op(path, "rt") as fh:
+        txt = fh.read()
+    rows = re.findall(r'<dof index="(\d+)" value="([^"]+)"', txt)
+    vals = np.zeros(len(rows))
+    for i, v in rows:
+        vals[int(i)] = float(v)
+    f.vector().set_local(vals)
+
+
 class Rectangle:
     def __init__(self, p0, p1):
         self.p0, self.p1 = p0, p1
@@ -406,8 +472,10 @@ class DirichletBC:
     """DirichletBC(V | V.sub(i)[.sub(c)], value, marker): 'topological' marking -- a boundary facet is constrained when the
     marker holds at all its vertices and its midpoint; every dof on it (vertices, and edge midpoints for P2) is set."""
 
-    def __init__(self, V, value, marker, method="topological"):
-        self.V, self.value, self.marker = V, value, marker
+    def __init__(self, V, value, marker, sub_id=None, method="topological"):
+        """marker: callable x[, on_boundary] -> bool, or a MeshFunction of facet markers together with `sub_id`
+        (DirichletBC(Q, g, sub_domains, 1), demo_advection-diffusion.py:79; master_advective_stokes.py:119-130)."""
+        self.V, self.value, self.marker, self.sub_id = V, value, marker, sub_id
         if isinstance(V, _SubSpace):
             self.space, self.block_ids = V.parent, V.block_ids()
         else:
@@ -423,16 +491,21 @@ class DirichletBC:
         """-> {block id: (dof indices, values)} in the block's own numbering."""
         mesh = self.space.mesh
         d = mesh.dim
-        fv, nrm, meas, owner = mesh.boundary_facets()
-        oloc = mesh.boundary_facet_local_index()
         vx = mesh.coords
-        bverts = np.unique(fv.ravel())
-        vin = np.zeros(mesh.num_vertices(), dtype=bool)
-        vin[bverts] = [self._mark(vx[i]) for i in bverts]
-        inside = vin[fv].all(1)
-        for f in np.nonzero(inside)[0]:
-            inside[f] = self._mark(vx[fv[f]].mean(0))
-        marked = np.nonzero(inside)[0]
+        if isinstance(self.marker, MeshFunction):
+            owner, oloc = self.marker.facets_with(self.sub_id)
+            fv = np.array([[mesh.cells[c][j] for j in range(d + 1) if j != k] for c, k in zip(owner, oloc)], dtype=np.int64).reshape(-1, d)
+            marked = np.arange(len(owner))
+        else:
+            fv, nrm, meas, owner = mesh.boundary_facets()
+            oloc = mesh.boundary_facet_local_index()
+            bverts = np.unique(fv.ravel())
+            vin = np.zeros(mesh.num_vertices(), dtype=bool)
+            vin[bverts] = [self._mark(vx[i]) for i in bverts]
+            inside = vin[fv].all(1)
+            for f in np.nonzero(inside)[0]:
+                inside[f] = self._mark(vx[fv[f]].mean(0))
+            marked = np.nonzero(inside)[0]
         degree = self.space.blocks[self.block_ids[0]][0]
         ncomp = len(self.block_ids)
         # collect (dof, point, owning cell, local facet) over marked facets, first occurrence wins
@@ -504,6 +577,10 @@ class File:
 
     def __init__(self, name, *a):
         self.name, self.count = name, 0
+
+    def __rshift__(self, f):
+        read_function_xml(self.name, f)
+        return self
 
     def __lshift__(self, f):
         import os

@@ -124,3 +124,47 @@ def test_modef_mass_balance_and_direct_vs_krylov():
     free = np.ones(n1, bool)
     free[bcs.p_dofs] = False
     assert np.abs(res[free]).max() < 1e-12
+
+
+def test_two_component_adaptive_reduces_to_plain_supg_without_reaction():
+    """a6 (mupopp.py:667-749) with Da = 0 and alpha = 0: c1 is frozen and the c0 row is the Sendur-SUPG CN advection-diffusion row."""
+    m = fem.rectangle_mesh(0, 0, 2, 1, 6, 5)
+    asm = forms.Assembler(m)
+    n2 = asm.P2.ndof
+    vel = ("P2", [0.4 * np.ones(n2), -0.3 * np.ones(n2)])
+    prm = forms.two_component_adaptive_params(100.0, 0.0, 0.01, 0.0, 0.05)
+    rng = np.random.default_rng(3)
+    c0n, c1n = 0.1 * rng.random(m.nv), 0.2 + 0.1 * rng.random(m.nv)
+    c0, c1 = forms.two_component_adaptive_step(asm, prm, vel, c0n, c1n, forms.adaptive_source(m.coords), np.zeros(0, dtype=np.int64), np.zeros(0))
+    assert rel(c1, c1n) < 1e-13
+    # a constant c0 stays constant
+    c0, _ = forms.two_component_adaptive_step(asm, prm, vel, 0.3 * np.ones(m.nv), c1n, forms.adaptive_source(m.coords), np.zeros(0, dtype=np.int64), np.zeros(0))
+    assert np.abs(c0 - 0.3).max() < 1e-12
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_stokes_poiseuille_known_answer(dim):
+    """a7: the Stokes block of mupopp.py:1044 with parabolic inflow reproduces plane Poiseuille flow exactly (quadratic u is in P3, linear p in P1)."""
+    from oracle import stokes as os_
+    if dim == 2:
+        m = fem.rectangle_mesh(0, 0, 2, 1, 4, 3)
+    else:
+        m = fem.box_mesh((0, 0, 0), (2, 1, 1), 3, 3, 2)
+    asm = forms.Assembler(m)
+    X3 = asm.P3.dof_coords()
+    n3, n1 = asm.P3.ndof, asm.P1.ndof
+    prof = lambda x: x[:, 1] * (1 - x[:, 1])
+    if dim == 2:
+        D = np.where((X3[:, 0] < 1e-12) | (X3[:, 1] < 1e-12) | (X3[:, 1] > 1 - 1e-12))[0]
+    else:   # channel between the planes y = 0, 1; free-slip is not available, so prescribe the exact profile on the z walls too
+        D = np.where((X3[:, 0] < 1e-12) | (X3[:, 1] < 1e-12) | (X3[:, 1] > 1 - 1e-12) | (X3[:, 2] < 1e-12) | (X3[:, 2] > 1 - 1e-12))[0]
+    g = [np.zeros(n3) for _ in range(dim)]
+    g[0][D] = prof(X3[D])
+    prm = os_.stokes_adr_params(Pe=1.0, Da=0.0, dt=1.0)
+    prev = forms.State(u=[np.zeros(n3)] * dim, p=np.zeros(n1), c0=np.zeros(n1), c1=np.zeros(n1), c2=np.zeros(n1))
+    st = os_.monolithic_step(asm, prm, prev, [D] * dim, [g[a][D] for a in range(dim)], np.zeros(0, dtype=np.int64), np.zeros(0))
+    assert np.abs(st.u[0] - prof(X3)).max() < 1e-10
+    for a in range(1, dim):
+        assert np.abs(st.u[a]).max() < 1e-10
+    # grad(u):grad(v) + div(v) p form: -lap(u) - grad(p) = 0 with u_x = y(1-y) gives dp/dx = +2, p = 0 at the natural outflow x = 2
+    assert np.abs(st.p - 2.0 * (m.coords[:, 0] - 2.0)).max() < 1e-9

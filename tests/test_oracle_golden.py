@@ -60,3 +60,15 @@ def test_golden_function_values_are_p2_consistent(golden):
     v = golden["dof_value"]
     assert np.isfinite(v).all()
     assert v.shape == (22272,)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/src/run/fenics_demo/dolfin_fine.xml.gz"), reason="reference tree not present")
+def test_product_xml_readers_reproduce_the_fixture(golden):
+    """mupopp_b200.fenics.Mesh / MeshFunction read the reference's DOLFIN-XML files (only where /root/reference exists)."""
+    from mupopp_b200 import fenics
+    ref = "/root/reference/src/run/fenics_demo/"
+    m = fenics.Mesh(ref + "dolfin_fine.xml.gz")
+    assert np.array_equal(m.cells, golden["cells"]) and np.allclose(m.coords, golden["coords"], rtol=0, atol=0)
+    mf = fenics.MeshFunction("size_t", m, ref + "dolfin_fine_subdomains.xml.gz")
+    assert np.array_equal(mf.entries, golden["facet_markers"])
+    assert len(m.boundary_facets()[0]) == 296 + 20 + 20

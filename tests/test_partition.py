@@ -90,3 +90,24 @@ def test_halo_plan_gloo(world):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, True) for r in range(world)]
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 4])
+def test_periodic_slabs_match_global_periodic_map(nranks):
+    """Periodic x/y faces: the local dof numbering of every slab maps onto the global periodic dofs."""
+    from mupopp_b200.mesh import box_periodic_map
+    g = mp.BoxMesh(BOX[0], BOX[1], *GRID)
+    pg = box_periodic_map(g, (0, 1))
+    assert pg.ndof == GRID[0] * GRID[1] * (GRID[2] + 1)
+    npl = (GRID[0] + 1) * (GRID[1] + 1)
+    cover = []
+    for r in range(nranks):
+        p = partition.slab_partition(BOX, GRID, r, nranks, periodic_xy=True)
+        k0 = max(p.planes[0] - 1, 0)
+        gv = k0 * npl + np.arange(p.mesh.num_vertices())
+        assert np.array_equal(p.global_ids[p.vert2dof], pg.vert2dof[gv])
+        assert p.n_local == p.vert2dof.max() + 1
+        for (nr, send_idx, rstart, rcount) in p.neigh:
+            assert len(send_idx) == rcount == GRID[0] * GRID[1] and rstart >= p.n_owned
+        cover.append(p.global_ids[: p.n_owned])
+    assert np.array_equal(np.sort(np.concatenate(cover)), np.arange(pg.ndof))
