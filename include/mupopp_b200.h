@@ -210,6 +210,11 @@ typedef struct {
 /* Jacobi-preconditioned CG (SPD: mass, pressure).  d_x holds the initial guess on entry. */
 int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
                  mp_solve_info *info);
+/* Chebyshev-Jacobi preconditioned CG: z = p_k(D^-1 A) D^-1 r on [lmin, lmax] (k = degree; k-1 extra SpMVs and no reductions per
+ * application).  mp_spectral_bound returns the Gershgorin bound max_i dinv_i sum_j |a_ij| >= lambda_max(D^-1 A). */
+int mp_spectral_bound(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, double *lmax);
+int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
+                           int degree, double lmin, double lmax, mp_solve_info *info);
 /* Jacobi-preconditioned BiCGStab (non-symmetric transport rows). */
 int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
                       mp_solve_info *info);

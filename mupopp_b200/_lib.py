@@ -101,6 +101,8 @@ SIGNATURES = {
     "mp_vmul": (C.c_int, [_VP, C.c_int64, C.c_double, _VP, _VP, _VP]),
     "mp_jacobi_setup": (C.c_int, [_VP, C.POINTER(MpCsr), _VP]),
     "mp_solve_pcg": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
+    "mp_spectral_bound": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, C.POINTER(C.c_double)]),
+    "mp_solve_pcg_chebyshev": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.POINTER(MpSolveInfo)]),
     "mp_solve_bicgstab": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_solve_gmres": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.c_int, C.POINTER(MpSolveInfo)]),
     "mp_nccl_unique_id": (C.c_int, [_VP]),

@@ -71,6 +71,7 @@ struct mp_ctx {
 namespace mp {
 constexpr int kLocalOff = 16;   // rank-local copy of the scalar block lives at d_scalars + kLocalOff (multi-GPU only)
 int allreduce_oop(mp_ctx *ctx, const double *d_send, double *d_recv, int count);
+int allreduce_max_host(mp_ctx *ctx, double *h_value);   // max over ranks of one host scalar (no-op on one GPU)
 int ws_get(mp_ctx *ctx, int slot, size_t bytes, void **out);
 inline void count_launch(mp_ctx *ctx, int n = 1) { ctx->launches += n; }
 }  // namespace mp

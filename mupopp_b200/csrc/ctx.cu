@@ -206,6 +206,16 @@ int mp_nccl_unique_id(uint8_t *out128) {
 }  // extern "C"
 
 namespace mp {
+int allreduce_max_host(mp_ctx *c, double *h_value) {
+    if (c->nranks <= 1 || !c->nccl_comm) return 0;
+    double *d = c->d_scalars + 60;   // scratch at the end of the 64-double scalar block
+    MP_CUDA(cudaMemcpyAsync(d, h_value, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    MP_NCCL(g_nccl.AllReduce(d, d, 1, kNcclFloat64, 2 /* ncclMax */, c->nccl_comm, c->stream));
+    MP_CUDA(cudaMemcpyAsync(h_value, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    MP_CUDA(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
 int allreduce_oop(mp_ctx *c, const double *d_send, double *d_recv, int count) {
     if (c->nranks <= 1 || !c->nccl_comm || count == 0) return 0;
     MP_NCCL(g_nccl.AllReduce(d_send, d_recv, (size_t)count, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream));

@@ -403,6 +403,83 @@ __global__ void __launch_bounds__(kThreads) k_bicg_x(int64_t n, const double *__
     grid_reduce<2>(acc, partials, counter, scal, sl_, true);
 }
 
+
+// ------------------------------------------------------------------ Chebyshev polynomial preconditioner (Jacobi-scaled)
+// z = p_k(D^-1 A) D^-1 r on [lmin, lmax]:  the "Chebyshev" option of BASELINE.json's north_star.  k-1 SpMVs per application and
+// no inner products, so a PCG iteration does k SpMVs per pair of reductions (what matters once the allreduce latency dominates).
+__global__ void __launch_bounds__(kThreads) k_cheb_first(int64_t n, double inv_theta, const double *__restrict__ r,
+                                                         const double *__restrict__ dinv, double *__restrict__ z,
+                                                         double *__restrict__ d, const double *scal) {
+    if (!solver_active(scal)) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        const double v = inv_theta * dinv[i] * r[i];
+        z[i] = v;
+        d[i] = v;
+    }
+}
+
+// t = A z (done by the caller): d = c1 d + c2 dinv (r - t) ; z += d
+__global__ void __launch_bounds__(kThreads) k_cheb_step(int64_t n, double c1, double c2, const double *__restrict__ r,
+                                                        const double *__restrict__ t, const double *__restrict__ dinv,
+                                                        double *__restrict__ z, double *__restrict__ d, const double *scal) {
+    if (!solver_active(scal)) return;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        const double dn = c1 * d[i] + c2 * dinv[i] * (r[i] - t[i]);
+        d[i] = dn;
+        z[i] += dn;
+    }
+}
+
+// general-preconditioner CG: x += alpha p ; r -= alpha q ; rr ; iter++
+__global__ void __launch_bounds__(kThreads) k_cgp_update(int64_t n, const double *__restrict__ p, const double *__restrict__ q,
+                                                         double *__restrict__ x, double *__restrict__ r, double *partials,
+                                                         unsigned int *counter, double *scal, int rz_cur) {
+    if (!solver_active(scal)) return;
+    const double alpha = safe_div(scal[rz_cur], scal[S_PQ]);
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        x[i] += alpha * p[i];
+        const double ri = r[i] - alpha * q[i];
+        r[i] = ri;
+        acc[0] += ri * ri;
+    }
+    const int sl_[1] = {S_RR};
+    grid_reduce<1>(acc, partials, counter, scal, sl_, true);
+}
+
+// rz' = r.z  (guarded: the slot keeps its value once converged)
+__global__ void __launch_bounds__(kThreads) k_cgp_rz(int64_t n, const double *__restrict__ r, const double *__restrict__ z,
+                                                     double *partials, unsigned int *counter, double *scal, int slot) {
+    if (!solver_active(scal)) return;
+    double acc[1] = {0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) acc[0] += r[i] * z[i];
+    const int sl_[1] = {slot};
+    grid_reduce<1>(acc, partials, counter, scal, sl_, false);
+}
+
+// p = z + beta p   (first == 1: p = z)
+__global__ void __launch_bounds__(kThreads) k_cgp_pupdate(int64_t n, int first, const double *__restrict__ z, double *__restrict__ p,
+                                                          const double *scal, int rz_cur, int rz_nxt) {
+    if (!solver_active(scal)) return;
+    const double beta = first ? 0.0 : safe_div(scal[rz_nxt], scal[rz_cur]);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x)
+        p[i] = first ? z[i] : z[i] + beta * p[i];
+}
+
+// Gershgorin bound of lambda_max(D^-1 A): max_i dinv_i * sum_j |a_ij|  (max is order independent; positive doubles compare as integers)
+__global__ void __launch_bounds__(kThreads) k_gershgorin(int64_t nrow, const int32_t *__restrict__ rowptr, const double *__restrict__ vals,
+                                                         const double *__restrict__ dinv, unsigned long long *out) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double v = 0.0;
+    if (r < nrow) {
+        double s = 0.0;
+        for (int32_t k = rowptr[r]; k < rowptr[r + 1]; ++k) s += fabs(vals[k]);
+        v = s * fabs(dinv[r]);
+    }
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+
 int grid_for(const mp_ctx *ctx, int64_t n_threads_wanted) {
     int64_t g = cdiv(n_threads_wanted, kThreads);
     int64_t cap = (int64_t)ctx->num_sm * 8;  // 8 x 256 threads = 2048 resident threads per SM
@@ -917,6 +994,94 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
                 MP_CUDA(cudaGetLastError());
                 MP_TRY(poll(ctx));
                 if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_bicgstab: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
+            }
+        }
+    }
+    return finish_solve(ctx, info);
+}
+
+extern "C" int mp_spectral_bound(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, double *lmax) {
+    MP_CHECK(ctx && d_dinv && lmax, "mp_spectral_bound: null argument");
+    MP_TRY(check_csr(A));
+    unsigned long long *d_out = reinterpret_cast<unsigned long long *>(ctx->d_scalars + S_COUNT + mp::kLocalOff);   // scratch slot
+    MP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), ctx->stream));
+    if (A->nrow > 0) {
+        k_gershgorin<<<(unsigned)cdiv(A->nrow, kThreads), kThreads, 0, ctx->stream>>>(A->nrow, A->d_rowptr, A->d_vals, d_dinv, d_out);
+        mp::count_launch(ctx);
+    }
+    double h = 0.0;
+    MP_CUDA(cudaMemcpyAsync(&h, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    MP_TRY(mp::allreduce_max_host(ctx, &h));
+    *lmax = h;
+    return 0;
+}
+
+// Chebyshev-Jacobi preconditioned CG.  degree >= 1 (1 == plain Jacobi scaling by 1/theta); [lmin, lmax] must contain the top of the
+// spectrum of D^-1 A (mp_spectral_bound gives a safe lmax; lmin = lmax / 30 is the customary smoother window).
+extern "C" int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
+                                      int degree, double lmin, double lmax, mp_solve_info *info) {
+    MP_CHECK(ctx && d_dinv && d_b && d_x && info, "mp_solve_pcg_chebyshev: null argument");
+    MP_CHECK(degree >= 1 && degree <= 16 && lmin > 0.0 && lmax > lmin, "mp_solve_pcg_chebyshev: need 1 <= degree <= 16 and 0 < lmin < lmax");
+    MP_TRY(check_csr(A));
+    const int64_t n = A->nrow, nc = A->ncol;
+    int64_t nnz = 0;
+    MP_TRY(nnz_of(ctx, A, &nnz));
+    const int lanes = pick_lanes(A, nnz);
+    double *w = nullptr;
+    MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(4 * n + 2 * nc + 8), (void **)&w));
+    double *r = w, *q = w + n, *d = w + 2 * n, *t = w + 3 * n, *p = w + 4 * n, *z = w + 4 * n + nc;   // p, z carry ghost entries
+    const int g1 = grid_for(ctx, n);
+    const double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta;
+    auto precond = [&]() -> int {   // z = p_k(D^-1 A) D^-1 r
+        k_cheb_first<<<g1, kThreads, 0, ctx->stream>>>(n, 1.0 / theta, r, d_dinv, z, d, ctx->d_scalars);
+        mp::count_launch(ctx);
+        double rho0 = 1.0 / sigma;
+        for (int i = 1; i < degree; ++i) {
+            const double rho1 = 1.0 / (2.0 * sigma - rho0);
+            MP_TRY(mp_halo_exchange(ctx, halo, z));
+            MP_TRY((launch_spmv<0, true>(ctx, A, lanes, z, t, nullptr, 0, 0)));
+            k_cheb_step<<<g1, kThreads, 0, ctx->stream>>>(n, rho1 * rho0, 2.0 * rho1 / delta, r, t, d_dinv, z, d, ctx->d_scalars);
+            mp::count_launch(ctx);
+            rho0 = rho1;
+        }
+        return 0;
+    };
+    const int every = info->check_every > 0 ? info->check_every : 10;
+    int total = 0;
+    for (int restart = 0; restart <= kMaxRestart; ++restart) {
+        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
+        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, q, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, nullptr, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_TMP0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        bool done = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done));
+        if (done || total >= info->maxit) break;
+        int cur = S_RZ0, nxt = S_RZ1;
+        MP_TRY(precond());
+        k_cgp_rz<<<g1, kThreads, 0, ctx->stream>>>(n, r, z, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur);
+        MP_TRY(reduce_slots(ctx, cur, 1));
+        k_cgp_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, 1, z, p, ctx->d_scalars, cur, cur);
+        mp::count_launch(ctx, 2);
+        for (; total < info->maxit;) {
+            MP_TRY(mp_halo_exchange(ctx, halo, p));
+            MP_TRY((launch_spmv<1, true>(ctx, A, lanes, p, q, p, S_PQ, 0)));
+            MP_TRY(reduce_slots(ctx, S_PQ, 1));
+            k_cgp_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur);
+            MP_TRY(reduce_slots(ctx, S_RR, 1));
+            MP_TRY(precond());
+            k_cgp_rz<<<g1, kThreads, 0, ctx->stream>>>(n, r, z, ctx->d_partials, ctx->d_counter, ctx->d_scalars, nxt);
+            MP_TRY(reduce_slots(ctx, nxt, 1));
+            k_cgp_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, 0, z, p, ctx->d_scalars, cur, nxt);
+            mp::count_launch(ctx, 3);
+            int tmp = cur; cur = nxt; nxt = tmp;
+            ++total;
+            if (total % every == 0 || total == info->maxit) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_pcg_chebyshev: NaN residual at iteration %d", total); return 4; }
                 if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
             }
         }

@@ -231,6 +231,8 @@ extern "C" int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr
     MP_CHECK(lr > 0 && ncell >= 0 && nrow > 0, "mp_plan_create: bad sizes");
     MP_CHECK(ncell * lr < (int64_t)INT32_MAX, "mp_plan_create: ncell*lr exceeds int32");
     MP_CHECK(nrow < INT32_MAX && ncol < INT32_MAX, "mp_plan_create: nrow/ncol exceed int32");
+    MP_CHECK(lc == 0 || d_col_dofs, "mp_plan_create: lc > 0 but d_col_dofs is null");
+    MP_CHECK(ncell * lr * (int64_t)(lc > 0 ? lc : 1) < (int64_t)INT32_MAX, "mp_plan_create: ncell*lr*lc exceeds int32");
     MP_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     mp_plan *p = new mp_plan();
@@ -302,7 +304,6 @@ extern "C" int mp_plan_create(mp_ctx *ctx, const int32_t *d_row_dofs, int32_t lr
 
     // ---- 2. CSR pattern: sort 64-bit (row,col) keys of every local entry, unique
     if (lc > 0) {
-        MP_CHECK(d_col_dofs, "mp_plan_create: lc > 0 but d_col_dofs is null");
         const int64_t nkeys = ninc_all * lc;
         if (nkeys >= (int64_t)INT32_MAX) { mp::set_error("mp_plan_create: ncell*lr*lc exceeds int32"); cleanup(); mp_plan_destroy(p); return 2; }
         PC(cudaMalloc(&pk, sizeof(uint64_t) * (nkeys + 1)));

@@ -226,13 +226,21 @@ class CsrMatrix:
         return sp.csr_matrix((self.vals.cpu().numpy(), self.colidx.cpu().numpy(), self.rowptr.cpu().numpy()),
                              shape=(self.nrow, self.ncol))
 
-    def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True, restart=50):
+    def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True, restart=50,
+              cheb_degree=3, cheb_ratio=30.0):
         if self.dinv is None or refresh_jacobi:
             self.jacobi_setup()
         self.sync_sell()
         info = MpSolveInfo(rtol, atol, int(maxit), int(check_every), 0, 0, 0.0)
         hh = halo.h if halo is not None else None
-        if method == "gmres":
+        if method == "pcg_chebyshev":
+            if getattr(self, "_lmax", None) is None or refresh_jacobi:
+                lm = C.c_double()
+                check(self.ctx.lib.mp_spectral_bound(self.ctx.h, C.byref(self.c), ptr(self.dinv), C.byref(lm)), "mp_spectral_bound")
+                self._lmax = lm.value
+            check(self.ctx.lib.mp_solve_pcg_chebyshev(self.ctx.h, C.byref(self.c), ptr(self.dinv), ptr(b), ptr(x), hh, int(cheb_degree),
+                                                      self._lmax / float(cheb_ratio), self._lmax, C.byref(info)), "mp_solve_pcg_chebyshev")
+        elif method == "gmres":
             check(self.ctx.lib.mp_solve_gmres(self.ctx.h, C.byref(self.c), ptr(self.dinv), ptr(b), ptr(x), hh, int(restart),
                                               C.byref(info)), "mp_solve_gmres")
         else:

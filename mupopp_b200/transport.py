@@ -129,10 +129,14 @@ class TransportSolverF:
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
                  rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
-                 vert2dof=None, row_ordered=True):
+                 vert2dof=None, row_ordered=True, p_precond="jacobi", cheb_degree=3):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
+        # pressure PCG preconditioner: "jacobi" (default) or "chebyshev" (degree-k Chebyshev-Jacobi polynomial: same time on one GPU at
+        # 200^3, 3-4x fewer reduction points per SpMV -- meant for multi-GPU runs; not yet the default there, see DESIGN.md section 5)
+        self.p_method = "pcg_chebyshev" if p_precond == "chebyshev" else "pcg"
+        self.cheb_degree = cheb_degree
         self.halo = halo
         self.dm = DeviceMesh(ctx, mesh, vert2dof)
         V, Cn, d = self.dm.ndof, self.dm.ncell, self.dm.dim
@@ -247,7 +251,7 @@ class TransportSolverF:
         self.plan.scatter_vector(self.evec, self.rhs)
         ctx.axpby(-1.0, self.flux_load[: self.nown], 1.0, self.rhs)
         self.L.apply_dirichlet(self.rhs, self.p_isbc, self.zeros_loc, matrix=False)
-        rp = self.L.solve("pcg", self.rhs, self.p, **kw)
+        rp = self.L.solve(self.p_method, self.rhs, self.p, cheb_degree=self.cheb_degree, **kw)
         self._exchange(self.p)
         # 4. velocity recovery, then rotate the state
         check(lib.mp_recover_velocity(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.p), ptr(self.c0_new), ptr(self.u)),

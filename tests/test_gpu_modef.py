@@ -153,7 +153,7 @@ def test_determinism_bitwise(ctx):
         assert np.array_equal(a, b)
 
 
-@pytest.mark.parametrize("method", ["gmres", "bicgstab", "pcg"])
+@pytest.mark.parametrize("method", ["gmres", "bicgstab", "pcg", "pcg_chebyshev"])
 def test_krylov_solvers_against_direct(ctx, method):
     """Each Krylov driver reproduces the LU solution of the same CSR system (SPD for pcg, SUPG transport otherwise)."""
     import ctypes as C
@@ -167,7 +167,7 @@ def test_krylov_solvers_against_direct(ctx, method):
     rng = np.random.default_rng(3)
     emat = ctx.empty(dm.ncell * 16)
     A = plan.new_matrix()
-    if method == "pcg":
+    if method.startswith("pcg"):
         check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(dm.c), None, 1.0, 1.0, ptr(emat)))
         plan.scatter_matrix(emat, A)
         isbc = np.zeros(om.nv, dtype=np.uint8)
@@ -243,3 +243,21 @@ def test_periodic_constrained_domain_matches_oracle(ctx, dim, n):
     for nm in ("c0", "c1", "c2", "p"):
         assert rel(getattr(s, nm).cpu().numpy(), getattr(st, nm)) < 1e-8, nm
     assert rel(s.u.cpu().numpy().reshape(-1, dim), st.u) < 1e-8
+
+
+def test_chebyshev_pressure_preconditioner_gives_the_same_fields(ctx):
+    """Chebyshev-Jacobi PCG for the pressure solve (north_star: "Jacobi or Chebyshev preconditioning") reproduces the Jacobi-PCG step."""
+    from mupopp_b200.transport import TransportSolverF
+    pm, om, model, oprm, bd, obc, f = _setup(3, 6, "ccs3")
+    out = []
+    for pre in ("jacobi", "chebyshev"):
+        s = TransportSolverF(ctx, pm, model, bd, f_source=f, rtol=1e-13, p_precond=pre, cheb_degree=3)
+        s.set_state(c1=0.1 * np.ones(om.nv))
+        its = []
+        for k in range(3):
+            r = s.step()
+            its.append(r["p"].niter)
+            assert r["p"].converged
+        out.append((s.p.cpu().numpy().copy(), s.c0.cpu().numpy().copy(), its))
+    assert rel(out[1][0], out[0][0]) < 1e-10 and rel(out[1][1], out[0][1]) < 1e-10
+    assert sum(out[1][2]) < sum(out[0][2])          # fewer (but more expensive) outer iterations

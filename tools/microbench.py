@@ -102,6 +102,12 @@ def main():
     torch.cuda.synchronize(); dt = time.time() - t0
     it_bytes = spmv_bytes + 8.0 * N + 56.0 * N + 32.0 * N
     print("pcg: %s  %.3f ms/iter  %.1f GB/s algorithmic per iteration" % (r, 1e3 * dt / max(r.niter, 1), it_bytes * r.niter / dt / 1e9), flush=True)
+    for meth, kw in (("pcg", {}), ("pcg_chebyshev", dict(cheb_degree=2)), ("pcg_chebyshev", dict(cheb_degree=3)), ("pcg_chebyshev", dict(cheb_degree=4))):
+        xs.zero_()
+        torch.cuda.synchronize(); t0 = time.time()
+        r = A.solve(meth, b, xs, rtol=1e-8, maxit=6000, **kw)
+        torch.cuda.synchronize(); dt = time.time() - t0
+        print("%s %s to rtol 1e-8: %s  total %.1f ms" % (meth, kw, r, 1e3 * dt), flush=True)
     xs.zero_()
     torch.cuda.synchronize(); t0 = time.time()
     r = A.solve("gmres", b, xs, rtol=1e-6, maxit=200)
