@@ -139,3 +139,78 @@ def slab_boundary_data(part: SlabPartition, u_marker, u_value, c0_marker=None, c
 def make_halo(ctx, part: SlabPartition):
     from .device import Halo
     return Halo(ctx, [n[0] for n in part.neigh], [n[1] for n in part.neigh], [n[2] for n in part.neigh], [n[3] for n in part.neigh])
+
+
+# ------------------------------------------------------------------ general meshes: recursive coordinate bisection
+def rcb_owner(coords, nranks):
+    """Recursive coordinate bisection of the vertices into `nranks` parts of (nearly) equal size (general
+    meshes have no METIS/SCOTCH here).  Deterministic: ties are broken by vertex id.  Returns owner[v] in [0, nranks)."""
+    owner = np.zeros(coords.shape[0], dtype=np.int32)
+
+    def split(idx, r0, nr):
+        if nr == 1:
+            owner[idx] = r0
+            return
+        nl = nr // 2
+        x = coords[idx]
+        axis = int(np.argmax(x.max(0) - x.min(0)))
+        order = np.lexsort((idx, x[:, axis]))
+        cut = (len(idx) * nl) // nr
+        split(idx[order[:cut]], r0, nl)
+        split(idx[order[cut:]], r0 + nl, nr - nl)
+
+    split(np.arange(coords.shape[0]), 0, nranks)
+    return owner
+
+
+def general_partition(mesh, owner, rank):
+    """Owner-computes partition of an arbitrary simplicial mesh for `rank`: local cells = every cell with an owned vertex; local vertex
+    numbering = [owned (ascending global id) | ghosts grouped by owning rank (ascending rank, then global id)], so each neighbour's
+    ghost block is contiguous, as mp_halo_exchange requires.  The send list to neighbour q is the ascending list of my vertices that
+    are ghosts on q -- the same order in which q stores them."""
+    owner = np.asarray(owner)
+    nranks = int(owner.max()) + 1
+    cells = mesh.cells.astype(np.int64)
+    cell_owner = owner[cells]                                   # (C, d+1)
+    mine = (cell_owner == rank).any(1)
+    lc = cells[mine]
+    verts = np.unique(lc.ravel())
+    owned = verts[owner[verts] == rank]
+    ghosts = verts[owner[verts] != rank]
+    gorder = np.lexsort((ghosts, owner[ghosts]))
+    ghosts = ghosts[gorder]
+    local_of = np.full(mesh.num_vertices(), -1, dtype=np.int64)
+    gids = np.concatenate([owned, ghosts])
+    local_of[gids] = np.arange(gids.size)
+    loc = Mesh(mesh.coords[gids], local_of[lc].astype(np.int32))
+    # true boundary facets only (cut faces of the partition are not boundary): restrict the global list to the local cells
+    gfv, gn, gmeas, gown = mesh.boundary_facets()
+    gloc = mesh.boundary_facet_local_index()
+    cell_local = np.full(mesh.num_cells(), -1, dtype=np.int64)
+    cell_local[np.nonzero(mine)[0]] = np.arange(int(mine.sum()))
+    keep = cell_local[gown] >= 0
+    loc._bfacets = (local_of[gfv[keep]], gn[keep].copy(), gmeas[keep].copy(), cell_local[gown[keep]])
+    loc._bfacet_local = gloc[keep].copy()
+    neigh = []
+    for q in range(nranks):
+        if q == rank:
+            continue
+        recv = ghosts[owner[ghosts] == q]                       # contiguous block in my numbering
+        # what q needs from me: my owned vertices appearing in cells where q owns a vertex
+        qcells = cells[(cell_owner == q).any(1)]
+        qv = np.unique(qcells.ravel())
+        send = qv[owner[qv] == rank]                            # ascending global id == q's storage order of its ghosts owned by me
+        if recv.size == 0 and send.size == 0:
+            continue
+        rstart = int(local_of[recv[0]]) if recv.size else int(gids.size)
+        neigh.append((q, local_of[send].astype(np.int32), rstart, int(recv.size)))
+    return SlabPartition(rank, nranks, None, None, loc, int(owned.size), int(gids.size), gids, neigh)
+
+
+def restrict_boundary_data(part: SlabPartition, global_bdata):
+    """Boundary data of a general partition from the data of the GLOBAL mesh (make_boundary_data on the whole mesh, computed once per
+    process): exact Dirichlet flags on ghost columns too, which a purely local facet search cannot guarantee for arbitrary cuts."""
+    from .transport import BoundaryDataF
+    g = part.global_ids
+    return BoundaryDataF(global_bdata.p_isbc[g].copy(), global_bdata.flux_load[g].copy(), global_bdata.c0_isbc[g].copy(),
+                         global_bdata.c0_g[g].copy())

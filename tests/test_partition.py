@@ -111,3 +111,65 @@ def test_periodic_slabs_match_global_periodic_map(nranks):
             assert len(send_idx) == rcount == GRID[0] * GRID[1] and rstart >= p.n_owned
         cover.append(p.global_ids[: p.n_owned])
     assert np.array_equal(np.sort(np.concatenate(cover)), np.arange(pg.ndof))
+
+
+def _general_mesh(kind):
+    if kind == "demo":
+        import os
+        g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fenics_demo_dofmap.npz"))
+        return mp.Mesh(g["coords"], g["cells"])
+    return mp.BoxMesh(BOX[0], BOX[1], *GRID)
+
+
+@pytest.mark.parametrize("kind,nranks", [("demo", 2), ("demo", 5), ("box", 3), ("box", 8)])
+def test_rcb_partition_is_consistent(kind, nranks):
+    """General (unstructured) partition: balanced RCB ownership, complete owned rows, and halo plans whose send/recv lists pair up."""
+    m = _general_mesh(kind)
+    owner = partition.rcb_owner(m.coords, nranks)
+    counts = np.bincount(owner, minlength=nranks)
+    assert counts.max() - counts.min() <= nranks          # balanced to within the bisection rounding
+    parts = [partition.general_partition(m, owner, r) for r in range(nranks)]
+    og = fem.Mesh(m.coords, m.cells.astype(np.int64))
+    Mg = forms.Assembler(og).mass(1, 1, 2).tocsr()
+    xg = np.cos(0.31 * np.arange(m.num_vertices()))
+    cover = []
+    for p in parts:
+        assert np.array_equal(p.mesh.coords, m.coords[p.global_ids])
+        assert (owner[p.global_ids[: p.n_owned]] == p.rank).all() and (owner[p.global_ids[p.n_owned:]] != p.rank).all()
+        cover.append(p.global_ids[: p.n_owned])
+        ol = fem.Mesh(p.mesh.coords, np.sort(p.mesh.cells.astype(np.int64), axis=1))
+        Ml = forms.Assembler(ol).mass(1, 1, 2).tocsr()
+        x = np.zeros(p.n_local)
+        x[: p.n_owned] = xg[p.global_ids[: p.n_owned]]
+        # emulate the halo exchange with the partner's send list
+        for (q, send_idx, rstart, rcount) in p.neigh:
+            back = [n for n in parts[q].neigh if n[0] == p.rank]
+            assert len(back) == 1
+            qsend = back[0][1]
+            assert len(qsend) == rcount
+            x[rstart:rstart + rcount] = xg[parts[q].global_ids[qsend]]
+        assert np.array_equal(x, xg[p.global_ids])
+        # owner-computes: local rows of owned vertices equal the global rows
+        yl = (Ml @ x)[: p.n_owned]
+        assert np.allclose(yl, (Mg @ xg)[p.global_ids[: p.n_owned]], rtol=1e-13, atol=1e-15)
+    assert np.array_equal(np.sort(np.concatenate(cover)), np.arange(m.num_vertices()))
+
+
+def test_general_partition_boundary_data_matches_global():
+    """Cut faces must not be taken for boundary: Dirichlet flags and the Neumann flux load of every owned vertex equal the global ones."""
+    from mupopp_b200.transport import make_boundary_data
+    m = mp.BoxMesh(BOX[0], BOX[1], *GRID)
+    top = lambda x: x[..., 2] > 1.0 - 1e-12
+    gbd = make_boundary_data(m, top, (0.0, 0.0, -0.5), top, 0.1)
+    owner = partition.rcb_owner(m.coords, 4)
+    for r in range(4):
+        p = partition.general_partition(m, owner, r)
+        bd = make_boundary_data(p.mesh, top, (0.0, 0.0, -0.5), top, 0.1)
+        own = p.global_ids[: p.n_owned]
+        assert np.array_equal(bd.p_isbc[: p.n_owned], gbd.p_isbc[own])
+        assert np.array_equal(bd.c0_isbc[: p.n_owned], gbd.c0_isbc[own])
+        assert np.allclose(bd.flux_load[: p.n_owned], gbd.flux_load[own], rtol=0, atol=1e-15)
+        # ghost columns need the right Dirichlet flags too (symmetric elimination zeroes those columns): restrict the global data
+        rb = partition.restrict_boundary_data(p, gbd)
+        assert np.array_equal(rb.p_isbc, gbd.p_isbc[p.global_ids]) and np.array_equal(rb.p_isbc[: p.n_owned], bd.p_isbc[: p.n_owned])
+        assert np.allclose(rb.flux_load[: p.n_owned], bd.flux_load[: p.n_owned], rtol=0, atol=1e-15)

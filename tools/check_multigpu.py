@@ -30,10 +30,16 @@ top = lambda x: x[..., 2] > 1.0 - 1e-12
 umark = lambda x: x[..., 2] > 1e-12
 uval = lambda x: np.stack([0 * x[..., 0], 0 * x[..., 0], np.where(x[..., 2] > 1.0 - 1e-12, -0.5, 0.0)], -1)
 src = lambda X: np.abs(np.sin(3 * np.pi * X[:, 0])) * (1 - np.tanh((1.0 - X[:, 2]) / 0.1))
+rcb = len(sys.argv) > 4 and sys.argv[4] == "rcb"          # general (unstructured-style) RCB partition instead of z-slabs
 if per:
     umark, uval = top, (0.0, 0.0, -0.5)
-part = partition.slab_partition(BOX, (n, n, nz), rank, world, periodic_xy=per)
-bd = partition.slab_boundary_data(part, umark, uval, top, 0.1)
+if rcb:
+    gmesh = mp.BoxMesh(BOX[0], BOX[1], n, n, nz)
+    part = partition.general_partition(gmesh, partition.rcb_owner(gmesh.coords, world), rank)
+    bd = partition.restrict_boundary_data(part, make_boundary_data(gmesh, umark, uval, top, 0.1))
+else:
+    part = partition.slab_partition(BOX, (n, n, nz), rank, world, periodic_xy=per)
+    bd = partition.slab_boundary_data(part, umark, uval, top, 0.1)
 halo = partition.make_halo(ctx, part)
 fs = src(part.mesh.coords)
 s = TransportSolverF(ctx, part.mesh, model, bd, f_source=part.periodic.restrict(fs) if per else fs, rtol=1e-13, halo=halo,
