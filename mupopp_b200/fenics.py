@@ -572,11 +572,11 @@ def solve(eq, u, bcs=None, solver_parameters=None, **kw):
 
 
 class File:
-    """Output sink: `File(name, "compressed") << f`.  VTK writing is out of scope; fields are kept as
-    .npy next to the requested name only when MUPOPP_B200_WRITE=1."""
+    """`File(name, "compressed") << f` writes a VTK time series (name.pvd + name000000.vtu ...), `File(name.xml[.gz]) >> f` reads DOLFIN-XML
+    function data.  Set MUPOPP_B200_WRITE=0 to turn the writer into a no-op (benchmark runs)."""
 
     def __init__(self, name, *a):
-        self.name, self.count = name, 0
+        self.name, self.count, self._series = name, 0, None
 
     def __rshift__(self, f):
         read_function_xml(self.name, f)
@@ -584,9 +584,17 @@ class File:
 
     def __lshift__(self, f):
         import os
-        if os.environ.get("MUPOPP_B200_WRITE") == "1":
-            os.makedirs(os.path.dirname(self.name) or ".", exist_ok=True)
-            fn = f[0] if isinstance(f, tuple) else f
-            np.save("%s.%06d.npy" % (self.name, self.count), fn.vector().get_local())
+        if os.environ.get("MUPOPP_B200_WRITE", "1") != "0":
+            from .io import PvdSeries
+            t = None
+            if isinstance(f, tuple):
+                f, t = f
+            if self._series is None:
+                self._series = PvdSeries(self.name)
+            mesh = f.space.mesh
+            nv = mesh.num_vertices()
+            cols = [f.blocks[k].cpu().numpy()[:nv] for k in range(len(f.blocks))]       # Lagrange fields at the vertices
+            data = cols[0] if len(cols) == 1 else np.stack(cols, axis=1)
+            self._series.write(mesh.coords, mesh.cells, {f._name: data}, t)
         self.count += 1
         return self
