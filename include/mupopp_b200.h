@@ -174,6 +174,31 @@ int mp_elem_p1_porosity_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *qu
                              const double *d_vel0, const double *d_vel1, const double *d_vel2, const double *d_phi0, const double *d_gam,
                              double *d_elem_mat, double *d_elem_vec);
 
+/* ------------------------------------------------------------------ scalar functionals (dolfin.assemble(<scalar form>), errornorm)
+ * J = sum_e weight[e] * sum_q w[q] * prod_{k<nfield} F_k(x_q) * (V(x_q) . g_e)      e = cells (dx) or boundary facets (ds(id))
+ * Call sites replaced: assemble(c00*phi0*dot(u0, n)*ds(1)) run/CCS2D/CCS_3comp.py:277; assemble(c02*dx), assemble(f*Da*c00*c01*dx),
+ * assemble(c00*dot(u, unitNormal)*ds(1)) run/stokes_ADR_3D/master_advective_stokes.py:232-265; errornorm(u, uh, 'L2')
+ * benchmark/sphere_3D_pure_shear/sphere.py:157-159 (= sqrt of the functional of (u - uh)^2 per component).
+ * F_k = scalar Lagrange field (P1/P2/P3) given by its dof vector, the cell dofmap and the basis values tabulated at the
+ * quadrature points of every reference entity (table id per entity: 0 for cells, the UFC local facet index for facets).
+ * V = optional vector factor: Lagrange components (vec_kind 1) or one constant vector per cell (vec_kind 2: mode F's DG0 velocity);
+ * g_e = per-entity direction (facet normal) or one constant direction.  Deterministic reduction; allreduced over ranks. */
+typedef struct {
+    int32_t nfield;                /* 0..4 scalar factors */
+    int32_t nb[4];                 /* local dofs of each factor */
+    const double *d_field[4];
+    const int32_t *d_dofs[4];      /* [ncell][nb[k]] */
+    const double *d_tab[4];        /* [ntab][nq][nb[k]] */
+    int32_t vec_kind, nbv;
+    const double *d_vec[3];        /* vec_kind 1: one dof vector per component; vec_kind 2: d_vec[0] = [ncell][dim] */
+    const int32_t *d_vdofs;        /* [ncell][nbv] */
+    const double *d_vtab;          /* [ntab][nq][nbv] */
+    int32_t nq, ntab;
+    const double *d_w;             /* [nq], sum = 1 (entity measures are in d_ent_weight) */
+} mp_functional;
+int mp_integrate(mp_ctx *ctx, int32_t dim, const mp_functional *f, int64_t nent, const int32_t *d_ent_cell, const int32_t *d_ent_tab,
+                 const double *d_ent_weight, const double *d_ent_g, const double *g_const, double *result);
+
 /* ------------------------------------------------------------------ linear algebra (PETSc Mat/Vec/KSP replacement)
  * Call sites replaced: KrylovSolver(...).solve modules/mupopp.py:289-303,410-425; the LU inside solve(a==L,..). */
 typedef struct {
@@ -186,7 +211,7 @@ typedef struct {
     const int32_t *d_colidx;
     const double *d_vals;
     /* optional SELL-32 mirror used by SpMV (NULL -> CSR kernels): slice s = rows 32s..32s+31 stored [j][lane],
-     * padded to the slice's longest row with (col = row, val = 0); see mp_plan_sell_info / mp_csr_to_sell */
+     * padded to the slice's longest row with (col = the row's first column, val = 0); see mp_plan_sell_info / mp_csr_to_sell */
     const int32_t *d_sell_sliceptr;
     const int32_t *d_sell_col;
     const double *d_sell_val;
@@ -236,6 +261,24 @@ int mp_halo_create(mp_ctx *ctx, int nneigh, const int32_t *neigh_rank, const int
                    const int32_t *recv_start, const int32_t *recv_count, mp_halo **out);
 int mp_halo_exchange(mp_ctx *ctx, mp_halo *halo, double *d_x);
 int mp_halo_destroy(mp_halo *halo);
+
+/* Peer-memory collectives over NVLink / NVSwitch (CUDA IPC), the fast path of the Krylov loops on N > 1 GPUs of one node:
+ *  - the allreduce of the Krylov scalars happens INSIDE the reducing kernel (mailbox windows, sequence-number flags, rank-ordered
+ *    sum => identical bits on every rank): no ncclAllReduce launch per inner product;
+ *  - the halo exchange is fused into the SELL-32 SpMV kernel: interface values are stored straight into the neighbours' ghost
+ *    windows, interior slices are multiplied while the stores are in flight, boundary slices after the neighbours' flags arrived.
+ * Set-up (host): every rank exports a 64-byte IPC handle, the host all-gathers them (torch.distributed) and attaches.
+ * NCCL stays the transport of everything outside the Krylov loops (coefficient halos before assembly) and the fallback when
+ * the windows are not attached; option "peer" (mp_ctx_set_option) switches between the two for A/B measurements. */
+int mp_comm_peer_export(mp_ctx *ctx, uint8_t *handle64);
+int mp_comm_peer_attach(mp_ctx *ctx, const uint8_t *handles /* [nranks][64], indexed by rank */);
+int mp_comm_peer_enabled(const mp_ctx *ctx);
+/* ghost window of one halo plan: nown owned columns, nghost ghost columns (local columns nown .. nown+nghost-1) */
+int mp_halo_peer_export(mp_ctx *ctx, mp_halo *halo, int64_t nown, int64_t nghost, uint8_t *handle64);
+/* per neighbour k (order of mp_halo_create): its window handle, the offset of MY block inside its ghost window
+ * (its recv_start for me minus its nown), its nghost, and my index in ITS neighbour list */
+int mp_halo_peer_attach(mp_ctx *ctx, mp_halo *halo, const uint8_t *neigh_handles /* [nneigh][64] */, const int64_t *peer_goff,
+                        const int64_t *peer_gcap, const int32_t *peer_slot);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,12 @@ class MpCompactionParams(C.Structure):
                 ("zhat", C.c_double * 3)]
 
 
+class MpFunctional(C.Structure):
+    _fields_ = [("nfield", C.c_int32), ("nb", C.c_int32 * 4), ("d_field", C.c_void_p * 4), ("d_dofs", C.c_void_p * 4),
+                ("d_tab", C.c_void_p * 4), ("vec_kind", C.c_int32), ("nbv", C.c_int32), ("d_vec", C.c_void_p * 3),
+                ("d_vdofs", C.c_void_p), ("d_vtab", C.c_void_p), ("nq", C.c_int32), ("ntab", C.c_int32), ("d_w", C.c_void_p)]
+
+
 class MpCsr(C.Structure):
     _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nnz", C.c_int64), ("max_row_nnz", C.c_int32), ("pad", C.c_int32),
                 ("d_rowptr", C.c_void_p), ("d_colidx", C.c_void_p), ("d_vals", C.c_void_p),
@@ -95,6 +101,8 @@ SIGNATURES = {
                                          _VP, _VP, _VP, _VP]),
     "mp_elem_p1_porosity_quad": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.c_double, C.c_double, _VP, _VP, _VP, _VP,
                                            _VP, _VP, _VP, _VP]),
+    "mp_integrate": (C.c_int, [_VP, C.c_int32, C.POINTER(MpFunctional), C.c_int64, _VP, _VP, _VP, _VP, C.POINTER(C.c_double),
+                               C.POINTER(C.c_double)]),
     "mp_spmv": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP]),
     "mp_dot": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.POINTER(C.c_double)]),
     "mp_axpby": (C.c_int, [_VP, C.c_int64, C.c_double, _VP, C.c_double, _VP]),
@@ -112,6 +120,11 @@ SIGNATURES = {
     "mp_halo_create": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP, _VP, C.POINTER(_VP)]),
     "mp_halo_exchange": (C.c_int, [_VP, _VP, _VP]),
     "mp_halo_destroy": (C.c_int, [_VP]),
+    "mp_comm_peer_export": (C.c_int, [_VP, _VP]),
+    "mp_comm_peer_attach": (C.c_int, [_VP, _VP]),
+    "mp_comm_peer_enabled": (C.c_int, [_VP]),
+    "mp_halo_peer_export": (C.c_int, [_VP, _VP, C.c_int64, C.c_int64, _VP]),
+    "mp_halo_peer_attach": (C.c_int, [_VP, _VP, _VP, _VP, _VP, _VP]),
 }
 
 _lib = None

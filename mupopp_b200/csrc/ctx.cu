@@ -85,14 +85,6 @@ constexpr int kNcclFloat64 = 8, kNcclSum = 0;
 
 }  // namespace mp
 
-struct mp_halo {
-    int nneigh = 0;
-    std::vector<int32_t> rank, send_off, recv_start, recv_count;
-    int32_t *d_send_idx = nullptr;  // owned copy
-    double *d_sendbuf = nullptr;
-    int64_t nsend = 0;
-};
-
 namespace {
 __global__ void k_pack(const double *__restrict__ x, const int32_t *__restrict__ idx, double *__restrict__ buf, int64_t n) {
     int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -115,6 +107,10 @@ int mp_ctx_create(int device, void *stream, mp_ctx **out) {
     MP_CHECK(device >= 0 && device < ndev, "mp_ctx_create: device %d out of range (%d devices)", device, ndev);
     MP_CUDA(cudaSetDevice(device));
     mp_ctx *c = new mp_ctx();
+    struct Guard {   // frees the partially built context on any early return below
+        mp_ctx *c; bool armed = true;
+        ~Guard() { if (armed) mp_ctx_destroy(c); }
+    } guard{c};
     c->device = device;
     // NULL = the CUDA default stream (what torch's default stream is): kernels are then ordered with the
     // caller's torch copies on that stream without any extra synchronisation.
@@ -126,10 +122,11 @@ int mp_ctx_create(int device, void *stream, mp_ctx **out) {
     MP_CUDA(cudaMalloc(&c->d_scalars, sizeof(double) * 64));
     MP_CUDA(cudaMemset(c->d_scalars, 0, sizeof(double) * 64));
     MP_CUDA(cudaMallocHost(&c->h_scalars, sizeof(double) * 64));
-    MP_CUDA(cudaMalloc(&c->d_counter, sizeof(unsigned int) * 4));
-    MP_CUDA(cudaMemset(c->d_counter, 0, sizeof(unsigned int) * 4));
+    MP_CUDA(cudaMalloc(&c->d_ctl, sizeof(mp::ReduceCtl)));
+    MP_CUDA(cudaMemset(c->d_ctl, 0, sizeof(mp::ReduceCtl)));
     MP_CUDA(cudaMalloc(&c->d_partials, sizeof(double) * 4096 * 8));
     MP_CUDA(cudaEventCreateWithFlags(&c->ev, cudaEventDisableTiming));
+    guard.armed = false;
     *out = c;
     return 0;
 }
@@ -140,7 +137,9 @@ int mp_ctx_destroy(mp_ctx *c) {
     cudaStreamSynchronize(c->stream);
     if (c->nccl_comm && mp::g_nccl.CommDestroy) mp::g_nccl.CommDestroy(c->nccl_comm);
     for (auto &w : c->work) if (w.ptr) cudaFree(w.ptr);
-    cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_counter); cudaFree(c->d_partials);
+    for (void *m : c->mbox_mapped) if (m) cudaIpcCloseMemHandle(m);
+    cudaFree(c->mbox); cudaFree(c->d_comm);
+    cudaFree(c->d_scalars); cudaFreeHost(c->h_scalars); cudaFree(c->d_ctl); cudaFree(c->d_partials);
     if (c->ev) cudaEventDestroy(c->ev);
     for (auto e : c->tev) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -159,6 +158,10 @@ int64_t mp_ctx_launch_count(const mp_ctx *c) { return c ? c->launches : -1; }
 int mp_ctx_set_option(mp_ctx *c, const char *name, int value) {
     MP_CHECK(c && name, "mp_ctx_set_option: null argument");
     if (!strcmp(name, "spmv_variant")) { c->spmv_variant = value; return 0; }
+    if (!strcmp(name, "peer")) {   // switch the peer-memory collectives on/off (A/B runs against the NCCL path); needs mp_comm_peer_attach
+        MP_CHECK(!value || c->peer_attached, "mp_ctx_set_option: peer windows are not attached");
+        return mp::set_peer_mode(c, value != 0);
+    }
     mp::set_error("mp_ctx_set_option: unknown option '%s'", name);
     return 2;
 }
@@ -216,6 +219,19 @@ int allreduce_max_host(mp_ctx *c, double *h_value) {
     return 0;
 }
 
+// peer mode on: grid_reduce exchanges through the mailbox windows and writes the GLOBAL scalar slots directly (no local copy);
+// off: rank-local sums land at +kLocalOff and an out-of-place ncclAllReduce follows (reduce_slots in krylov.cu).
+int set_peer_mode(mp_ctx *c, bool on) {
+    if (on && !c->peer_attached) return 0;
+    MP_CUDA(cudaStreamSynchronize(c->stream));
+    mp::CommDev *comm = on ? c->d_comm : nullptr;
+    const unsigned int off = (!on && c->nranks > 1) ? (unsigned int)kLocalOff : 0u;
+    MP_CUDA(cudaMemcpy(&c->d_ctl->comm, &comm, sizeof(comm), cudaMemcpyHostToDevice));
+    MP_CUDA(cudaMemcpy(&c->d_ctl->local_off, &off, sizeof(off), cudaMemcpyHostToDevice));
+    c->peer = on;
+    return 0;
+}
+
 int allreduce_oop(mp_ctx *c, const double *d_send, double *d_recv, int count) {
     if (c->nranks <= 1 || !c->nccl_comm || count == 0) return 0;
     MP_NCCL(g_nccl.AllReduce(d_send, d_recv, (size_t)count, kNcclFloat64, kNcclSum, c->nccl_comm, c->stream));
@@ -236,7 +252,7 @@ int mp_comm_init(mp_ctx *c, int nranks, int rank, const uint8_t *id128) {
     c->rank = rank;
     // reductions now land in the rank-local scalar block (see grid_reduce in krylov.cu)
     const unsigned int off = nranks > 1 ? (unsigned int)mp::kLocalOff : 0u;
-    MP_CUDA(cudaMemcpy(c->d_counter + 1, &off, sizeof(off), cudaMemcpyHostToDevice));
+    MP_CUDA(cudaMemcpy(&c->d_ctl->local_off, &off, sizeof(off), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -246,7 +262,8 @@ int mp_comm_destroy(mp_ctx *c) {
         mp::g_nccl.CommDestroy(c->nccl_comm);
         c->nccl_comm = nullptr;
         c->nranks = 1; c->rank = 0;
-        cudaMemset(c->d_counter + 1, 0, sizeof(unsigned int));
+        cudaMemset(&c->d_ctl->local_off, 0, sizeof(unsigned int));
+        mp::set_peer_mode(c, false);
     }
     return 0;
 }
@@ -261,7 +278,12 @@ int mp_allreduce_sum(mp_ctx *c, double *d_buf, int count) {
 int mp_halo_create(mp_ctx *c, int nneigh, const int32_t *neigh_rank, const int32_t *send_off, const int32_t *d_send_idx,
                    const int32_t *recv_start, const int32_t *recv_count, mp_halo **out) {
     MP_CHECK(c && out && nneigh >= 0, "mp_halo_create: bad argument");
+    MP_CHECK(nneigh <= mp::kMaxNeigh, "mp_halo_create: more than %d neighbours", mp::kMaxNeigh);
     mp_halo *h = new mp_halo();
+    struct Guard {
+        mp_halo *h; bool armed = true;
+        ~Guard() { if (armed) mp_halo_destroy(h); }
+    } guard{h};
     h->nneigh = nneigh;
     h->rank.assign(neigh_rank, neigh_rank + nneigh);
     h->send_off.assign(send_off, send_off + nneigh + 1);
@@ -273,6 +295,7 @@ int mp_halo_create(mp_ctx *c, int nneigh, const int32_t *neigh_rank, const int32
         MP_CUDA(cudaMemcpyAsync(h->d_send_idx, d_send_idx, sizeof(int32_t) * h->nsend, cudaMemcpyDeviceToDevice, c->stream));
         MP_CUDA(cudaMalloc(&h->d_sendbuf, sizeof(double) * h->nsend));
     }
+    guard.armed = false;
     *out = h;
     return 0;
 }
@@ -286,20 +309,119 @@ int mp_halo_exchange(mp_ctx *c, mp_halo *h, double *d_x) {
         mp::count_launch(c);
     }
     MP_NCCL(mp::g_nccl.GroupStart());
-    for (int k = 0; k < h->nneigh; ++k) {
+    int first_err = 0;   // the group is always closed, whatever a Send/Recv returns
+    for (int k = 0; k < h->nneigh && !first_err; ++k) {
         int32_t ns = h->send_off[k + 1] - h->send_off[k];
-        if (ns > 0) MP_NCCL(mp::g_nccl.Send(h->d_sendbuf + h->send_off[k], (size_t)ns, mp::kNcclFloat64, h->rank[k], c->nccl_comm, c->stream));
-        if (h->recv_count[k] > 0)
-            MP_NCCL(mp::g_nccl.Recv(d_x + h->recv_start[k], (size_t)h->recv_count[k], mp::kNcclFloat64, h->rank[k], c->nccl_comm, c->stream));
+        if (ns > 0) first_err = mp::g_nccl.Send(h->d_sendbuf + h->send_off[k], (size_t)ns, mp::kNcclFloat64, h->rank[k], c->nccl_comm, c->stream);
+        if (!first_err && h->recv_count[k] > 0)
+            first_err = mp::g_nccl.Recv(d_x + h->recv_start[k], (size_t)h->recv_count[k], mp::kNcclFloat64, h->rank[k], c->nccl_comm, c->stream);
     }
-    MP_NCCL(mp::g_nccl.GroupEnd());
+    const int end_err = mp::g_nccl.GroupEnd();
+    if (first_err || end_err) {
+        const int e = first_err ? first_err : end_err;
+        mp::set_error("mp_halo_exchange: NCCL error %d (%s)", e, mp::g_nccl.ErrStr ? mp::g_nccl.ErrStr(e) : "?");
+        return 3;
+    }
     return 0;
 }
 
 int mp_halo_destroy(mp_halo *h) {
     if (!h) return 0;
+    for (void *m : h->mapped) if (m) cudaIpcCloseMemHandle(m);
+    cudaFree(h->window); cudaFree(h->d_dev); cudaFree(h->d_slice_kind); cudaFree(h->d_bslices);
     cudaFree(h->d_send_idx); cudaFree(h->d_sendbuf);
     delete h;
+    return 0;
+}
+
+/* ---- peer-memory windows (CUDA IPC over NVLink): in-kernel allreduce of the Krylov scalars and halo push fused into SpMV */
+int mp_comm_peer_export(mp_ctx *c, uint8_t *handle64) {
+    MP_CHECK(c && handle64, "mp_comm_peer_export: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
+    MP_CUDA(cudaSetDevice(c->device));
+    if (!c->mbox) {
+        MP_CUDA(cudaMalloc(&c->mbox, sizeof(mp::MboxWindow)));
+        MP_CUDA(cudaMemset(c->mbox, 0, sizeof(mp::MboxWindow)));
+        MP_CUDA(cudaDeviceSynchronize());     // the zeroed window must exist before any peer can write into it
+    }
+    cudaIpcMemHandle_t hd;
+    MP_CUDA(cudaIpcGetMemHandle(&hd, c->mbox));
+    memcpy(handle64, &hd, 64);
+    return 0;
+}
+
+int mp_comm_peer_attach(mp_ctx *c, const uint8_t *handles) {
+    MP_CHECK(c && handles && c->mbox, "mp_comm_peer_attach: call mp_comm_peer_export first");
+    MP_CHECK(c->nranks >= 1 && c->nranks <= mp::kMaxRanks, "mp_comm_peer_attach: 1..%d ranks supported", mp::kMaxRanks);
+    MP_CHECK(!c->peer_attached, "mp_comm_peer_attach: already attached");
+    MP_CUDA(cudaSetDevice(c->device));
+    mp::CommDev hd;
+    memset(&hd, 0, sizeof(hd));
+    hd.nranks = c->nranks; hd.rank = c->rank; hd.seq = 1; hd.error = 0;
+    for (int r = 0; r < c->nranks; ++r) {
+        if (r == c->rank) { hd.win[r] = (mp::MboxWindow *)c->mbox; continue; }
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, handles + 64 * (size_t)r, 64);
+        void *p = nullptr;
+        MP_CUDA(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        c->mbox_mapped.push_back(p);
+        hd.win[r] = (mp::MboxWindow *)p;
+    }
+    MP_CUDA(cudaMalloc(&c->d_comm, sizeof(mp::CommDev)));
+    MP_CUDA(cudaMemcpy(c->d_comm, &hd, sizeof(hd), cudaMemcpyHostToDevice));
+    c->peer_attached = true;
+    return mp::set_peer_mode(c, true);
+}
+
+int mp_comm_peer_enabled(const mp_ctx *c) { return c && c->peer ? 1 : 0; }
+
+int mp_halo_peer_export(mp_ctx *c, mp_halo *h, int64_t nown, int64_t nghost, uint8_t *handle64) {
+    MP_CHECK(c && h && handle64 && nown >= 0 && nghost >= 0, "mp_halo_peer_export: bad argument");
+    MP_CUDA(cudaSetDevice(c->device));
+    if (!h->window) {
+        const size_t bytes = mp::kHaloHdr + sizeof(double) * 2 * (size_t)(nghost > 0 ? nghost : 1);
+        MP_CUDA(cudaMalloc(&h->window, bytes));
+        MP_CUDA(cudaMemset(h->window, 0, bytes));
+        MP_CUDA(cudaDeviceSynchronize());
+        h->nown = nown; h->nghost = nghost;
+    }
+    cudaIpcMemHandle_t hd;
+    MP_CUDA(cudaIpcGetMemHandle(&hd, h->window));
+    memcpy(handle64, &hd, 64);
+    return 0;
+}
+
+int mp_halo_peer_attach(mp_ctx *c, mp_halo *h, const uint8_t *neigh_handles, const int64_t *peer_goff, const int64_t *peer_gcap,
+                        const int32_t *peer_slot) {
+    MP_CHECK(c && h && h->window, "mp_halo_peer_attach: call mp_halo_peer_export first");
+    MP_CHECK(h->nneigh == 0 || (neigh_handles && peer_goff && peer_gcap && peer_slot), "mp_halo_peer_attach: null argument");
+    MP_CHECK(!h->peer, "mp_halo_peer_attach: already attached");
+    MP_CUDA(cudaSetDevice(c->device));
+    mp::HaloDev &d = h->h_dev;
+    memset(&d, 0, sizeof(d));
+    d.nneigh = h->nneigh; d.nsend = (int)h->nsend; d.nown = h->nown; d.nghost = h->nghost;
+    d.send_idx = h->d_send_idx;
+    for (int k = 0; k <= h->nneigh; ++k) d.send_off[k] = h->send_off[k];
+    d.gwin = (double *)((char *)h->window + mp::kHaloHdr);
+    d.flag = (unsigned long long *)h->window;
+    d.seq = 1;
+    for (int k = 0; k < h->nneigh; ++k) {
+        MP_CHECK(peer_slot[k] >= 0 && peer_slot[k] < mp::kMaxNeigh, "mp_halo_peer_attach: bad peer slot");
+        MP_CHECK(peer_goff[k] >= 0 && peer_goff[k] + (h->send_off[k + 1] - h->send_off[k]) <= peer_gcap[k],
+                 "mp_halo_peer_attach: my block does not fit neighbour %d's ghost window", h->rank[k]);
+        cudaIpcMemHandle_t ih;
+        memcpy(&ih, neigh_handles + 64 * (size_t)k, 64);
+        void *p = nullptr;
+        MP_CUDA(cudaIpcOpenMemHandle(&p, ih, cudaIpcMemLazyEnablePeerAccess));
+        h->mapped.push_back(p);
+        d.peer_gwin[k] = (double *)((char *)p + mp::kHaloHdr);
+        d.peer_goff[k] = peer_goff[k];
+        d.peer_gcap[k] = peer_gcap[k];
+        d.peer_flag[k] = (unsigned long long *)p + 2 * (size_t)peer_slot[k];
+    }
+    MP_CUDA(cudaMalloc(&h->d_dev, sizeof(mp::HaloDev)));
+    MP_CUDA(cudaMemcpy(h->d_dev, &d, sizeof(d), cudaMemcpyHostToDevice));
+    h->peer = true;
     return 0;
 }
 

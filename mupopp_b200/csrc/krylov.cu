@@ -8,86 +8,9 @@
 // the assembled system, which a tightly converged Krylov iteration reproduces.
 #include <string.h>
 
-#include "common.cuh"
+#include "reduce.cuh"
 
 namespace {
-
-constexpr int kThreads = 256;
-constexpr int kMaxBlocks = 4096;  // partial sums per reduction slot
-constexpr int kMaxRestart = 4;    // residual-replacement restarts of the Krylov recurrences
-inline int64_t cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
-
-// device scalar slots
-// layout: (S_A0,S_RR) and (S_RR,S_A1) are contiguous pairs so that the ping-ponged recurrence scalar and
-// the residual norm travel in ONE allreduce per reduction point on multi-GPU runs.
-enum {
-    S_BB = 0, S_TOL2 = 1, S_ITER = 2,
-    S_A0 = 3, S_RR = 4, S_A1 = 5,       // A0/A1: r.z (CG) or rhat.r (BiCGStab), ping-pong
-    S_PQ = 6,                           // p.Ap (CG)  /  rhat.v (BiCGStab)
-    S_TS = 7, S_TT = 8,                 // BiCGStab t.s, t.t
-    S_TMP0 = 9,
-    S_NCOL = 10,                        // GMRES: Givens columns completed in the current cycle
-    S_COUNT = 16
-};
-constexpr int S_RZ0 = S_A0, S_RZ1 = S_A1, S_RHO0 = S_A0, S_RHO1 = S_A1, S_RV = S_PQ;
-
-__device__ __forceinline__ double safe_div(double a, double b) { return b == 0.0 ? 0.0 : a / b; }
-
-// Block-level sum of NR accumulators, partials to global, the last block to arrive adds the partials in a
-// fixed order and stores the results: no floating-point atomics => bitwise reproducible for a given grid.
-// Multi-GPU: rank-local sums go to the LOCAL copy of the scalar block (offset counter[1] = kLocalOff) and an out-of-place
-// ncclAllReduce(local -> global) follows; kernels only ever READ the global copy.  This keeps the allreduce idempotent when the
-// producing kernel has become a no-op after convergence (an in-place allreduce would multiply the stale value by nranks).
-template <int NR>
-__device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restrict__ partials, unsigned int *counter,
-                                            double *__restrict__ scal, const int (&slots)[NR], bool bump_iter, bool use_off = true) {
-    __shared__ double sm[NR][kThreads / 32];
-    __shared__ bool last;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        double v = acc[r];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sm[r][w] = v;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int r = 0; r < NR; ++r) {
-            double v = 0.0;
-            for (int k = 0; k < kThreads / 32; ++k) v += sm[r][k];
-            partials[r * kMaxBlocks + blockIdx.x] = v;
-        }
-        __threadfence();
-        unsigned int t = atomicAdd(counter, 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-#pragma unroll
-    for (int r = 0; r < NR; ++r) {
-        double v = 0.0;
-        for (int k = threadIdx.x; k < (int)gridDim.x; k += kThreads) v += __ldcg(&partials[r * kMaxBlocks + k]);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        __syncthreads();
-        if (lane == 0) sm[r][w] = v;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s = 0.0;
-            for (int k = 0; k < kThreads / 32; ++k) s += sm[r][k];
-            scal[slots[r] + (use_off ? (int)counter[1] : 0)] = s;
-        }
-    }
-    if (threadIdx.x == 0) {
-        *counter = 0u;
-        if (bump_iter) scal[S_ITER] += 1.0;
-    }
-}
-
-__device__ __forceinline__ bool solver_active(const double *scal) { return scal[S_RR] > scal[S_TOL2]; }
 
 // ------------------------------------------------------------------ SpMV: S lanes per row
 // DOT: 0 none | 1: slot0 = sum w[row]*y[row] | 2: slot0 = sum y*w, slot1 = sum y*y
@@ -95,7 +18,7 @@ template <int S, int DOT, bool GUARD>
 __global__ void __launch_bounds__(kThreads)
 k_spmv(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
        const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
-       unsigned int *counter, double *scal, int slot0, int slot1) {
+       mp::ReduceCtl *ctl, double *scal, int slot0, int slot1) {
     if (GUARD && !solver_active(scal)) return;
     constexpr int RPW = 32 / S;  // rows per warp per pass
     const int lane = threadIdx.x & 31, sub = lane / S, sl = lane % S;
@@ -120,8 +43,8 @@ k_spmv(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restri
             if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
         }
     }
-    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, counter, scal, sl_, false); }
-    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, ctl, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
 }
 
 
@@ -133,7 +56,7 @@ template <int DOT, bool GUARD>
 __global__ void __launch_bounds__(kThreads)
 k_spmv_stream(int64_t nrow, int rpb, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
               const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
-              double *partials, unsigned int *counter, double *scal, int slot0, int slot1) {
+              double *partials, mp::ReduceCtl *ctl, double *scal, int slot0, int slot1) {
     if (GUARD && !solver_active(scal)) return;
     extern __shared__ double prod[];
     double acc[DOT == 0 ? 1 : DOT];
@@ -158,8 +81,8 @@ k_spmv_stream(int64_t nrow, int rpb, const int32_t *__restrict__ rowptr, const i
         }
         __syncthreads();
     }
-    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, counter, scal, sl_, false); }
-    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, ctl, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
 }
 
 // ------------------------------------------------------------------ SpMV, warp-stream variant (short regular rows: P1 operators)
@@ -172,7 +95,7 @@ template <int MAXJ, int DOT, bool GUARD>
 __global__ void __launch_bounds__(kThreads)
 k_spmv_warp(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
             const double *__restrict__ vals, const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w,
-            double *partials, unsigned int *counter, double *scal, int slot0, int slot1) {
+            double *partials, mp::ReduceCtl *ctl, double *scal, int slot0, int slot1) {
     if (GUARD && !solver_active(scal)) return;
     extern __shared__ double smem_d[];
     const int lane = threadIdx.x & 31;
@@ -213,8 +136,8 @@ k_spmv_warp(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__r
         }
         __syncwarp();
     }
-    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, counter, scal, sl_, false); }
-    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, ctl, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
 }
 
 // ------------------------------------------------------------------ SpMV, SELL-32 (production kernel for P1 operators)
@@ -226,7 +149,7 @@ template <int DOT, bool GUARD>
 __global__ void __launch_bounds__(kThreads, 8)
 k_spmv_sell(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *__restrict__ scol, const double *__restrict__ sval,
             const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
-            unsigned int *counter, double *scal, int slot0, int slot1) {
+            mp::ReduceCtl *ctl, double *scal, int slot0, int slot1) {
     if (GUARD && !solver_active(scal)) return;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -248,8 +171,111 @@ k_spmv_sell(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *_
             if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
         }
     }
-    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, counter, scal, sl_, false); }
-    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, counter, scal, sl_, false); }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, ctl, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
+}
+
+// ------------------------------------------------------------------ SELL-32 SpMV fused with the halo exchange over peer memory
+// Multi-GPU production kernel (peer mode).  One launch does what k_pack + ncclSend/ncclRecv + k_spmv_sell did:
+//   1. the first blocks PUSH this rank's interface values of x straight into the neighbours' ghost windows (plain stores over
+//      NVLink into CUDA-IPC mapped memory), the last pusher releases a sequence-number flag in every neighbour's window;
+//   2. every warp multiplies its INTERIOR slices (no ghost column) while those stores are in flight;
+//   3. warps that own boundary slices wait for the neighbours' flags and multiply them, reading ghost columns (col >= nown)
+//      from the local ghost window.  Ghost windows are double-buffered by the parity of the push number: a neighbour starts
+//      push s+1 only after its own SpMV s, for which it needed MY push s, which I issue after finishing SpMV s-1.
+// Row sums and dot partials are accumulated in the same fixed order on every run (interior slices ascending, then the boundary
+// list ascending), so results stay bitwise reproducible.
+template <int DOT, bool GUARD>
+__global__ void __launch_bounds__(kThreads, 8)
+k_spmv_sell_peer(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *__restrict__ scol, const double *__restrict__ sval,
+                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
+                 mp::ReduceCtl *ctl, double *scal, int slot0, int slot1, mp::HaloDev *H) {
+    if (GUARD && !solver_active(scal)) return;
+    const unsigned long long seq = H->seq;            // bumped by the last block to finish, i.e. after every block has read it
+    const int par = (int)(seq & 1ull);
+    const int lane = threadIdx.x & 31;
+    // ---- 1. push
+    const int nsend = H->nsend, nneigh = H->nneigh;
+    const int npb = min((int)gridDim.x, max(1, (nsend + kThreads - 1) / kThreads));
+    if ((int)blockIdx.x < npb) {
+        for (int t = blockIdx.x * kThreads + threadIdx.x; t < nsend; t += npb * kThreads) {
+            int k = 0;
+            while (t >= H->send_off[k + 1]) ++k;
+            H->peer_gwin[k][(int64_t)par * H->peer_gcap[k] + H->peer_goff[k] + (t - H->send_off[k])] = x[H->send_idx[t]];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int old = atomicAdd(&ctl->push_count, 1u);
+            if (old == (unsigned int)npb - 1u) {
+                ctl->push_count = 0u;
+                __threadfence_system();               // the other pushers' fenced stores are ordered before the flags below
+                for (int k = 0; k < nneigh; ++k) st_release_sys(H->peer_flag[k] + par, seq);
+            }
+        }
+    }
+    // ---- 2. interior slices
+    const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
+    const int64_t nslice = (nrow + 31) >> 5;
+    const uint8_t *__restrict__ kind = H->slice_kind;
+    double acc[DOT == 0 ? 1 : DOT];
+#pragma unroll
+    for (int r = 0; r < (DOT == 0 ? 1 : DOT); ++r) acc[r] = 0.0;
+    (void)acc;
+    for (int64_t s = warp; s < nslice; s += nwarp) {
+        if (kind[s]) continue;
+        const int32_t b = sliceptr[s], e = sliceptr[s + 1];
+        double sum = 0.0;
+#pragma unroll 4
+        for (int32_t k = b + lane; k < e; k += 32) sum += sval[k] * x[scol[k]];
+        const int64_t row = (s << 5) + lane;
+        if (row < nrow) {
+            y[row] = sum;
+            if constexpr (DOT == 1) acc[0] += w[row] * sum;
+            if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
+        }
+    }
+    // ---- 3. boundary slices (handed to the warps from the top end: those got one interior slice fewer)
+    const int64_t rwarp = nwarp - 1 - warp;
+    const int32_t nb = H->nbslice;
+    if (rwarp < nb) {
+        int ok = 1;
+        if (lane == 0)
+            for (int k = 0; k < nneigh; ++k) ok &= wait_flag(H->flag + 2 * k + par, seq) ? 1 : 0;
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok && lane == 0) scal[S_RR] = __longlong_as_double(0x7ff8000000000000ll);   // dead neighbour: the host sees a NaN residual
+        const int64_t nown = H->nown;
+        const double *__restrict__ gw = H->gwin + (int64_t)par * H->nghost - nown;
+        for (int64_t i = rwarp; i < nb; i += nwarp) {
+            const int64_t s = H->bslices[i];
+            const int32_t b = sliceptr[s], e = sliceptr[s + 1];
+            double sum = 0.0;
+#pragma unroll 2
+            for (int32_t k = b + lane; k < e; k += 32) {
+                const int32_t c = scol[k];
+                const double xv = c < nown ? x[c] : __ldcg(gw + c);      // ghost data arrived during this kernel: read it from L2
+                sum += sval[k] * xv;
+            }
+            const int64_t row = (s << 5) + lane;
+            if (row < nrow) {
+                y[row] = sum;
+                if constexpr (DOT == 1) acc[0] += w[row] * sum;
+                if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
+            }
+        }
+    }
+    // ---- 4. completion: the last block to get here opens the next push number
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int old = atomicAdd(&ctl->done_count, 1u);
+        if (old == gridDim.x - 1) {
+            ctl->done_count = 0u;
+            H->seq = seq + 1ull;
+        }
+    }
+    if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, ctl, scal, sl_, false); }
+    if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
 }
 
 // ------------------------------------------------------------------ BLAS-1
@@ -264,11 +290,11 @@ __global__ void __launch_bounds__(kThreads) k_vmul(int64_t n, double a, const do
 }
 
 __global__ void __launch_bounds__(kThreads) k_dot(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
-                                                  double *partials, unsigned int *counter, double *scal, int slot) {
+                                                  double *partials, mp::ReduceCtl *ctl, double *scal, int slot) {
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) acc[0] += x[i] * y[i];
     const int sl_[1] = {slot};
-    grid_reduce<1>(acc, partials, counter, scal, sl_, false);
+    grid_reduce<1>(acc, partials, ctl, scal, sl_, false);
 }
 
 __global__ void __launch_bounds__(kThreads) k_jacobi_setup(int64_t nrow, const int32_t *__restrict__ rowptr,
@@ -286,7 +312,7 @@ __global__ void __launch_bounds__(kThreads) k_jacobi_setup(int64_t nrow, const i
 __global__ void __launch_bounds__(kThreads) k_init_residual(int64_t n, const double *__restrict__ b, const double *__restrict__ q,
                                                             const double *__restrict__ dinv, double *__restrict__ r,
                                                             double *__restrict__ p, double *__restrict__ rhat, double *partials,
-                                                            unsigned int *counter, double *scal, int slot_rz) {
+                                                            mp::ReduceCtl *ctl, double *scal, int slot_rz) {
     double acc[3] = {0.0, 0.0, 0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
         const double bi = b[i], ri = bi - q[i];
@@ -299,14 +325,14 @@ __global__ void __launch_bounds__(kThreads) k_init_residual(int64_t n, const dou
         acc[2] += rhat ? ri * ri : ri * zi;
     }
     const int sl_[3] = {S_BB, S_RR, slot_rz};
-    grid_reduce<3>(acc, partials, counter, scal, sl_, false);
+    grid_reduce<3>(acc, partials, ctl, scal, sl_, false);
 }
 
 // CG: alpha = rz/pq ; x += alpha p ; r -= alpha q ; rz' = r.(dinv r) ; rr = r.r ; iter++
 // (4 independent element groups per thread and trip => 20 loads in flight per thread)
 __global__ void __launch_bounds__(kThreads) k_cg_update(int64_t n, const double *__restrict__ p, const double *__restrict__ q,
                                                         const double *__restrict__ dinv, double *__restrict__ x,
-                                                        double *__restrict__ r, double *partials, unsigned int *counter,
+                                                        double *__restrict__ r, double *partials, mp::ReduceCtl *ctl,
                                                         double *scal, int rz_cur, int rz_nxt) {
     if (!solver_active(scal)) return;
     const double alpha = safe_div(scal[rz_cur], scal[S_PQ]);
@@ -332,7 +358,7 @@ __global__ void __launch_bounds__(kThreads) k_cg_update(int64_t n, const double 
         }
     }
     const int sl_[2] = {rz_nxt, S_RR};
-    grid_reduce<2>(acc, partials, counter, scal, sl_, true);
+    grid_reduce<2>(acc, partials, ctl, scal, sl_, true);
 }
 
 // CG: beta = rz'/rz ; p = dinv r + beta p
@@ -387,7 +413,7 @@ __global__ void __launch_bounds__(kThreads) k_bicg_s(int64_t n, const double *__
 __global__ void __launch_bounds__(kThreads) k_bicg_x(int64_t n, const double *__restrict__ y, const double *__restrict__ z,
                                                      const double *__restrict__ s, const double *__restrict__ t,
                                                      const double *__restrict__ rhat, double *__restrict__ x, double *__restrict__ r,
-                                                     double *partials, unsigned int *counter, double *scal, int rho_cur, int rho_nxt) {
+                                                     double *partials, mp::ReduceCtl *ctl, double *scal, int rho_cur, int rho_nxt) {
     if (!solver_active(scal)) return;
     const double alpha = safe_div(scal[rho_cur], scal[S_RV]);
     const double omega = safe_div(scal[S_TS], scal[S_TT]);
@@ -400,7 +426,7 @@ __global__ void __launch_bounds__(kThreads) k_bicg_x(int64_t n, const double *__
         acc[1] += ri * ri;
     }
     const int sl_[2] = {rho_nxt, S_RR};
-    grid_reduce<2>(acc, partials, counter, scal, sl_, true);
+    grid_reduce<2>(acc, partials, ctl, scal, sl_, true);
 }
 
 
@@ -433,7 +459,7 @@ __global__ void __launch_bounds__(kThreads) k_cheb_step(int64_t n, double c1, do
 // general-preconditioner CG: x += alpha p ; r -= alpha q ; rr ; iter++
 __global__ void __launch_bounds__(kThreads) k_cgp_update(int64_t n, const double *__restrict__ p, const double *__restrict__ q,
                                                          double *__restrict__ x, double *__restrict__ r, double *partials,
-                                                         unsigned int *counter, double *scal, int rz_cur) {
+                                                         mp::ReduceCtl *ctl, double *scal, int rz_cur) {
     if (!solver_active(scal)) return;
     const double alpha = safe_div(scal[rz_cur], scal[S_PQ]);
     double acc[1] = {0.0};
@@ -444,17 +470,17 @@ __global__ void __launch_bounds__(kThreads) k_cgp_update(int64_t n, const double
         acc[0] += ri * ri;
     }
     const int sl_[1] = {S_RR};
-    grid_reduce<1>(acc, partials, counter, scal, sl_, true);
+    grid_reduce<1>(acc, partials, ctl, scal, sl_, true);
 }
 
 // rz' = r.z  (guarded: the slot keeps its value once converged)
 __global__ void __launch_bounds__(kThreads) k_cgp_rz(int64_t n, const double *__restrict__ r, const double *__restrict__ z,
-                                                     double *partials, unsigned int *counter, double *scal, int slot) {
+                                                     double *partials, mp::ReduceCtl *ctl, double *scal, int slot) {
     if (!solver_active(scal)) return;
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) acc[0] += r[i] * z[i];
     const int sl_[1] = {slot};
-    grid_reduce<1>(acc, partials, counter, scal, sl_, false);
+    grid_reduce<1>(acc, partials, ctl, scal, sl_, false);
 }
 
 // p = z + beta p   (first == 1: p = z)
@@ -514,7 +540,7 @@ int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double
         if (cap > kMaxBlocks) cap = kMaxBlocks;
         const int g = (int)(nblk < cap ? nblk : cap);
         k_spmv_sell<DOT, GUARD><<<g, kThreads, 0, ctx->stream>>>(A->nrow, A->d_sell_sliceptr, A->d_sell_col, A->d_sell_val, x, y, w,
-                                                                  ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1);
+                                                                  ctx->d_partials, ctx->d_ctl, ctx->d_scalars, slot0, slot1);
         if (timed) {
             cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
             ctx->tev_used += 2;
@@ -540,7 +566,7 @@ int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double
                 attr_set = true;                                                                                            \
             }                                                                                                               \
             k_spmv_warp<MJ, DOT, GUARD><<<g, kThreads, smem, ctx->stream>>>(A->nrow, A->d_rowptr, A->d_colidx, A->d_vals, x, y, w, \
-                                                                             ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1); \
+                                                                             ctx->d_partials, ctx->d_ctl, ctx->d_scalars, slot0, slot1); \
         } while (0)
         if (maxj == 8) LW(8); else if (maxj == 16) LW(16); else LW(32);
 #undef LW
@@ -561,7 +587,7 @@ int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double
         int64_t cap = (int64_t)ctx->num_sm * 8;
         int g = (int)(nblk < cap ? nblk : cap);
         k_spmv_stream<DOT, GUARD><<<g, kThreads, smem, ctx->stream>>>(A->nrow, rpb, A->d_rowptr, A->d_colidx, A->d_vals, x, y, w,
-                                                                       ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1);
+                                                                       ctx->d_partials, ctx->d_ctl, ctx->d_scalars, slot0, slot1);
         if (timed) {
             cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
             ctx->tev_used += 2;
@@ -572,7 +598,7 @@ int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double
     }
 #define L(S_)                                                                                                           \
     k_spmv<S_, DOT, GUARD><<<grid, kThreads, 0, ctx->stream>>>(A->nrow, A->d_rowptr, A->d_colidx, A->d_vals, x, y, w,  \
-                                                                ctx->d_partials, ctx->d_counter, ctx->d_scalars, slot0, slot1)
+                                                                ctx->d_partials, ctx->d_ctl, ctx->d_scalars, slot0, slot1)
     switch (lanes) {
         case 2: L(2); break;
         case 4: L(4); break;
@@ -590,6 +616,34 @@ int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double
     return 0;
 }
 
+// y = A x with the ghost update of x: peer mode = ONE kernel (push + interior + wait + boundary, k_spmv_sell_peer);
+// otherwise k_pack + grouped ncclSend/ncclRecv followed by the single-GPU kernels.
+template <int DOT, bool GUARD>
+int spmv_halo(mp_ctx *ctx, const mp_csr *A, mp_halo *halo, int lanes, double *x, double *y, const double *w, int slot0, int slot1) {
+    const bool sell = A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0;
+    if (halo && halo->peer && halo->nneigh > 0 && ctx->nranks > 1 && ctx->peer && sell && A->nrow > 0 && halo->nown == A->nrow) {
+        MP_TRY(mp::halo_classify(ctx, halo, A->nrow, A->d_sell_sliceptr, A->d_sell_col));
+        const bool timed = ctx->timing && ctx->tev_used + 2 <= ctx->tev.size();
+        if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
+        const int64_t nslice = (A->nrow + 31) / 32;
+        int64_t nblk = (nslice + (kThreads / 32) - 1) / (kThreads / 32);
+        int64_t cap = (int64_t)ctx->num_sm * 8;
+        if (cap > kMaxBlocks) cap = kMaxBlocks;
+        const int g = (int)(nblk < cap ? nblk : cap);
+        k_spmv_sell_peer<DOT, GUARD><<<g, kThreads, 0, ctx->stream>>>(A->nrow, A->d_sell_sliceptr, A->d_sell_col, A->d_sell_val, x, y, w,
+                                                                       ctx->d_partials, ctx->d_ctl, ctx->d_scalars, slot0, slot1, halo->d_dev);
+        if (timed) {
+            cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
+            ctx->tev_used += 2;
+        }
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        return 0;
+    }
+    MP_TRY(mp_halo_exchange(ctx, halo, x));
+    return launch_spmv<DOT, GUARD>(ctx, A, lanes, x, y, w, slot0, slot1);
+}
+
 int nnz_of(mp_ctx *ctx, const mp_csr *A, int64_t *nnz) {
     (void)ctx;
     *nnz = A->nnz;
@@ -598,13 +652,22 @@ int nnz_of(mp_ctx *ctx, const mp_csr *A, int64_t *nnz) {
 
 // rank-local slot values (written at +kLocalOff by grid_reduce) -> global slots on every rank; no-op on one GPU
 int reduce_slots(mp_ctx *ctx, int slot, int count) {
-    if (ctx->nranks <= 1) return 0;
+    if (ctx->nranks <= 1 || ctx->peer) return 0;   // peer mode: grid_reduce has already allreduced inside the kernel
     return mp::allreduce_oop(ctx, ctx->d_scalars + mp::kLocalOff + slot, ctx->d_scalars + slot, count);
 }
 
+}  // namespace
+int mp::reduce_slots_public(mp_ctx *ctx, int slot, int count) { return reduce_slots(ctx, slot, count); }
+namespace {
+
 int poll(mp_ctx *ctx) {
     MP_CUDA(cudaMemcpyAsync(ctx->h_scalars, ctx->d_scalars, sizeof(double) * S_COUNT, cudaMemcpyDeviceToHost, ctx->stream));
+    int *h_err = reinterpret_cast<int *>(ctx->h_scalars + 48);
+    *h_err = 0;
+    if (ctx->peer && ctx->d_comm)
+        MP_CUDA(cudaMemcpyAsync(h_err, &ctx->d_comm->error, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    MP_CHECK(*h_err == 0, "peer-memory exchange timed out: a neighbouring rank stopped answering");
     return 0;
 }
 
@@ -617,7 +680,7 @@ int check_csr(const mp_csr *A, bool for_solver = true) {
 
 // first == true: set the tolerance from ||b|| and zero the iteration counter (one synchronising poll per solve);
 // first == false (restart): only test the freshly evaluated TRUE residual against the stored tolerance.
-int start_solve(mp_ctx *ctx, mp_solve_info *info, bool first, bool *done) {
+int start_solve(mp_ctx *ctx, mp_solve_info *info, bool first, bool *done, bool *zero_rhs = nullptr) {
     MP_TRY(reduce_slots(ctx, S_BB, 1));
     MP_TRY(reduce_slots(ctx, S_RR, 1));
     MP_TRY(poll(ctx));
@@ -634,8 +697,17 @@ int start_solve(mp_ctx *ctx, mp_solve_info *info, bool first, bool *done) {
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
     info->niter = 0;
     info->relres = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    if (zero_rhs) *zero_rhs = !(bb > 0.0);
     *done = !(rr > tol * tol);
     info->converged = *done ? 1 : 0;
+    return 0;
+}
+
+// ||b|| == 0 (allreduced, so every rank agrees): the solution is x = 0.  Without this the relative test has tolerance 0 and the
+// recurrence would spin to maxit from a non-zero initial guess (PETSc avoids it with its absolute floor atol = 1e-50).
+int zero_solution(mp_ctx *ctx, double *d_x, int64_t n, mp_solve_info *info) {
+    MP_CUDA(cudaMemsetAsync(d_x, 0, sizeof(double) * (size_t)n, ctx->stream));
+    info->niter = 0; info->converged = 1; info->relres = 0.0;
     return 0;
 }
 
@@ -679,7 +751,7 @@ __global__ void __launch_bounds__(kThreads) k_gmres_start(int64_t n, const doubl
 
 // out[k0+v] = V_{k0+v} . w   for v < cnt <= 8
 __global__ void __launch_bounds__(kThreads) k_multidot8(int64_t n, const double *__restrict__ V, int64_t ld, int k0, int cnt,
-                                                        const double *__restrict__ w, double *partials, unsigned int *counter,
+                                                        const double *__restrict__ w, double *partials, mp::ReduceCtl *ctl,
                                                         double *out, const double *scal) {
     if (!solver_active(scal)) return;
     double acc[8];
@@ -692,14 +764,14 @@ __global__ void __launch_bounds__(kThreads) k_multidot8(int64_t n, const double 
             if (v < cnt) acc[v] += V[(int64_t)(k0 + v) * ld + i] * wi;
     }
     const int sl_[8] = {k0, k0 + 1, k0 + 2, k0 + 3, k0 + 4, k0 + 5, k0 + 6, k0 + 7};
-    grid_reduce<8>(acc, partials, counter, out, sl_, false, false);
+    grid_reduce<8>(acc, partials, ctl, out, sl_, false, false);
 }
 
 // w -= sum_{k<=j} h[k] V_k ; optionally slot S_TMP0 = ||w||^2
 template <bool NORM>
 __global__ void __launch_bounds__(kThreads) k_gmres_orth(int64_t n, const double *__restrict__ V, int64_t ld, int j,
                                                          const double *__restrict__ h, double *__restrict__ w, double *partials,
-                                                         unsigned int *counter, double *scal) {
+                                                         mp::ReduceCtl *ctl, double *scal) {
     if (!solver_active(scal)) return;
     double acc[1] = {0.0};
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
@@ -710,7 +782,7 @@ __global__ void __launch_bounds__(kThreads) k_gmres_orth(int64_t n, const double
     }
     if (NORM) {
         const int sl_[1] = {S_TMP0};
-        grid_reduce<1>(acc, partials, counter, scal, sl_, false);
+        grid_reduce<1>(acc, partials, ctl, scal, sl_, false);
     }
 }
 
@@ -805,9 +877,8 @@ extern "C" int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv
     int total = 0;
     for (int cycle = 0; cycle < 100000; ++cycle) {
         // true residual r = b - A x at the start of every cycle
-        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
-        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, w, nullptr, 0, 0)));
-        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, w, d_dinv, r, nullptr, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_TMP0);
+        MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, w, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, w, d_dinv, r, nullptr, nullptr, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_TMP0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
         bool done = false;
@@ -817,19 +888,18 @@ extern "C" int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv
         mp::count_launch(ctx);
         bool conv = false;
         for (int j = 0; j < m && total < info->maxit; ++j) {
-            MP_TRY(mp_halo_exchange(ctx, halo, z));
-            MP_TRY((launch_spmv<0, true>(ctx, A, lanes, z, w, nullptr, 0, 0)));
+            MP_TRY((spmv_halo<0, true>(ctx, A, halo, lanes, z, w, nullptr, 0, 0)));
             for (int pass = 0; pass < 2; ++pass) {   // classical Gram-Schmidt, applied twice
                 double *h = pass == 0 ? S.h1 : S.h2;
-                double *hl = ctx->nranks > 1 ? (pass == 0 ? S.h1loc : S.h2loc) : h;   // rank-local dots, then out-of-place allreduce
+                double *hl = (ctx->nranks > 1 && !ctx->peer) ? (pass == 0 ? S.h1loc : S.h2loc) : h;   // rank-local dots, then out-of-place allreduce
                 for (int k0 = 0; k0 <= j; k0 += 8) {
                     const int cnt = (j + 1 - k0) < 8 ? (j + 1 - k0) : 8;
-                    k_multidot8<<<g1, kThreads, 0, ctx->stream>>>(n, V, n, k0, cnt, w, ctx->d_partials, ctx->d_counter, hl, ctx->d_scalars);
+                    k_multidot8<<<g1, kThreads, 0, ctx->stream>>>(n, V, n, k0, cnt, w, ctx->d_partials, ctx->d_ctl, hl, ctx->d_scalars);
                     mp::count_launch(ctx);
                 }
-                if (ctx->nranks > 1) MP_TRY(mp::allreduce_oop(ctx, hl, h, j + 1));
-                if (pass == 0) k_gmres_orth<false><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_counter, ctx->d_scalars);
-                else k_gmres_orth<true><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_counter, ctx->d_scalars);
+                if (ctx->nranks > 1 && !ctx->peer) MP_TRY(mp::allreduce_oop(ctx, hl, h, j + 1));
+                if (pass == 0) k_gmres_orth<false><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_ctl, ctx->d_scalars);
+                else k_gmres_orth<true><<<g1, kThreads, 0, ctx->stream>>>(n, V, n, j, h, w, ctx->d_partials, ctx->d_ctl, ctx->d_scalars);
                 mp::count_launch(ctx);
             }
             MP_TRY(reduce_slots(ctx, S_TMP0, 1));
@@ -883,7 +953,7 @@ extern "C" int mp_vmul(mp_ctx *ctx, int64_t n, double a, const double *d_x, cons
 
 extern "C" int mp_dot(mp_ctx *ctx, int64_t n, const double *d_x, const double *d_y, double *result) {
     MP_CHECK(ctx && d_x && d_y && result && n >= 0, "mp_dot: bad argument");
-    k_dot<<<grid_for(ctx, n > 0 ? n : 1), kThreads, 0, ctx->stream>>>(n, d_x, d_y, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_TMP0);
+    k_dot<<<grid_for(ctx, n > 0 ? n : 1), kThreads, 0, ctx->stream>>>(n, d_x, d_y, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_TMP0);
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
     MP_TRY(reduce_slots(ctx, S_TMP0, 1));
@@ -920,9 +990,8 @@ extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, 
     // outer loop = residual replacement: after the recurrence says "converged" the TRUE residual b - A x is
     // evaluated and the iteration restarted from x if it is not below the tolerance yet.
     for (int restart = 0; restart <= kMaxRestart; ++restart) {
-        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
-        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, q, nullptr, 0, 0)));
-        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, p, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RZ0);
+        MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, q, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, p, nullptr, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_RZ0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
         MP_TRY(reduce_slots(ctx, S_RZ0, 1));
@@ -931,10 +1000,9 @@ extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, 
         if (done || total >= info->maxit) break;
         int cur = S_RZ0, nxt = S_RZ1;
         for (; total < info->maxit;) {
-            MP_TRY(mp_halo_exchange(ctx, halo, p));
-            MP_TRY((launch_spmv<1, true>(ctx, A, lanes, p, q, p, S_PQ, 0)));
+            MP_TRY((spmv_halo<1, true>(ctx, A, halo, lanes, p, q, p, S_PQ, 0)));
             MP_TRY(reduce_slots(ctx, S_PQ, 1));
-            k_cg_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_dinv, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
+            k_cg_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_dinv, d_x, r, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, cur, nxt);
             MP_TRY(reduce_slots(ctx, (nxt < S_RR ? nxt : S_RR), 2));
             k_cg_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, r, d_dinv, p, ctx->d_scalars, cur, nxt);
             mp::count_launch(ctx, 2);
@@ -966,9 +1034,8 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
     const int every = info->check_every > 0 ? info->check_every : 10;   // rank-independent (collective control flow)
     int total = 0;
     for (int restart = 0; restart <= kMaxRestart; ++restart) {   // residual replacement, see mp_solve_pcg
-        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
-        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, v, nullptr, 0, 0)));
-        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, v, d_dinv, r, nullptr, rhat, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_RHO0);
+        MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, v, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, v, d_dinv, r, nullptr, rhat, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_RHO0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
         MP_TRY(reduce_slots(ctx, S_RHO0, 1));
@@ -978,14 +1045,12 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
         int cur = S_RHO0, nxt = S_RHO1;
         for (int it = 0; total < info->maxit; ++it) {
             k_bicg_p<<<g1, kThreads, 0, ctx->stream>>>(n, it == 0 ? 1 : 0, r, v, d_dinv, p, y, ctx->d_scalars, cur);
-            MP_TRY(mp_halo_exchange(ctx, halo, y));
-            MP_TRY((launch_spmv<1, true>(ctx, A, lanes, y, v, rhat, S_RV, 0)));
+            MP_TRY((spmv_halo<1, true>(ctx, A, halo, lanes, y, v, rhat, S_RV, 0)));
             MP_TRY(reduce_slots(ctx, S_RV, 1));
             k_bicg_s<<<g1, kThreads, 0, ctx->stream>>>(n, r, v, d_dinv, s, z, ctx->d_scalars, cur);
-            MP_TRY(mp_halo_exchange(ctx, halo, z));
-            MP_TRY((launch_spmv<2, true>(ctx, A, lanes, z, t, s, S_TS, S_TT)));
+            MP_TRY((spmv_halo<2, true>(ctx, A, halo, lanes, z, t, s, S_TS, S_TT)));
             MP_TRY(reduce_slots(ctx, S_TS, 2));
-            k_bicg_x<<<g1, kThreads, 0, ctx->stream>>>(n, y, z, s, t, rhat, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur, nxt);
+            k_bicg_x<<<g1, kThreads, 0, ctx->stream>>>(n, y, z, s, t, rhat, d_x, r, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, cur, nxt);
             MP_TRY(reduce_slots(ctx, (nxt < S_RR ? nxt : S_RR), 2));
             mp::count_launch(ctx, 3);
             int tmp = cur; cur = nxt; nxt = tmp;
@@ -1040,8 +1105,7 @@ extern "C" int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double
         double rho0 = 1.0 / sigma;
         for (int i = 1; i < degree; ++i) {
             const double rho1 = 1.0 / (2.0 * sigma - rho0);
-            MP_TRY(mp_halo_exchange(ctx, halo, z));
-            MP_TRY((launch_spmv<0, true>(ctx, A, lanes, z, t, nullptr, 0, 0)));
+            MP_TRY((spmv_halo<0, true>(ctx, A, halo, lanes, z, t, nullptr, 0, 0)));
             k_cheb_step<<<g1, kThreads, 0, ctx->stream>>>(n, rho1 * rho0, 2.0 * rho1 / delta, r, t, d_dinv, z, d, ctx->d_scalars);
             mp::count_launch(ctx);
             rho0 = rho1;
@@ -1051,9 +1115,8 @@ extern "C" int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double
     const int every = info->check_every > 0 ? info->check_every : 10;
     int total = 0;
     for (int restart = 0; restart <= kMaxRestart; ++restart) {
-        MP_TRY(mp_halo_exchange(ctx, halo, d_x));
-        MP_TRY((launch_spmv<0, false>(ctx, A, lanes, d_x, q, nullptr, 0, 0)));
-        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, nullptr, nullptr, ctx->d_partials, ctx->d_counter, ctx->d_scalars, S_TMP0);
+        MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, q, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, nullptr, nullptr, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_TMP0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
         bool done = false;
@@ -1061,18 +1124,17 @@ extern "C" int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double
         if (done || total >= info->maxit) break;
         int cur = S_RZ0, nxt = S_RZ1;
         MP_TRY(precond());
-        k_cgp_rz<<<g1, kThreads, 0, ctx->stream>>>(n, r, z, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur);
+        k_cgp_rz<<<g1, kThreads, 0, ctx->stream>>>(n, r, z, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, cur);
         MP_TRY(reduce_slots(ctx, cur, 1));
         k_cgp_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, 1, z, p, ctx->d_scalars, cur, cur);
         mp::count_launch(ctx, 2);
         for (; total < info->maxit;) {
-            MP_TRY(mp_halo_exchange(ctx, halo, p));
-            MP_TRY((launch_spmv<1, true>(ctx, A, lanes, p, q, p, S_PQ, 0)));
+            MP_TRY((spmv_halo<1, true>(ctx, A, halo, lanes, p, q, p, S_PQ, 0)));
             MP_TRY(reduce_slots(ctx, S_PQ, 1));
-            k_cgp_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_x, r, ctx->d_partials, ctx->d_counter, ctx->d_scalars, cur);
+            k_cgp_update<<<g1, kThreads, 0, ctx->stream>>>(n, p, q, d_x, r, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, cur);
             MP_TRY(reduce_slots(ctx, S_RR, 1));
             MP_TRY(precond());
-            k_cgp_rz<<<g1, kThreads, 0, ctx->stream>>>(n, r, z, ctx->d_partials, ctx->d_counter, ctx->d_scalars, nxt);
+            k_cgp_rz<<<g1, kThreads, 0, ctx->stream>>>(n, r, z, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, nxt);
             MP_TRY(reduce_slots(ctx, nxt, 1));
             k_cgp_pupdate<<<g1, kThreads, 0, ctx->stream>>>(n, 0, z, p, ctx->d_scalars, cur, nxt);
             mp::count_launch(ctx, 3);

@@ -111,7 +111,9 @@ __global__ void k_sell_width(const int32_t *__restrict__ rowptr, int32_t nrow, i
     if (lane == 0) width32[s] = 32 * v;
 }
 
-// fill SELL columns (padding: the row itself) or values (padding: 0)
+// fill SELL columns or values.  Padding entries carry value 0 and a column that is VALID for the operator: the row's first
+// column (0 for an empty / out-of-range row), never the row index itself -- rectangular blocks (P2xP1: nrow > ncol) would
+// otherwise gather x[] past its end, and 0 * NaN/Inf from a neighbouring allocation poisons the row.
 template <bool VALS>
 __global__ void k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx, const double *__restrict__ vals,
                             int32_t nrow, int64_t nslice, const int32_t *__restrict__ sell_ptr, int32_t *__restrict__ scol,
@@ -124,7 +126,7 @@ __global__ void k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *_
     const int32_t rb = r < nrow ? rowptr[r] : 0, len = r < nrow ? rowptr[r + 1] - rb : 0;
     for (int j = 0; j < w; ++j) {
         if (VALS) sval[b + 32 * j + lane] = j < len ? vals[rb + j] : 0.0;
-        else scol[b + 32 * j + lane] = j < len ? colidx[rb + j] : (int32_t)(r < nrow ? r : 0);
+        else scol[b + 32 * j + lane] = j < len ? colidx[rb + j] : (len > 0 ? colidx[rb] : 0);
     }
 }
 
@@ -212,7 +214,59 @@ k_scatter_vector(const int32_t *__restrict__ inc_ptr, const int32_t *__restrict_
     out[r] = (beta == 0.0) ? s : beta * out[r] + s;
 }
 
+// peer-mode halo: a SELL slice is a BOUNDARY slice when any of its entries references a ghost column (col >= nown)
+__global__ void k_slice_kind(const int32_t *__restrict__ sliceptr, const int32_t *__restrict__ scol, int64_t nslice, int64_t nown,
+                             uint8_t *__restrict__ kind) {
+    const int lane = threadIdx.x & 31;
+    const int64_t s = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (s >= nslice) return;
+    int any = 0;
+    for (int32_t k = sliceptr[s] + lane; k < sliceptr[s + 1]; k += 32) any |= scol[k] >= nown ? 1 : 0;
+    any = __any_sync(0xffffffffu, any);
+    if (lane == 0) kind[s] = any ? 1 : 0;
+}
+
 }  // namespace
+
+// Slice lists of `halo` for one operator (cached on the halo by the identity of the SELL column array: the operators of a
+// timestep share one plan).  The boundary list is produced by an order-preserving selection => ascending => reproducible sums.
+int mp::halo_classify(mp_ctx *ctx, mp_halo *h, int64_t nrow, const int32_t *d_sliceptr, const int32_t *d_scol) {
+    if (h->classified_for == (const void *)d_scol) return 0;
+    MP_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t nslice = (nrow + 31) / 32;
+    cudaFree(h->d_slice_kind); cudaFree(h->d_bslices);
+    h->d_slice_kind = nullptr; h->d_bslices = nullptr;
+    MP_CUDA(cudaMalloc(&h->d_slice_kind, (size_t)(nslice > 0 ? nslice : 1)));
+    MP_CUDA(cudaMalloc(&h->d_bslices, sizeof(int32_t) * (size_t)(nslice > 0 ? nslice : 1)));
+    int32_t nb = 0;
+    if (nslice > 0) {
+        k_slice_kind<<<(unsigned)cdiv(nslice * 32, kThreads), kThreads, 0, st>>>(d_sliceptr, d_scol, nslice, h->nown, h->d_slice_kind);
+        mp::count_launch(ctx);
+        int32_t *d_n = nullptr;
+        void *tmp = nullptr;
+        MP_CUDA(cudaMalloc(&d_n, sizeof(int32_t)));
+        size_t tb = 0;
+        cub::CountingInputIterator<int32_t> ids(0);
+        cudaError_t e = cub::DeviceSelect::Flagged(nullptr, tb, ids, h->d_slice_kind, h->d_bslices, d_n, (int)nslice, st);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp, tb + 16);
+        if (e == cudaSuccess) e = cub::DeviceSelect::Flagged(tmp, tb, ids, h->d_slice_kind, h->d_bslices, d_n, (int)nslice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&nb, d_n, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(tmp); cudaFree(d_n);
+        if (e != cudaSuccess) { mp::set_error("halo_classify: %s", cudaGetErrorString(e)); return 1; }
+    }
+    h->h_dev.slice_kind = h->d_slice_kind;
+    h->h_dev.bslices = h->d_bslices;
+    h->h_dev.nbslice = nb;
+    // only the classification fields change: the sequence number lives on the device and must not be reset
+    MP_CUDA(cudaMemcpyAsync(&h->d_dev->slice_kind, &h->h_dev.slice_kind, sizeof(void *), cudaMemcpyHostToDevice, st));
+    MP_CUDA(cudaMemcpyAsync(&h->d_dev->bslices, &h->h_dev.bslices, sizeof(void *), cudaMemcpyHostToDevice, st));
+    MP_CUDA(cudaMemcpyAsync(&h->d_dev->nbslice, &h->h_dev.nbslice, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MP_CUDA(cudaStreamSynchronize(st));
+    h->classified_for = (const void *)d_scol;
+    return 0;
+}
 
 extern "C" int mp_plan_destroy(mp_plan *p) {
     if (!p) return 0;

@@ -76,6 +76,37 @@ class Context:
         check(self.lib.mp_comm_init(self.h, nranks, rank, buf), "mp_comm_init")
         self.nranks, self.rank = nranks, rank
 
+    def enable_peer(self, allgather=None):
+        """Attach the peer-memory (CUDA IPC over NVLink) mailbox windows: the Krylov inner products are then allreduced inside
+        the reducing kernels.  `allgather(obj) -> [obj of rank 0, ...]` is the host-side exchange of the 64-byte IPC handles
+        (default: torch.distributed.all_gather_object).  Returns True when the fast path is on."""
+        if allgather is None:
+            allgather = _dist_allgather
+        if self.nranks == 1:
+            allgather = lambda obj: [obj]
+        buf = (C.c_uint8 * 64)()
+        check(self.lib.mp_comm_peer_export(self.h, buf), "mp_comm_peer_export")
+        handles = allgather(bytes(buf))
+        if len(handles) != self.nranks:
+            raise _lib.MpError("enable_peer: %d handles for %d ranks" % (len(handles), self.nranks))
+        blob = (C.c_uint8 * (64 * self.nranks)).from_buffer_copy(b"".join(handles))
+        err = None
+        try:
+            check(self.lib.mp_comm_peer_attach(self.h, blob), "mp_comm_peer_attach")
+        except _lib.MpError as e:          # e.g. CUDA IPC not permitted between these processes: every rank must then stay on NCCL
+            err = str(e)
+        errs = allgather(err)
+        self._allgather = allgather
+        if any(e is not None for e in errs):
+            if err is None:
+                self.set_option("peer", 0)
+            self.peer_error = next(e for e in errs if e is not None)
+            return False
+        return self.peer_enabled()
+
+    def peer_enabled(self):
+        return bool(self.lib.mp_comm_peer_enabled(self.h))
+
     def unique_id(self) -> bytes:
         buf = (C.c_uint8 * 128)()
         check(self.lib.mp_nccl_unique_id(buf), "mp_nccl_unique_id")
@@ -274,9 +305,38 @@ class Halo:
         check(ctx.lib.mp_halo_create(ctx.h, n, arr(neigh_rank), arr(send_off), ptr(self.d_send_idx), arr(recv_start),
                                      arr(recv_count), C.byref(h)), "mp_halo_create")
         self.h = h
+        self.neigh_rank = [int(r) for r in neigh_rank]
+        self.recv_start = [int(r) for r in recv_start]
+        self.recv_count = [int(r) for r in recv_count]
 
     def exchange(self, x):
         check(self.ctx.lib.mp_halo_exchange(self.ctx.h, self.h, ptr(x)), "mp_halo_exchange")
+
+    def enable_peer(self, n_owned, n_local, allgather=None):
+        """Ghost window of this halo in peer memory: the SELL SpMV of the Krylov loops then pushes the interface values into the
+        neighbours' windows itself (no k_pack + ncclSend/ncclRecv).  Collective over all ranks."""
+        ctx = self.ctx
+        if allgather is None:
+            allgather = getattr(ctx, "_allgather", None) or _dist_allgather
+        nghost = int(n_local) - int(n_owned)
+        buf = (C.c_uint8 * 64)()
+        check(ctx.lib.mp_halo_peer_export(ctx.h, self.h, int(n_owned), nghost, buf), "mp_halo_peer_export")
+        mine = dict(handle=bytes(buf), neigh=self.neigh_rank, goff=[s - int(n_owned) for s in self.recv_start], nghost=nghost)
+        everyone = allgather(mine)
+        n = len(self.neigh_rank)
+        handles, goff, gcap, slot = b"", [], [], []
+        for q in self.neigh_rank:
+            theirs = everyone[q]
+            j = theirs["neigh"].index(ctx.rank)        # the relation is symmetric for owner-computes partitions
+            handles += theirs["handle"]
+            goff.append(theirs["goff"][j])
+            gcap.append(theirs["nghost"])
+            slot.append(j)
+        hb = (C.c_uint8 * max(64 * n, 1)).from_buffer_copy(handles if n else b"\0")
+        a64 = lambda a: (C.c_int64 * max(len(a), 1))(*[int(v) for v in a])
+        a32 = lambda a: (C.c_int32 * max(len(a), 1))(*[int(v) for v in a])
+        check(ctx.lib.mp_halo_peer_attach(ctx.h, self.h, hb, a64(goff), a64(gcap), a32(slot)), "mp_halo_peer_attach")
+        return True
 
     def __del__(self):
         try:
@@ -285,6 +345,13 @@ class Halo:
                 self.h = None
         except Exception:
             pass
+
+
+def _dist_allgather(obj):
+    import torch.distributed as dist
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
 
 
 def transport_params(Pe, Da, phi, alpha, dt, sigma, rho0, gamma, fracs, zhat, K, reaction, ncomp, supg):

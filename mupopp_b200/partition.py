@@ -136,9 +136,16 @@ def slab_boundary_data(part: SlabPartition, u_marker, u_value, c0_marker=None, c
     return make_boundary_data(part.mesh, u_marker, u_value, c0_marker, c0_value, periodic=part.periodic)
 
 
-def make_halo(ctx, part: SlabPartition):
+def make_halo(ctx, part: SlabPartition, peer=None):
+    """Halo plan of a partition.  `peer` (default: on when the context's peer-memory windows are attached) also creates the ghost
+    window that lets the SpMV kernel exchange interface dofs over NVLink by itself; collective over all ranks."""
     from .device import Halo
-    return Halo(ctx, [n[0] for n in part.neigh], [n[1] for n in part.neigh], [n[2] for n in part.neigh], [n[3] for n in part.neigh])
+    h = Halo(ctx, [n[0] for n in part.neigh], [n[1] for n in part.neigh], [n[2] for n in part.neigh], [n[3] for n in part.neigh])
+    if peer is None:
+        peer = ctx.nranks > 1 and ctx.peer_enabled()
+    if peer:
+        h.enable_peer(part.n_owned, part.n_local)
+    return h
 
 
 # ------------------------------------------------------------------ general meshes: recursive coordinate bisection

@@ -129,7 +129,7 @@ class TransportSolverF:
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
                  rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
-                 vert2dof=None, row_ordered=True, p_precond="jacobi", cheb_degree=3):
+                 vert2dof=None, row_ordered=True, p_precond="jacobi", cheb_degree=3, p_guess="extrapolate"):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
@@ -137,6 +137,8 @@ class TransportSolverF:
         # 200^3, 3-4x fewer reduction points per SpMV -- meant for multi-GPU runs; not yet the default there)
         self.p_method = "pcg_chebyshev" if p_precond == "chebyshev" else "pcg"
         self.cheb_degree = cheb_degree
+        self.p_guess = p_guess          # "extrapolate" (2 p^n - p^(n-1)) or "previous" (p^n) as the pressure PCG's initial iterate
+        self._p_hist = 0                # pressure solutions of the current time series held in (p, p_old)
         self.halo = halo
         self.dm = DeviceMesh(ctx, mesh, vert2dof)
         V, Cn, d = self.dm.ndof, self.dm.ncell, self.dm.dim
@@ -176,6 +178,7 @@ class TransportSolverF:
         # state
         self.u = ctx.zeros(Cn * d)
         self.p = ctx.zeros(V)
+        self.p_old = ctx.zeros(V)
         self.c0 = ctx.zeros(V)
         self.c1 = ctx.zeros(V)
         self.c2 = ctx.zeros(V)
@@ -184,6 +187,7 @@ class TransportSolverF:
         self.c2_new = ctx.zeros(V)
         self.rhs = ctx.zeros(self.nown)
         self.rhs2 = ctx.zeros(self.nown)
+        self.rhs_c0 = ctx.zeros(self.nown)
         self.fsrc = ctx.zeros(V) if f_source is None else ctx.to_device(np.asarray(f_source, dtype=np.float64))
         self.last = {}
 
@@ -191,6 +195,8 @@ class TransportSolverF:
         for name, v in (("c0", c0), ("c1", c1), ("c2", c2), ("p", p), ("u", u)):
             if v is not None:
                 getattr(self, name).copy_(self.ctx.to_device(np.asarray(v, dtype=np.float64).ravel()))
+                if name == "p":
+                    self._p_hist = 0     # a new time series: no extrapolation across the jump
 
     def _exchange(self, x):
         if self.halo is not None:
@@ -203,11 +209,11 @@ class TransportSolverF:
         residual, so every rank takes the same branch."""
         from ._lib import MpError
         if self.c0_method == "gmres":
-            return self.A.solve("gmres", self.rhs, self.c0_new, restart=self.gmres_restart, **kw)
+            return self.A.solve("gmres", self.rhs_c0, self.c0_new, restart=self.gmres_restart, **kw)
         kb = dict(kw)
         kb["maxit"] = min(kw["maxit"], 1000)
         try:
-            r0 = self.A.solve("bicgstab", self.rhs, self.c0_new, **kb)
+            r0 = self.A.solve("bicgstab", self.rhs_c0, self.c0_new, **kb)
             if r0.converged:
                 return r0
         except MpError as e:
@@ -215,50 +221,96 @@ class TransportSolverF:
                 raise
         self.c0_new.copy_(self.c0)
         self.fallbacks = getattr(self, "fallbacks", 0) + 1
-        return self.A.solve("gmres", self.rhs, self.c0_new, restart=max(self.gmres_restart, 100), **kw)   # long recurrences: robust
+        return self.A.solve("gmres", self.rhs_c0, self.c0_new, restart=max(self.gmres_restart, 100), **kw)   # long recurrences: robust
 
-    def step(self):
+    # ---- the pieces of one step (step() runs them in order; the at-size parity tests call them one by one)
+    def assemble_reaction_rows(self):
+        """rhs / rhs2 <- loads of the c1 (, c2) consistent-mass rows from the state (c0, c1, c2)."""
         ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
         three = self.model.ncomp == 3
-        kw = dict(rtol=self.rtol, maxit=self.maxit, halo=self.halo, check_every=self.check_every, refresh_jacobi=False)
-        # 1. c1 (, c2): consistent-mass solves with the reaction load
         check(lib.mp_elem_p1_reaction_rhs(ctx.h, C.byref(m), C.byref(prm), ptr(self.c0), ptr(self.c1), ptr(self.c2) if three else None,
                                           ptr(self.evec), ptr(self.evec2) if three else None), "mp_elem_p1_reaction_rhs")
         self.plan.scatter_vector(self.evec, self.rhs)
-        self.c1_new.copy_(self.c1)
-        r1 = self.M.solve("pcg", self.rhs, self.c1_new, **kw)
-        self._exchange(self.c1_new)
-        r2 = None
         if three:
             self.plan.scatter_vector(self.evec2, self.rhs2)
-            self.c2_new.copy_(self.c2)
-            r2 = self.M.solve("pcg", self.rhs2, self.c2_new, **kw)
-            self._exchange(self.c2_new)
-        # 2. c0: CN + SUPG with the lagged velocity u^n
+
+    def assemble_c0_row(self):
+        """A, rhs <- Crank-Nicolson + SUPG row with the lagged velocity u^n and the NEW c1 (, c2); Dirichlet rows eliminated."""
+        ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
+        three = self.model.ncomp == 3
         check(lib.mp_elem_p1_transport(ctx.h, C.byref(m), C.byref(prm), ptr(self.u), ptr(self.c0), ptr(self.c1),
                                        ptr(self.c2) if three else None, ptr(self.c1_new), ptr(self.c2_new) if three else None,
                                        ptr(self.fsrc), ptr(self.emat), ptr(self.evec)), "mp_elem_p1_transport")
         self.plan.scatter_matrix(self.emat, self.A)
-        self.plan.scatter_vector(self.evec, self.rhs)
-        self.A.apply_dirichlet(self.rhs, self.c0_isbc, self.c0_g)
+        self.plan.scatter_vector(self.evec, self.rhs_c0)
+        self.A.apply_dirichlet(self.rhs_c0, self.c0_isbc, self.c0_g)
         self.A.jacobi_setup()
-        self.c0_new.copy_(self.c0)
-        r0 = self._solve_c0(kw)
-        self._exchange(self.c0_new)
-        # 3. pressure with the NEW c0, warm start from p^n
+
+    def assemble_pressure_rhs(self):
+        """rhs <- buoyancy load with the NEW c0 minus the prescribed boundary flux, p = 0 rows eliminated (the operator L is constant)."""
+        ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
         check(lib.mp_elem_p1_pressure_rhs(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.c0_new), ptr(self.evec)),
               "mp_elem_p1_pressure_rhs")
         self.plan.scatter_vector(self.evec, self.rhs)
         ctx.axpby(-1.0, self.flux_load[: self.nown], 1.0, self.rhs)
         self.L.apply_dirichlet(self.rhs, self.p_isbc, self.zeros_loc, matrix=False)
-        rp = self.L.solve(self.p_method, self.rhs, self.p, cheb_degree=self.cheb_degree, **kw)
-        self._exchange(self.p)
-        # 4. velocity recovery, then rotate the state
+
+    def recover_velocity(self):
+        ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
         check(lib.mp_recover_velocity(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.p), ptr(self.c0_new), ptr(self.u)),
               "mp_recover_velocity")
+
+    def step(self):
+        three = self.model.ncomp == 3
+        kw = dict(rtol=self.rtol, maxit=self.maxit, halo=self.halo, check_every=self.check_every, refresh_jacobi=False)
+        # 1. c1 (, c2): consistent-mass solves with the reaction load
+        self.assemble_reaction_rows()
+        self.c1_new.copy_(self.c1)
+        r1 = self.M.solve("pcg", self.rhs, self.c1_new, **kw)
+        self._exchange(self.c1_new)
+        r2 = None
+        if three:
+            self.c2_new.copy_(self.c2)
+            r2 = self.M.solve("pcg", self.rhs2, self.c2_new, **kw)
+            self._exchange(self.c2_new)
+        # 2. c0: CN + SUPG with the lagged velocity u^n
+        self.assemble_c0_row()
+        self.c0_new.copy_(self.c0)
+        r0 = self._solve_c0(kw)
+        self._exchange(self.c0_new)
+        # 3. pressure with the NEW c0.  Initial guess: p^n, or the linear extrapolation 2 p^n - p^(n-1) once two solutions of THIS
+        #    time series exist (fewer PCG iterations for the same answer: the tolerance is relative to ||b||, not to the guess)
+        self.assemble_pressure_rhs()
+        if self.p_guess == "extrapolate" and self._p_hist >= 2:
+            self.p_old.mul_(-1.0).add_(self.p, alpha=2.0)            # p_old <- 2 p^n - p^(n-1): becomes the iterate
+            self.p, self.p_old = self.p_old, self.p
+        else:
+            self.p_old.copy_(self.p)
+        rp = self.L.solve(self.p_method, self.rhs, self.p, cheb_degree=self.cheb_degree, **kw)
+        self._p_hist += 1
+        self._exchange(self.p)
+        # 4. velocity recovery, then rotate the state
+        self.recover_velocity()
         self.c0, self.c0_new = self.c0_new, self.c0
         self.c1, self.c1_new = self.c1_new, self.c1
         if three:
             self.c2, self.c2_new = self.c2_new, self.c2
         self.last = dict(c1=r1, c2=r2, c0=r0, p=rp)
         return self.last
+
+    def true_residuals(self):
+        """||b - A x|| / ||b|| of the LAST c0 and p solves, recomputed with one SpMV each (bench.py reports them; owned rows,
+        allreduced over ranks).  Call right after step(): A / L / rhs still hold the p system, the c0 system is re-assembled."""
+        ctx = self.ctx
+        out = {}
+        tmp = ctx.zeros(self.nown)
+
+        def relres(A, b, x):
+            self._exchange(x)
+            A.spmv(x, tmp)
+            ctx.axpby(1.0, b, -1.0, tmp)
+            return float(np.sqrt(ctx.dot(tmp, tmp) / max(ctx.dot(b, b), 1e-300)))
+
+        out["p"] = relres(self.L, self.rhs, self.p)
+        out["c0"] = relres(self.A, self.rhs_c0, self.c0)          # the state was rotated: c0 is the solution of the last c0 row
+        return out

@@ -178,60 +178,62 @@ def make_bcs_periodic(mesh, axes, dof, u_pred, u_value, c0_pred=None, c0_value=0
     return BCsF(p_dofs=p_dofs.astype(np.int64), flux_load=flux, c0_dofs=c0_dofs.astype(np.int64), c0_vals=c0_vals)
 
 
+class StepSystems:
+    """The linear systems of ONE mode-F timestep from state `prev`, built lazily in solve order: c1, c2 (mass rows), c0 (needs the
+    new c1, c2), p (needs the new c0).  `step` solves them; the at-size GPU parity tests only ASSEMBLE them and check that the GPU
+    fields satisfy them (residual parity needs no CPU solve, so it reaches sizes where a CPU solve takes minutes).
+    `P`: periodic prolongation (V x ndof); fields, fsrc and bcs are then in dof numbering and every operator is P^T A P."""
+
+    def __init__(self, asm: Assembler, prm: TransportParams, prev: StateF, fsrc, bcs: BCsF, P=None):
+        self.asm, self.prm, self.prev, self.fsrc, self.bcs, self.P = asm, prm, prev, fsrc, bcs, P
+        self.PT = P.T.tocsr() if P is not None else None
+        self.M1 = asm.mass(1, 1, QDEG["mass_p1"])
+        self.M1d = self.fold(self.M1)
+        self.c0v, self.c1v = self.v(prev.c0), self.v(prev.c1)
+        self.c2v = self.v(prev.c2) if prm.ncomp == 3 else None
+        self.R = asm.reaction_q(prm, self.c0v, self.c1v, QDEG_F)
+
+    def v(self, x):                      # dof vector -> vertex values
+        return x if self.P is None else self.P @ x
+
+    def fold(self, A):
+        return A if self.P is None else (self.PT @ A @ self.P).tocsr()
+
+    def foldv(self, b):
+        return b if self.P is None else self.PT @ b
+
+    def c1(self):
+        prm = self.prm
+        return self.M1d, self.foldv(self.M1 @ self.c1v - prm.dt / (1 - prm.phi) * self.asm.load(1, QDEG_F, self.R[1]))
+
+    def c2(self):
+        prm = self.prm
+        return self.M1d, self.foldv(self.M1 @ self.c2v + prm.dt / (1 - prm.phi) * self.asm.load(1, QDEG_F, self.R[2]))
+
+    def c0(self, c1_new, c2_new):
+        asm, prm, nc = self.asm, self.prm, self.prm.ncomp
+        A00, S, qd = asm.c0_row(prm, ("DG0", self.prev.u), QDEG_F)
+        b = asm.c0_rhs(prm, qd, self.c0v, self.c1v, self.c2v if nc == 3 else None, self.v(self.fsrc), QDEG_F)
+        b = b - S @ (self.v(c1_new) + (self.v(c2_new) if nc == 3 else 0.0))
+        return fem.apply_dirichlet_symmetric(self.fold(A00), self.foldv(b), self.bcs.c0_dofs, self.bcs.c0_vals)
+
+    def p(self, c0_new):
+        L, bp = pressure_system(self.asm, self.prm, self.v(c0_new))
+        return fem.apply_dirichlet_symmetric(self.fold(L), self.foldv(bp) - self.bcs.flux_load, self.bcs.p_dofs,
+                                             np.zeros(len(self.bcs.p_dofs)))
+
+    def u(self, p_new, c0_new):
+        return recover_velocity(self.asm, self.prm, self.v(p_new), self.v(c0_new))
+
+
 def step(asm: Assembler, prm: TransportParams, prev: StateF, fsrc, bcs: BCsF, solver="lu", rtol=1e-13, info=None, P=None):
     """One mode-F timestep; `solver='lu'` (splu) or 'krylov' (SciPy cg/bicgstab + Jacobi,
     the CPU baseline leg of bench.py).  `P`: periodic prolongation (V x ndof); fields, fsrc and bcs are then in dof numbering."""
-    if P is not None:
-        return _step_periodic(asm, prm, prev, fsrc, bcs, P, solver, rtol, info)
+    sysm = StepSystems(asm, prm, prev, fsrc, bcs, P)
     nc = prm.ncomp
-    M1 = asm.mass(1, 1, QDEG["mass_p1"])
-    R1, R2, R3 = asm.reaction_q(prm, prev.c0, prev.c1, QDEG_F)
 
-    def spd_solve(A, b, x0=None, tag=""):
-        if solver == "lu":
-            return spla.splu(A.tocsc()).solve(b)
-        Dinv = sp.diags(1.0 / A.diagonal())
-        it = [0]
-        x, _ = spla.cg(A, b, x0=x0, rtol=rtol, atol=0.0, M=Dinv, maxiter=20000, callback=lambda xk: it.__setitem__(0, it[0] + 1))
-        if info is not None:
-            info[tag] = it[0]
-        return x
-
-    def gen_solve(A, b, x0=None, tag=""):
-        if solver == "lu":
-            return spla.splu(A.tocsc()).solve(b)
-        Dinv = sp.diags(1.0 / A.diagonal())
-        it = [0]
-        x, _ = spla.bicgstab(A, b, x0=x0, rtol=rtol, atol=0.0, M=Dinv, maxiter=20000, callback=lambda xk: it.__setitem__(0, it[0] + 1))
-        if info is not None:
-            info[tag] = it[0]
-        return x
-
-    c1 = spd_solve(M1, M1 @ prev.c1 - prm.dt / (1 - prm.phi) * asm.load(1, QDEG_F, R2), prev.c1, "c1")
-    c2 = None
-    if nc == 3:
-        c2 = spd_solve(M1, M1 @ prev.c2 + prm.dt / (1 - prm.phi) * asm.load(1, QDEG_F, R3), prev.c2, "c2")
-    A00, S, qd = asm.c0_row(prm, ("DG0", prev.u), QDEG_F)
-    b = asm.c0_rhs(prm, qd, prev.c0, prev.c1, prev.c2 if nc == 3 else None, fsrc, QDEG_F)
-    b = b - S @ (c1 + (c2 if nc == 3 else 0.0))
-    Abc, bbc = fem.apply_dirichlet_symmetric(A00, b, bcs.c0_dofs, bcs.c0_vals)
-    c0 = gen_solve(Abc, bbc, prev.c0, "c0")
-    L, bp = pressure_system(asm, prm, c0)
-    bp = bp - bcs.flux_load
-    Lbc, bpbc = fem.apply_dirichlet_symmetric(L, bp, bcs.p_dofs, np.zeros(len(bcs.p_dofs)))
-    p = spd_solve(Lbc, bpbc, prev.p, "p")
-    u = recover_velocity(asm, prm, p, c0)
-    return StateF(u=u, p=p, c0=c0, c1=c1, c2=c2)
-
-
-def _step_periodic(asm, prm, prev, fsrc, bcs, P, solver, rtol, info):
-    """Mode-F step on a periodic P1 space: every vertex-level operator A becomes P^T A P, every load P^T b."""
-    nc = prm.ncomp
-    PT = P.T.tocsr()
-    v = lambda x: P @ x                      # dof vector -> vertex values
-    fold = lambda A: (PT @ A @ P).tocsr()
-
-    def solve_(A, b, x0, spd, tag):
+    def solve_(Ab, x0, spd, tag):
+        A, b = Ab
         if solver == "lu":
             return spla.splu(A.tocsc()).solve(b)
         Dinv = sp.diags(1.0 / A.diagonal())
@@ -242,21 +244,8 @@ def _step_periodic(asm, prm, prev, fsrc, bcs, P, solver, rtol, info):
             info[tag] = it[0]
         return x
 
-    c0v, c1v = v(prev.c0), v(prev.c1)
-    c2v = v(prev.c2) if nc == 3 else None
-    M1 = asm.mass(1, 1, QDEG["mass_p1"])
-    M1p = fold(M1)
-    R1, R2, R3 = asm.reaction_q(prm, c0v, c1v, QDEG_F)
-    c1 = solve_(M1p, PT @ (M1 @ c1v - prm.dt / (1 - prm.phi) * asm.load(1, QDEG_F, R2)), prev.c1, True, "c1")
-    c2 = None
-    if nc == 3:
-        c2 = solve_(M1p, PT @ (M1 @ c2v + prm.dt / (1 - prm.phi) * asm.load(1, QDEG_F, R3)), prev.c2, True, "c2")
-    A00, S, qd = asm.c0_row(prm, ("DG0", prev.u), QDEG_F)
-    b = asm.c0_rhs(prm, qd, c0v, c1v, c2v, v(fsrc), QDEG_F) - S @ (v(c1) + (v(c2) if nc == 3 else 0.0))
-    Abc, bbc = fem.apply_dirichlet_symmetric(fold(A00), PT @ b, bcs.c0_dofs, bcs.c0_vals)
-    c0 = solve_(Abc, bbc, prev.c0, False, "c0")
-    L, bp = pressure_system(asm, prm, v(c0))
-    Lbc, bpbc = fem.apply_dirichlet_symmetric(fold(L), PT @ bp - bcs.flux_load, bcs.p_dofs, np.zeros(len(bcs.p_dofs)))
-    p = solve_(Lbc, bpbc, prev.p, True, "p")
-    u = recover_velocity(asm, prm, v(p), v(c0))
-    return StateF(u=u, p=p, c0=c0, c1=c1, c2=c2)
+    c1 = solve_(sysm.c1(), prev.c1, True, "c1")
+    c2 = solve_(sysm.c2(), prev.c2, True, "c2") if nc == 3 else None
+    c0 = solve_(sysm.c0(c1, c2), prev.c0, False, "c0")
+    p = solve_(sysm.p(c0), prev.p, True, "p")
+    return StateF(u=sysm.u(p, c0), p=p, c0=c0, c1=c1, c2=c2)

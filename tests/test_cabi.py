@@ -55,3 +55,4 @@ def test_struct_sizes_match_header():
     assert C.sizeof(_lib.MpTransportParams) == 8 * 15 + 16
     assert C.sizeof(_lib.MpCsr) == 80
     assert C.sizeof(_lib.MpSolveInfo) == 40
+    assert C.sizeof(_lib.MpFunctional) == 184

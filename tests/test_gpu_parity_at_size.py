@@ -1,0 +1,372 @@
+"""Parity AT SIZE: the mode-F hot path against the oracle on meshes where the grid-stride loops, the
+multi-wave reductions, SELL with more slices than resident warps and the 64-bit index arithmetic are all engaged.
+
+* 64^3 (274 625 dofs/field, 1.57 M cells), natural and periodic side walls: every ASSEMBLED operator and right-hand side of one
+  timestep equals the oracle's (probed with fixed vectors: A w, b; <= 1e-12), from a prescribed smooth state; then free-running
+  steps must converge with TRUE residuals <= 1e-11.  No CPU solve is needed, which is what makes this size affordable.
+* 48^3, natural and periodic: fields against the oracle's own Krylov path (rtol 1e-14), per solve <= 1e-10 (GPU restarted from the
+  oracle's previous state) and <= 1e-8 after 3 free-running steps -- BASELINE.json's stated tolerances.
+* config 1 at BASELINE's 64x64 through the drop-in API against a sparse LU.
+* mode R vs mode F: the gap between the reference's mixed P2/P1 discretisation and the primal P1 form (reported, not asserted tight).
+The slow oracle parts are cached on disk (tests/oracle_cache.py); `python tests/test_gpu_parity_at_size.py` warms the cache on a CPU.
+"""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from oracle import fem, forms, modef          # noqa: E402
+from oracle_cache import cached               # noqa: E402
+
+BOX = ((0.0, 0.0, 0.0), (4.0, 4.0, 1.0))
+PHYS = dict(Pe=500.0, Da=0.1, phi=0.05, alpha=1e-8, dt=0.1, K=1.0, gam_rho=1.0)      # bench.py / CCS_3comp.py:29-39
+ZH = (0.0, 0.0, 1.0)
+
+
+def rel(a, b):
+    return float(np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300))
+
+
+def source_term(X):
+    f = np.zeros(X.shape[0])
+    for ii in range(20):
+        f += 0.1 * np.abs(np.sin(ii * np.pi * X[:, 0]))
+    return f * (1.0 - np.tanh((1.0 - X[:, 2]) / 0.01))
+
+
+# ------------------------------------------------------------------ oracle side (CPU; cached)
+def _oracle_problem(n, sides):
+    om = fem.box_mesh(BOX[0], BOX[1], n, n, n)
+    asm = forms.Assembler(om)
+    prm = forms.ccs_three_component_params(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"], dt=PHYS["dt"],
+                                           K=PHYS["K"], zhat=ZH, gam_rho=PHYS["gam_rho"])
+    top = lambda x: x[2] > 1.0 - 1e-12
+    uval = lambda x: np.array([0.0, 0.0, -0.5])
+    if sides == "periodic":
+        P, dof = modef.periodic_prolongation(om, (0, 1), BOX[0], BOX[1])
+        bcs = modef.make_bcs_periodic(om, (0, 1), dof, top, uval, top, 0.1)
+        first = np.full(P.shape[1], -1, dtype=np.int64)
+        first[dof[::-1]] = np.arange(om.nv)[::-1]
+        Xd = om.coords[first]
+    else:
+        P, bcs, Xd = None, modef.make_bcs(om, top, uval, top, 0.1), om.coords
+    return om, asm, prm, bcs, P, Xd
+
+
+def _prescribed_state(Xd, cent):
+    """Smooth fields, periodic in x and y with the box period 4 (usable for both kinds of side wall)."""
+    x, y, z = Xd[:, 0], Xd[:, 1], Xd[:, 2]
+    s, c = np.sin(0.5 * np.pi * x), np.cos(0.5 * np.pi * y)
+    st = dict(c0=0.05 + 0.03 * s * c * z, c1=0.1 + 0.02 * np.cos(0.5 * np.pi * x) * (1.0 - z), c2=0.01 + 0.005 * np.sin(0.5 * np.pi * y),
+              p=s * z * (1.0 - z) + 0.3 * z)
+    st["c1_new"] = 0.99 * st["c1"]
+    st["c2_new"] = 1.01 * st["c2"] + 1e-4
+    st["c0_new"] = st["c0"] + 0.01 * z
+    cx, cy, cz = cent[:, 0], cent[:, 1], cent[:, 2]
+    st["u"] = np.stack([0.3 * np.sin(0.5 * np.pi * cy), -0.2 * np.cos(0.5 * np.pi * cx), -0.5 + 0.1 * cz], 1)
+    return st
+
+
+def _pattern_digest(rowptr, colidx):
+    """SHA-256 of the int32 CSR pattern (rowptr, then colidx): bit-exactness of pattern and dof numbering without shipping 16 MB."""
+    import hashlib
+    h = hashlib.sha256()
+    h.update(np.ascontiguousarray(rowptr, dtype=np.int32).tobytes())
+    h.update(np.ascontiguousarray(colidx, dtype=np.int32).tobytes())
+    return np.frombuffer(h.digest(), dtype=np.uint8).copy()
+
+
+def _probes(nd):
+    i = np.arange(nd, dtype=np.float64)
+    return np.cos(0.37 * i), np.sin(0.11 * i + 1.0)
+
+
+def oracle_assembly_probes(n, sides):
+    def compute():
+        om, asm, prm, bcs, P, Xd = _oracle_problem(n, sides)
+        st = _prescribed_state(Xd, om.coords[om.cells].mean(1))
+        prev = modef.StateF(u=st["u"], p=st["p"], c0=st["c0"], c1=st["c1"], c2=st["c2"])
+        f = source_term(Xd)
+        S = modef.StepSystems(asm, prm, prev, f, bcs, P)
+        w0, w1 = _probes(Xd.shape[0])
+        M, b1 = S.c1()
+        _, b2 = S.c2()
+        A0, b0 = S.c0(st["c1_new"], st["c2_new"])
+        L, bp = S.p(st["c0_new"])
+        u = S.u(st["p"], st["c0_new"])
+        Mp = M.tocsr().copy()
+        Mp.sort_indices()                                       # the CSR pattern of the (folded) P1 space: columns ascending
+        return dict(b1=b1, b2=b2, b0=b0, bp=bp, Mw0=M @ w0, A0w0=A0 @ w0, A0w1=A0 @ w1, Lw0=L @ w0, Lw1=L @ w1,
+                    u_sub=u[::97].copy(), u_norm=np.array([np.linalg.norm(u)]),
+                    pattern=_pattern_digest(Mp.indptr, Mp.indices))
+    return cached("asm_probes", dict(n=n, sides=sides, phys=PHYS, v=3), compute)
+
+
+def oracle_steps(n, sides, nsteps, rtol=1e-14):
+    """States of `nsteps` oracle steps (Krylov path) from the bench's initial state (c1 = 0.1, everything else 0)."""
+    def compute():
+        om, asm, prm, bcs, P, Xd = _oracle_problem(n, sides)
+        nd = Xd.shape[0]
+        f = source_term(Xd)
+        st = modef.StateF(u=np.zeros((om.nc, 3)), p=np.zeros(nd), c0=np.zeros(nd), c1=0.1 * np.ones(nd), c2=np.zeros(nd))
+        out = {}
+        for k in range(nsteps):
+            info = {}
+            st = modef.step(asm, prm, st, f, bcs, solver="krylov", rtol=rtol, info=info, P=P)
+            for nm in ("c0", "c1", "c2", "p"):
+                out["%s_%d" % (nm, k)] = getattr(st, nm)
+            out["iters_%d" % k] = np.array([info.get(t, 0) for t in ("c1", "c2", "c0", "p")])
+        return out
+    return cached("steps", dict(n=n, sides=sides, nsteps=nsteps, rtol=rtol, phys=PHYS, v=1), compute)
+
+
+# ------------------------------------------------------------------ product side
+def _product_problem(ctx, n, sides, rtol=1e-13, **kw):
+    import mupopp_b200 as mp
+    from mupopp_b200.mesh import box_periodic_map
+    from mupopp_b200.transport import TransportModel, TransportSolverF, make_boundary_data
+    model = TransportModel.ccs_three_component(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"], dt=PHYS["dt"],
+                                               K=PHYS["K"], zh=ZH, gam_rho=PHYS["gam_rho"])
+    mesh = mp.BoxMesh(BOX[0], BOX[1], n, n, n)
+    top = lambda x: x[..., 2] > 1.0 - 1e-12
+    pmap = box_periodic_map(mesh, (0, 1)) if sides == "periodic" else None
+    bd = make_boundary_data(mesh, top, (0.0, 0.0, -0.5), top, 0.1, periodic=pmap)
+    Xd = mesh.coords[pmap.dof2vert] if pmap is not None else mesh.coords
+    s = TransportSolverF(ctx, mesh, model, bd, f_source=source_term(Xd), rtol=rtol, maxit=50000,
+                         vert2dof=pmap.vert2dof if pmap is not None else None, **kw)
+    return mesh, Xd, s
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sides", ["natural", "periodic"])
+def test_assembled_systems_match_oracle_at_64(ctx, sides):
+    n = 64
+    ref = oracle_assembly_probes(n, sides)
+    mesh, Xd, s = _product_problem(ctx, n, sides)
+    nd = Xd.shape[0]
+    assert nd == (n * n * (n + 1) if sides == "periodic" else (n + 1) ** 3)
+    rp, ci = s.plan.csr_pattern()                                        # sparsity pattern and dof numbering: bit-exact
+    assert np.array_equal(_pattern_digest(rp.cpu().numpy(), ci.cpu().numpy()), ref["pattern"])
+    st = _prescribed_state(Xd, mesh.coords[mesh.cells].mean(1))
+    s.set_state(c0=st["c0"], c1=st["c1"], c2=st["c2"], p=st["p"], u=st["u"])
+    dev = lambda a: ctx.to_device(np.ascontiguousarray(a, dtype=np.float64))
+    w0, w1 = (dev(w) for w in _probes(nd))
+    y = ctx.zeros(nd)
+    tol = 1e-12
+    # c1 / c2 rows
+    s.assemble_reaction_rows()
+    assert rel(s.rhs.cpu().numpy(), ref["b1"]) < tol and rel(s.rhs2.cpu().numpy(), ref["b2"]) < tol
+    assert rel(s.M.spmv(w0, y).cpu().numpy(), ref["Mw0"]) < tol
+    # c0 row (matrix through two probe vectors, rhs incl. the SUPG coupling to the new c1, c2 and the Dirichlet lifting)
+    s.c1_new.copy_(dev(st["c1_new"]))
+    s.c2_new.copy_(dev(st["c2_new"]))
+    s.assemble_c0_row()
+    assert rel(s.rhs_c0.cpu().numpy(), ref["b0"]) < tol
+    assert rel(s.A.spmv(w0, y).cpu().numpy(), ref["A0w0"]) < tol
+    assert rel(s.A.spmv(w1, y).cpu().numpy(), ref["A0w1"]) < tol
+    # pressure operator and load
+    s.c0_new.copy_(dev(st["c0_new"]))
+    s.assemble_pressure_rhs()
+    assert rel(s.rhs.cpu().numpy(), ref["bp"]) < tol
+    assert rel(s.L.spmv(w0, y).cpu().numpy(), ref["Lw0"]) < tol and rel(s.L.spmv(w1, y).cpu().numpy(), ref["Lw1"]) < tol
+    # velocity recovery
+    s.recover_velocity()
+    u = s.u.cpu().numpy().reshape(-1, 3)
+    assert rel(u[::97], ref["u_sub"]) < tol and abs(np.linalg.norm(u) - ref["u_norm"][0]) < tol * ref["u_norm"][0]
+    # free-running steps from the bench's initial state: converged, and the TRUE residuals of the c0 / p systems are small
+    s.set_state(c0=np.zeros(nd), c1=0.1 * np.ones(nd), c2=np.zeros(nd), p=np.zeros(nd), u=np.zeros(3 * mesh.num_cells()))
+    for k in range(3):
+        res = s.step()
+        assert all(r is None or r.converged for r in res.values()), res
+        tr = s.true_residuals()
+        assert tr["p"] < 1e-11 and tr["c0"] < 1e-11, tr
+    assert getattr(s, "fallbacks", 0) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sides", ["natural", "periodic"])
+def test_fields_match_oracle_krylov_at_48(ctx, sides):
+    n, nsteps = 48, 3
+    ref = oracle_steps(n, sides, nsteps)
+    mesh, Xd, s = _product_problem(ctx, n, sides, rtol=1e-14)
+    nd = Xd.shape[0]
+    zero = dict(c0=np.zeros(nd), c1=0.1 * np.ones(nd), c2=np.zeros(nd), p=np.zeros(nd))
+    # per solve: restart the GPU from the oracle's previous state (velocity recovered on the GPU from that state)
+    worst = {}
+    for k in range(nsteps):
+        prev = zero if k == 0 else {nm: ref["%s_%d" % (nm, k - 1)] for nm in ("c0", "c1", "c2", "p")}
+        s.set_state(c0=prev["c0"], c1=prev["c1"], c2=prev["c2"], p=prev["p"])
+        if k == 0:
+            s.u.zero_()
+        else:
+            s.c0_new.copy_(s.c0)
+            s.recover_velocity()              # u^n = recovery(p^n, c0^n): what the previous step left behind
+        res = s.step()
+        assert all(r is None or r.converged for r in res.values()), res
+        for nm in ("c1", "c2", "c0", "p"):
+            e = rel(getattr(s, nm).cpu().numpy(), ref["%s_%d" % (nm, k)])
+            worst[nm] = max(worst.get(nm, 0.0), e)
+    print("48^3 %s per-solve rel L2 vs oracle Krylov:" % sides, worst, "oracle iterations (c1,c2,c0,p):", ref["iters_%d" % (nsteps - 1)])
+    assert max(worst.values()) < 1e-10, worst
+    # free-running
+    s.set_state(**zero)
+    s.u.zero_()
+    for k in range(nsteps):
+        s.step()
+    errs = {nm: rel(getattr(s, nm).cpu().numpy(), ref["%s_%d" % (nm, nsteps - 1)]) for nm in ("c0", "c1", "c2", "p")}
+    print("48^3 %s after %d steps:" % (sides, nsteps), errs)
+    assert max(errs.values()) < 1e-8, errs
+
+
+@pytest.mark.gpu
+def test_config1_at_baseline_size_64x64(ctx):
+    """BASELINE configs[0]: UnitSquareMesh 64x64, mixed P2/P1 Darcy + 10 ADR steps through the mupopp/fenics API vs sparse LU."""
+    import scipy.sparse.linalg as spla
+    sys.path.insert(0, os.path.join(ROOT, "examples"))
+    import config1_darcy_adr as ex
+    n, nsteps = 64, 10
+    up, c = ex.run(n, nsteps, verbose=False)
+
+    def compute():
+        om = fem.unit_square_mesh(n, n)
+        asm = forms.Assembler(om)
+        n1, n2 = asm.P1.ndof, asm.P2.ndof
+        X2 = asm.P2.dof_coords()
+        bot, top = np.where(X2[:, 1] < 1e-14)[0], np.where(X2[:, 1] > 1 - 1e-14)[0]
+        D = np.concatenate([bot, top])
+        gy = np.concatenate([np.sin(2 * np.pi * X2[bot, 0]), np.ones(len(top))])
+        A, b = forms.darcy_bilinear_system(asm, K=0.1, zhat=(0.0, 1.0))
+        Abc, bbc = fem.apply_dirichlet_symmetric(A, b, np.concatenate([D, n2 + D]), np.concatenate([np.zeros(len(D)), gy]))
+        x = spla.splu(Abc.tocsc()).solve(bbc)
+        uo = [x[:n2], x[n2:2 * n2]]
+        X1 = om.coords
+        cb, ct = np.where(X1[:, 1] < 1e-14)[0], np.where(X1[:, 1] > 1 - 1e-14)[0]
+        co = 0.1 * np.ones(n1)
+        for k in range(nsteps):
+            Ao, bo = forms.adr_single_system(asm, 100.0, 10.0, 0.1, ("P2", uo), co)
+            Ab, bb = fem.apply_dirichlet_symmetric(Ao, bo, np.concatenate([ct, cb]), np.concatenate([np.zeros(len(ct)), np.ones(len(cb))]))
+            co = spla.splu(Ab.tocsc()).solve(bb)
+        return dict(ux=uo[0], uy=uo[1], p=x[2 * n2:], c=co)
+    ref = cached("config1", dict(n=n, nsteps=nsteps, v=1), compute)
+    e = dict(ux=rel(up.get(0), ref["ux"]), uy=rel(up.get(1), ref["uy"]), p=rel(up.get(2), ref["p"]), c=rel(c.get(), ref["c"]))
+    print("config 1 at 64x64:", e)
+    assert e["ux"] < 1e-9 and e["uy"] < 1e-9 and e["p"] < 1e-9 and e["c"] < 1e-8, e
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dim,n", [(2, 64), (3, 16), (3, 32)])
+def test_mode_r_vs_mode_f_gap(ctx, dim, n):
+    """How far the benchmarked primal P1 form (mode F: DG0 velocity, P1 pressure Poisson) is from the reference's own mixed P2/P1
+    discretisation (mode R) on the same mesh, data and 3 timesteps: both are consistent discretisations of the same PDEs, so the gap
+    is O(h) and must shrink under refinement.  The numbers are written to gpurun_out/r_vs_f_gap.json and quoted in DESIGN.md."""
+    import json
+    import mupopp_b200 as mp
+    from mupopp_b200 import moder
+    from mupopp_b200.transport import TransportModel, TransportSolverF, make_boundary_data
+    zh = (0.0, 1.0) if dim == 2 else (0.0, 0.0, 1.0)
+    mesh = mp.RectangleMesh((0, 0), (2, 1), n, n) if dim == 2 else mp.BoxMesh((0, 0, 0), (2, 2, 1), n, n, n)
+    model = TransportModel.ccs_three_component(Pe=500, Da=0.1, phi=0.05, alpha=1e-3, dt=0.1, K=1.0, zh=zh)
+    X = mesh.coords
+    f = np.abs(np.sin(3 * np.pi * X[:, 0])) * (1 - np.tanh((1.0 - X[:, -1]) / 0.1))
+    uval = np.zeros(dim)
+    uval[-1] = -0.5
+    top = lambda x: x[..., -1] > 1.0 - 1e-12
+    nv = mesh.num_vertices()
+    # mode F
+    bd = make_boundary_data(mesh, top, uval, top, 0.1)
+    sf = TransportSolverF(ctx, mesh, model, bd, f_source=f, rtol=1e-12)
+    sf.set_state(c1=0.1 * np.ones(nv))
+    # mode R (the reference's discretisation): u = uval on the top P2 dofs, c0 = 0.1 on the top vertices
+    sp = moder.Spaces(ctx, mesh)
+    X2 = sp.dof_coords(2)
+    t2 = (X2[:, -1] > 1.0 - 1e-12)
+    u_isbc = [t2.astype(np.uint8)] * dim
+    u_g = [np.where(t2, uval[c], 0.0) for c in range(dim)]
+    t1 = (X[:, -1] > 1.0 - 1e-12)
+    sr = moder.TransportSolverR(ctx, mesh, model, u_isbc, u_g, t1.astype(np.uint8), np.where(t1, 0.1, 0.0), f_source=f, rtol=1e-12)
+    sr.set_state(c1=0.1 * np.ones(nv))
+    for k in range(3):
+        sf.step()
+        sr.step()
+    # cell means of the P2 velocity (exact cell average: triangles = mean of the edge-midpoint values; tets = -1/20 sum(vertices) + 1/5 sum(edges))
+    cd2 = sp.cd2_host
+    nb1 = dim + 1
+    ur = np.stack([u.cpu().numpy() for u in sr.u], 1)[cd2]                 # (C, nb2, dim)
+    if dim == 2:
+        ur_mean = ur[:, nb1:].mean(1)
+    else:
+        ur_mean = -0.05 * ur[:, :nb1].sum(1) + 0.2 * ur[:, nb1:].sum(1)
+    uf = sf.u.cpu().numpy().reshape(-1, dim)
+    gap = dict(dim=dim, n=n, c0=rel(sf.c0.cpu().numpy(), sr.c0.cpu().numpy()), c1=rel(sf.c1.cpu().numpy(), sr.c1.cpu().numpy()),
+               p=rel(sf.p.cpu().numpy(), sr.p.cpu().numpy()), u_dg0=rel(uf, ur_mean))
+    print("mode F vs mode R after 3 steps:", gap)
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    with open(os.path.join(out, "r_vs_f_gap.json"), "a") as fh:
+        fh.write(json.dumps(gap) + "\n")
+    assert gap["p"] < 0.2 and gap["c0"] < 0.5 and gap["u_dg0"] < 0.5, gap       # same PDE, O(h) apart; not a parity statement
+
+
+@pytest.mark.gpu
+def test_peer_mailbox_allreduce_is_transparent_on_one_gpu():
+    """The in-kernel allreduce (mailbox windows + sequence flags) with a single rank must reproduce the plain reductions bit
+    for bit: same PCG / BiCGStab iterates.  Exercises the flag protocol of csrc/krylov.cu::grid_reduce without a second GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mupopp_b200.device import Context
+    outs = []
+    for peer in (False, True):
+        c = Context(0)
+        if peer:
+            assert c.enable_peer()
+        mesh, Xd, s = _product_problem(c, 16, "periodic", rtol=1e-13)
+        nd = Xd.shape[0]
+        s.set_state(c1=0.1 * np.ones(nd))
+        its = []
+        for k in range(3):
+            r = s.step()
+            assert all(v is None or v.converged for v in r.values())
+            its.append([v.niter if v else 0 for v in r.values()])
+        outs.append((s.c0.cpu().numpy().copy(), s.p.cpu().numpy().copy(), its))
+        del s
+        c.close()
+    assert outs[0][2] == outs[1][2]
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport,layout", [("peer", "slab"), ("nccl", "slab"), ("peer", "periodic"), ("peer", "rcb")])
+def test_two_ranks_reproduce_one_gpu(transport, layout):
+    """tools/check_multigpu.py under torchrun with 2 ranks: partitioned fields == single-GPU fields (<= 1e-8), for the peer-memory
+    transport (in-kernel allreduce + halo push fused into SpMV) and for NCCL, z-slabs / periodic slabs / general RCB partition."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = dict(os.environ, MUPOPP_B200_TRANSPORT=transport)
+    args = ["20", "3", "24"] + ([layout] if layout != "slab" else [])
+    port = 29500 + (os.getpid() % 400)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", "check_multigpu.py")] + args
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    print(r.stdout[-3000:], r.stderr[-2000:])
+    assert r.returncode == 0 and "MULTIGPU_OK" in r.stdout
+
+
+if __name__ == "__main__":          # warm the oracle cache on a CPU box
+    import time
+    for sides in ("natural", "periodic"):
+        t = time.time()
+        oracle_assembly_probes(64, sides)
+        print("probes 64", sides, "%.0f s" % (time.time() - t), flush=True)
+    for sides in ("natural", "periodic"):
+        t = time.time()
+        oracle_steps(48, sides, 3)
+        print("steps 48", sides, "%.0f s" % (time.time() - t), flush=True)

@@ -24,6 +24,11 @@ ctx = Context(local)
 ids = [ctx.unique_id() if rank == 0 else None]
 dist.broadcast_object_list(ids, src=0)
 ctx.init_comm(world, rank, ids[0])
+transport = os.environ.get("MUPOPP_B200_TRANSPORT", "peer")   # peer (NVLink windows, default) | nccl
+if transport == "peer":
+    on = ctx.enable_peer()
+    if rank == 0:
+        print("peer-memory collectives:", "on" if on else "unavailable (%s) -> NCCL" % getattr(ctx, "peer_error", "?"))
 BOX = ((0.0, 0.0, 0.0), (2.0, 2.0, 1.0))
 model = TransportModel.ccs_three_component(Pe=500, Da=0.1, phi=0.05, alpha=1e-3, dt=0.1, K=1.0, zh=(0.0, 0.0, 1.0))
 top = lambda x: x[..., 2] > 1.0 - 1e-12
