@@ -296,25 +296,43 @@ def run_b200(args):
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
 
-    # ---- timed region 2: the SAME K steps from the SAME saved state, end to end with HOST state buffers (e2e):
-    #      every step copies its input state host->device from pinned memory and its result device->host.
+    # ---- timed region 2 (e2e): the SAME K steps from the SAME saved state, with HOST state buffers: every step copies its input
+    #      state host->device from pinned memory and its result device->host.  On one GPU the step is the reference-facing plugin
+    #      call itself -- `a, L = CCS.advection_diffusion_three_component(W, mesh, sol_0, dt, f_source=S, K=1.0); solve(a == L, sol, bc)`
+    #      on a periodic `constrained_domain` space (mupopp_b200.mupopp / mupopp_b200.fenics); on N > 1 GPUs, where the facade has no
+    #      partitioned spaces, it is TransportSolverF.step on the rank's slab.
     restore()
-    names = ["c0", "c1", "c2", "p", "u"]
-    host_in = {k: torch.empty_like(getattr(s, k), device="cpu").pin_memory() for k in names}
-    host_out = {k: torch.empty_like(getattr(s, k), device="cpu").pin_memory() for k in names}
-    for k in names:
-        host_in[k].copy_(getattr(s, k))
+    api = None
+    if nranks == 1 and args.sides == "periodic" and not args.no_api:
+        t1 = time.perf_counter()
+        api = ApiProblem(args, ctx, s, saved)
+        log("[bench] drop-in API problem built in %.1f s (FunctionSpace with constrained_domain, DirichletBC, CCS forms)" % (time.perf_counter() - t1))
+        dev_in, dev_out = api.device_buffers()
+    else:
+        names = ["c0", "c1", "c2", "p", "u"]
+        dev_in = dev_out = [getattr(s, k) for k in names]
+    host_in = [torch.empty_like(t, device="cpu").pin_memory() for t in dev_in]
+    host_out = [torch.empty_like(t, device="cpu").pin_memory() for t in dev_out]
+    src = api.initial_state() if api is not None else dev_in
+    for h, t in zip(host_in, src):
+        h.copy_(t)
     torch.cuda.synchronize()
-    bytes_in = sum(int(v.numel()) * 8 for v in host_in.values())
-    bytes_out = sum(int(v.numel()) * 8 for v in host_out.values())
+    bytes_in = sum(int(v.numel()) * 8 for v in host_in)
+    bytes_out = sum(int(v.numel()) * 8 for v in host_out)
     hbuf = {"in": host_in, "out": host_out}
 
     def e2e_step(k):
-        for nm in names:
-            getattr(s, nm).copy_(hbuf["in"][nm], non_blocking=True)          # H2D of this step's input state
-        r = s.step()
-        for nm in names:
-            hbuf["out"][nm].copy_(getattr(s, nm), non_blocking=True)         # D2H of the step's result
+        if api is None:
+            d_in = d_out = [getattr(s, nm) for nm in names]                 # (the solver rotates its state tensors every step)
+        else:
+            d_in, d_out = dev_in, dev_out
+        for t, h in zip(d_in, hbuf["in"]):
+            t.copy_(h, non_blocking=True)                                    # H2D of this step's input state
+        r = api.step() if api is not None else s.step()
+        if api is None:
+            d_out = [getattr(s, nm) for nm in names]
+        for h, t in zip(hbuf["out"], d_out):
+            h.copy_(t, non_blocking=True)                                    # D2H of the step's result
         torch.cuda.current_stream().synchronize()
         hbuf["in"], hbuf["out"] = hbuf["out"], hbuf["in"]                     # the next step starts from the host copy
         return r
@@ -323,6 +341,9 @@ def run_b200(args):
     iters2 = [check_step(r, "e2e step %d" % k) for k, r in enumerate(results2)]
     clocks = sampler.stop() if rank == 0 else None
     e2e_value = 1e3 / (ms_e2e / args.steps)
+    e2e_call = ("CCS.advection_diffusion_three_component(...) + solve(a == L, sol, bc) on FunctionSpace(mesh, MixedElement([V, Q, Qc, Qc, Qc]), "
+                "constrained_domain=pbc)") if api is not None else "TransportSolverF.step() on the rank's z-slab"
+    del api
 
     # ---- pass 3 (untimed for the metric): the dominant kernel's launches timed one by one with CUDA events on the launch stream,
     #      over the first steps of the same window (roofline.achieved); kept out of regions 1 and 2 so that neither is perturbed.
@@ -358,7 +379,7 @@ def run_b200(args):
                "true_relative_residuals_last_step": true_res,
                "clocks": clocks, "gpu_launches": int(launches),
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": bytes_in, "d2h_bytes_per_step": bytes_out,
-                       "ms_per_step": ms_e2e / args.steps, "copy_ms_per_step": ms_e2e / args.steps - ms_step},
+                       "ms_per_step": ms_e2e / args.steps, "overhead_vs_resident_ms_per_step": ms_e2e / args.steps - ms_step, "call": e2e_call},
                "roofline": {"bound": "hbm", "kernel": "%s (SELL-32 SpMV inside PCG/BiCGStab, per-rank operator)"
                                                       % ("k_spmv_sell_peer" if (nranks > 1 and ctx.peer_enabled()) else "k_spmv_sell"),
                             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
@@ -391,6 +412,72 @@ def run_b200(args):
     return 0
 
 
+class ApiProblem:
+    """The bench workload expressed with the reference-facing API, exactly as a run script would write it
+    (/root/reference/src/run/CCS2D/CCS_3comp.py:127-143,206-263 lifted to the 3-D box)."""
+
+    def __init__(self, args, ctx, solver, saved):
+        import torch
+        import mupopp_b200.fenics as fx
+        from mupopp_b200 import mupopp as mp_api
+        fx._CTX = ctx                                       # one GPU context / stream for both problems
+        n = args.n
+        (x0, y0, z0), (x1, y1, z1) = BOX
+        mesh = solver.dm.host                               # the BoxMesh the resident-state problem was built on
+
+        class PeriodicBoundary(fx.SubDomain):
+            def inside(self, x, on_boundary):
+                return bool((fx.near(x[0], x0) or fx.near(x[1], y0)) and not (fx.near(x[0], x1) or fx.near(x[1], y1)) and on_boundary)
+
+            def map(self, x, y):
+                y[0], y[1], y[2] = x[0], x[1], x[2]
+                if fx.near(x[0], x1):
+                    y[0] = x[0] - (x1 - x0)
+                if fx.near(x[1], y1):
+                    y[1] = x[1] - (y1 - y0)
+
+        class SourceTerm(fx.Expression):
+            def __init__(self, top):
+                self.top = top
+
+            def eval(self, values, x):
+                g1 = x[0] * 0.0
+                for ii in range(0, 20):
+                    g1 += 0.1 * np.abs(np.sin(ii * x[0] * np.pi))
+                values[0] = (1.0 - np.tanh((self.top - x[2]) / 0.01)) * g1
+
+        cell = mesh.ufl_cell()
+        V = fx.VectorElement("Lagrange", cell, 2)
+        Q = fx.FiniteElement("Lagrange", cell, 1)
+        Qc = fx.FiniteElement("Lagrange", cell, 1)
+        self.W = fx.FunctionSpace(mesh, fx.MixedElement([V, Q, Qc, Qc, Qc]), constrained_domain=PeriodicBoundary())
+        top = lambda x: x[2] > z1 - 1e-12
+        self.bc = [fx.DirichletBC(self.W.sub(0), fx.Constant((0.0, 0.0, -0.5)), top), fx.DirichletBC(self.W.sub(2), fx.Constant(0.1), top)]
+        self.ccs = mp_api.CCS(Pe=PHYS["Pe"], Da=PHYS["Da"], phi=PHYS["phi"], alpha=PHYS["alpha"])
+        self.S = SourceTerm(z1)
+        self.sol_0, self.sol = fx.Function(self.W), fx.Function(self.W)
+        self.mesh, self.fx, self.args = mesh, fx, args
+        ncell = mesh.num_cells()
+        self.sol_0.cell_velocity = torch.zeros(3 * ncell, dtype=torch.float64, device=ctx.device)
+        self.sol.cell_velocity = torch.zeros(3 * ncell, dtype=torch.float64, device=ctx.device)
+        self._init = [saved["p"], saved["c0"], saved["c1"], saved["c2"], saved["u"]]
+        self.zh = fx.Constant((0.0, 0.0, 1.0))
+
+    def device_buffers(self):
+        """Input state of a step = blocks [p, c0, c1, c2] of sol_0 + its cellwise velocity; result = the same of sol (+ the nodal velocity
+        blocks, which the scripts write to file)."""
+        d = 3
+        return (self.sol_0.blocks[d:] + [self.sol_0.cell_velocity], self.sol.blocks[d:] + [self.sol.cell_velocity])
+
+    def initial_state(self):
+        return self._init
+
+    def step(self):
+        a, L = self.ccs.advection_diffusion_three_component(self.W, self.mesh, self.sol_0, PHYS["dt"], f_source=self.S, K=PHYS["K"], zh=self.zh,
+                                                            gam_rho=PHYS["gam_rho"])
+        return self.fx.solve(a == L, self.sol, self.bc, solver_parameters={"relative_tolerance": self.args.rtol})
+
+
 def ncu_traffic(args, nranks):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, read from the committed ncu capture of THIS
     operator (profiles/r2_ncu_spmv.json, written by tools/ncu_summary.py from the .ncu-rep of `bench.py --steps 1 --warmup 1`)."""
@@ -415,8 +502,9 @@ def main():
     ap.add_argument("--ref-n", type=int, default=28, help="sample size of the CPU oracle leg")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer-memory windows over NVLink (in-kernel allreduce, halo push fused into SpMV) or plain NCCL")
-    ap.add_argument("--p-guess", default="extrapolate", choices=["extrapolate", "previous"],
-                    help="initial iterate of the pressure PCG: 2 p^n - p^(n-1) or p^n")
+    ap.add_argument("--p-guess", default="previous", choices=["extrapolate", "previous"],
+                    help="initial iterate of the pressure PCG: p^n (default) or 2 p^n - p^(n-1) (measured: no fewer iterations, "
+                         "profiles/r2_pressure_guess.md -- the tolerance is relative to ||b||, and the front moves non-smoothly)")
     ap.add_argument("--rtol", type=float, default=1e-12)
     ap.add_argument("--maxit", type=int, default=50000)
     ap.add_argument("--c0-method", default="bicgstab", choices=["gmres", "bicgstab"],
@@ -425,6 +513,7 @@ def main():
     ap.add_argument("--p-precond", default="jacobi", choices=["jacobi", "chebyshev"], help="pressure PCG preconditioner")
     ap.add_argument("--cheb-degree", type=int, default=3)
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--skip-api", dest="no_api", action="store_true", help="e2e through TransportSolverF.step instead of the mupopp/fenics plugin call")
     ap.add_argument("--sides", default="periodic", choices=["natural", "noflow", "periodic"],
                     help="x/y faces: periodic constrained_domain (default; what the reference's CCS scripts use, CCS_3comp.py:131-143,212), "
                          "impermeable u.n=0, or natural p=0 (CCS_3D_side_source.py)")

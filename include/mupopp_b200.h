@@ -129,6 +129,10 @@ int mp_elem_p1_pressure_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport
 int mp_recover_velocity(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_K,
                         const double *d_p, const double *d_c0, double *d_ucell);
 
+/* elem_vec[c][i] = |cell| * (d_ucell ? d_ucell[c][comp] : 1): scattered and divided by the lumped volumes it gives the
+ * volume-weighted vertex average of a cellwise field (the nodal velocity written by `velocity_out << u0`, run/CCS2D/CCS_3comp.py:265-266) */
+int mp_elem_p1_cell_load(mp_ctx *ctx, const mp_mesh *mesh, const double *d_ucell, int comp, double *d_elem_vec);
+
 /* Generic affine element kernel ("tensor representation"): elem_mat[c][i][j] = scale * sum_t geo_t(c) * T0[t][i][j]
  *   kind 0 MASS  (1 tensor,  geo = |detJ|)                      kind 1 GRAD  (dim tensors, geo_a = |detJ| Jinv[a][dir]: row value x column d/dx_dir)
  *   kind 2 GRADT (as GRAD with row derivative x column value)   kind 3 STIFF (dim^2 tensors, geo_ab = |detJ| (Jinv Jinv^T)_ab)

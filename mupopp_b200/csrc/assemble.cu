@@ -482,6 +482,21 @@ __global__ void __launch_bounds__(kThreads) k_p1_pressure_rhs(mp_mesh m, mp_tran
     store_vec<D>(m, evec, c, b);
 }
 
+// evec[c][i] = |cell| * (ucell ? ucell[c][comp] : 1): load of the volume-weighted vertex average of a cellwise field
+// (the nodal velocity the run scripts write to file, e.g. `velocity_out << u0`, run/CCS2D/CCS_3comp.py:265-266)
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_cell_load(mp_mesh m, const double *__restrict__ ucell, int comp, double *__restrict__ evec) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m, c, G);
+    const double v = G.vol * (ucell ? ucell[c * D + comp] : 1.0);
+    double b[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) b[i] = v;
+    store_vec<D>(m, evec, c, b);
+}
+
 // u = -(K/phi)(grad p + sigma rho zhat): DarcyAdvection (sigma=-1) gives u = -k(grad p - drho zhat)/phi (mupopp.py:563)
 template <int D>
 __global__ void __launch_bounds__(kThreads) k_recover_velocity(mp_mesh m, mp_transport_params P, const double *__restrict__ K,
@@ -1020,6 +1035,13 @@ extern "C" int mp_elem_p1_pressure_rhs(mp_ctx *ctx, const mp_mesh *mesh, const m
     MP_TRY(check_mesh(ctx, mesh));
     MP_CHECK(prm && d_c0 && d_elem_vec, "mp_elem_p1_pressure_rhs: null argument");
     DISPATCH_DIM(mesh, k_p1_pressure_rhs, *prm, d_K, d_c0, d_elem_vec);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_cell_load(mp_ctx *ctx, const mp_mesh *mesh, const double *d_ucell, int comp, double *d_elem_vec) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(d_elem_vec && comp >= 0 && comp < mesh->dim, "mp_elem_p1_cell_load: bad argument");
+    DISPATCH_DIM(mesh, k_p1_cell_load, d_ucell, comp, d_elem_vec);
     return 0;
 }
 

@@ -16,6 +16,9 @@ import torch
 from . import mesh as _mesh
 from .device import Context
 
+from numpy import cos, exp, pi, sin, sqrt, tan, tanh  # noqa: F401,E402  (names the run scripts pick up from `from fenics import *`)
+
+np = np
 DOLFIN_EPS = 3.0e-16
 parameters = {"std_out_all_processes": False, "form_compiler": {"quadrature_degree": None, "cpp_optimize": True}}
 _CTX = None
@@ -132,6 +135,76 @@ class MeshFunction:
         e = self.entries[self.entries[:, 2] == value]
         return e[:, 0], e[:, 1]
 
+    def set_all(self, value):
+        self.entries[:, 2] = int(value)
+
+    @staticmethod
+    def boundary(mesh, value=0):
+        """FacetFunction("size_t", mesh): one entry per BOUNDARY facet (interior facets never carry a marker in the in-scope
+        scripts: they are only used under ds)."""
+        fv, nrm, meas, owner = mesh.boundary_facets()
+        loc = mesh.boundary_facet_local_index()
+        mf = MeshFunction("size_t", mesh)
+        mf.entries = np.stack([owner, loc, np.full(len(owner), int(value))], 1).astype(np.int64)
+        mf._bgeom = (fv, nrm, meas)
+        return mf
+
+    def facet_geometry(self, value):
+        """(owning cell, local facet, outward unit normal, measure) of the facets marked `value`."""
+        m = self.mesh
+        d = m.dim
+        sel = self.entries[:, 2] == value
+        owner, loc = self.entries[sel, 0], self.entries[sel, 1]
+        if owner.size == 0:
+            return owner, loc, np.zeros((0, d)), np.zeros(0)
+        cells = m.cells[owner].astype(np.int64)
+        idx = np.array([[j for j in range(d + 1) if j != k] for k in range(d + 1)])[loc]          # (F, d) local vertices of the facet
+        fv = np.take_along_axis(cells, idx, axis=1)
+        x = m.coords[fv]
+        opp = m.coords[cells[np.arange(len(owner)), loc]]
+        if d == 2:
+            t = x[:, 1] - x[:, 0]
+            n = np.stack([t[:, 1], -t[:, 0]], 1)
+            meas = np.linalg.norm(t, axis=1)
+        else:
+            n = np.cross(x[:, 1] - x[:, 0], x[:, 2] - x[:, 0])
+            meas = 0.5 * np.linalg.norm(n, axis=1)
+        n = n / np.linalg.norm(n, axis=1, keepdims=True)
+        n[((x[:, 0] - opp) * n).sum(1) < 0] *= -1.0
+        return owner, loc, n, meas
+
+
+def FacetFunction(kind, mesh, value=0):
+    return MeshFunction.boundary(mesh, value)
+
+
+class SubDomain:
+    """dolfin.SubDomain: override inside(x, on_boundary) (and map(x, y) for a periodic `constrained_domain`)."""
+
+    def inside(self, x, on_boundary):
+        return False
+
+    def map(self, x, y):
+        y[:] = x
+
+    def mark(self, mesh_function, value):
+        """Mark the boundary facets whose vertices AND midpoint are inside (DOLFIN's default check_midpoint=True)."""
+        m = mesh_function.mesh
+        d = m.dim
+        e = mesh_function.entries
+        if e.shape[0] == 0:
+            return
+        cells = m.cells[e[:, 0]].astype(np.int64)
+        idx = np.array([[j for j in range(d + 1) if j != k] for k in range(d + 1)])[e[:, 1]]
+        fv = np.take_along_axis(cells, idx, axis=1)
+        verts = np.unique(fv)
+        vin = np.zeros(m.num_vertices(), dtype=bool)
+        vin[verts] = [bool(self.inside(m.coords[v], True)) for v in verts]
+        ok = vin[fv].all(1)
+        for f in np.nonzero(ok)[0]:
+            ok[f] = bool(self.inside(m.coords[fv[f]].mean(0), True))
+        e[ok, 2] = int(value)
+
 
 def read_function_xml(path, f):
     """`File(path) >> f` for DOLFIN-XML function data (rows `dof index, value`): UFC block numbering is assumed, which is what the
@@ -167,6 +240,45 @@ def generate_mesh(domain, resolution):
     if len(ext) == 2:
         return _mesh.RectangleMesh(p0, p1, n[0], n[1])
     return _mesh.BoxMesh(p0, p1, n[0], n[1], n[2])
+
+
+def periodic_map_from_subdomain(mesh, pbc):
+    """mesh.PeriodicMap of a DOLFIN periodic `constrained_domain`: a boundary vertex x that is not `inside` is a SLAVE when
+    `pbc.map(x, y)` lands on a mesh vertex y with `pbc.inside(y, True)`; it then shares that master's dof.  Dofs are numbered
+    compactly in master-vertex order (the same rule as mesh.box_periodic_map and the oracle's periodic_prolongation)."""
+    if isinstance(pbc, _mesh.PeriodicMap):
+        return pbc
+    X = mesh.coords
+    d = mesh.dim
+    fv = mesh.boundary_facets()[0]
+    bverts = np.unique(fv.ravel())
+    ext = float(np.max(X.max(0) - X.min(0)))
+    lo = X.min(0)
+    scale = 1.0 / (1e-7 * ext)
+    key_of = lambda p: tuple(np.round((np.asarray(p) - lo) * scale).astype(np.int64))
+    is_master = {int(v): bool(pbc.inside(X[v], True)) for v in bverts}
+    where = {key_of(X[v]): int(v) for v in bverts if is_master[int(v)]}
+    master = np.arange(X.shape[0])
+    y = np.zeros(d)
+    axes = set()
+    for v in bverts:
+        v = int(v)
+        if is_master[v]:
+            continue
+        y[:] = X[v]
+        pbc.map(X[v], y)
+        m = where.get(key_of(y))
+        if m is not None and m != v:
+            master[v] = m
+            axes.update(int(a) for a in np.nonzero(np.abs(X[v] - X[m]) > 1e-9 * ext)[0])
+    while True:                                     # path compression (corner vertices of multiply periodic boxes)
+        nxt = master[master]
+        if np.array_equal(nxt, master):
+            break
+        master = nxt
+    ism = master == np.arange(X.shape[0])
+    dof_of_master = np.cumsum(ism) - 1
+    return _mesh.PeriodicMap(dof_of_master[master], tuple(sorted(axes)), (X.min(0), X.max(0)))
 
 
 class _UfcCell:
@@ -221,8 +333,11 @@ class FunctionSpace:
     """Scalar, vector or mixed Lagrange space with UFC block numbering; blocks = [(degree, offset, ndof)]."""
 
     def __init__(self, mesh, element, degree=None, constrained_domain=None, _parent=None, _sub=None):
-        if constrained_domain is not None:
-            raise NotImplementedError("periodic constrained_domain is not on the B200 path yet (SURVEY.md section 8 f1)")
+        # periodic `constrained_domain` (run/CCS2D/CCS_3comp.py:131-143,212; run/CCS/CCS_3D_top_source.py:134-158,211): slave vertices
+        # share the dof of their master.  Such spaces are solved by mode F (P1 fields, cellwise velocity): P1 blocks carry one dof per
+        # vertex CLASS; the velocity sub-space is STORED at the P1 dofs as well (the vertex average of the cellwise recovery, what the
+        # scripts write to file), the cellwise velocity itself travels with the Function (Function.cell_velocity).
+        self.periodic = periodic_map_from_subdomain(mesh, constrained_domain) if constrained_domain is not None else None
         self.mesh = mesh
         if isinstance(element, str):
             element = FiniteElement(element, mesh.ufl_cell(), degree)
@@ -244,13 +359,16 @@ class FunctionSpace:
             if e.degree not in (1, 2, 3):
                 raise NotImplementedError("Lagrange degree %d" % e.degree)
             nd = mesh.num_vertices()
-            if e.degree == 2:
+            deg = e.degree
+            if self.periodic is not None:
+                nd, deg = self.periodic.ndof, 1
+            elif e.degree == 2:
                 nd += mesh.num_edges()
             elif e.degree == 3:
                 nd += 2 * mesh.num_edges() + (mesh.num_cells() if mesh.dim == 2 else mesh.faces.shape[0])
             for _ in range(e.ncomp):
                 idx.append(len(self.blocks))
-                self.blocks.append((e.degree, off, nd))
+                self.blocks.append((deg, off, nd))
                 off += nd
             self.sub_blocks.append(idx)
         self._dim = off
@@ -268,6 +386,8 @@ class FunctionSpace:
 
     def dof_coords(self, degree):
         m = self.mesh
+        if self.periodic is not None:
+            return m.coords[self.periodic.dof2vert]
         if degree == 1:
             return m.coords
         e = m.edges
@@ -358,9 +478,23 @@ def _evaluate(value, pts, ncomp, cell_info=None):
         return np.full((n, ncomp), float(value))
     if isinstance(value, Constant):
         return np.broadcast_to(value.value.reshape(1, -1), (n, ncomp)).copy()
+    if isinstance(value, Function):
+        if len(value.blocks) != ncomp or any(b.numel() != n for b in value.blocks):
+            raise NotImplementedError("evaluating a Function at points other than its own dofs")
+        return np.stack([b.cpu().numpy() for b in value.blocks], 1)
     if isinstance(value, Expression):
-        out = np.zeros((n, ncomp))
         use_cell = hasattr(value, "eval_cell") and cell_info is not None
+        if not use_cell and n > 64:
+            # vectorised attempt: x[k] are coordinate ARRAYS.  Works for expressions written with numpy-style arithmetic (the names
+            # sin/cos/tanh/exp/sqrt exported by this module are numpy's); anything that branches on x falls back to the point loop.
+            try:
+                vals = [None] * max(ncomp, 1)
+                value.eval(vals, [pts[:, k] for k in range(pts.shape[1])])
+                cols = [np.broadcast_to(np.asarray(v, dtype=float), (n,)) for v in vals[:ncomp]]
+                return np.stack(cols, 1).copy()
+            except Exception:
+                pass
+        out = np.zeros((n, ncomp))
         buf = np.zeros(max(ncomp, 1))
         for i in range(n):
             buf[:] = 0.0
@@ -385,6 +519,7 @@ class Function:
         else:
             self.blocks, self.ids = _blocks, _ids
         self._name = "f"
+        self.cell_velocity = None       # mode F: the cellwise (DG0) velocity [ncell*dim] behind the stored vertex averages
 
     def function_space(self):
         return self.space
@@ -398,7 +533,10 @@ class Function:
             blks = [self.blocks[self.ids.index(i)] for i in idx]
             if deepcopy:
                 blks = [b.clone() for b in blks]
-            out.append(Function(self.space, blks, list(idx)))
+            f = Function(self.space, blks, list(idx))
+            if self.cell_velocity is not None and list(idx) == list(self.space.sub_blocks[0]) and len(idx) == self.space.mesh.dim:
+                f.cell_velocity = self.cell_velocity.clone() if deepcopy else self.cell_velocity
+            out.append(f)
         return tuple(out)
 
     def sub(self, i):
@@ -413,6 +551,17 @@ class Function:
     def assign(self, other):
         for a, b in zip(self.blocks, other.blocks):
             a.copy_(b)
+        if getattr(other, "cell_velocity", None) is not None and len(self.blocks) == len(other.blocks):
+            self.cell_velocity = other.cell_velocity.clone()
+
+    # ---- integrand algebra for scalar functionals: c*phi0*dot(u, n)*ds(1), c*(1-phi0)*dx, ...  (see assemble())
+    def __mul__(self, other):
+        return _Integrand.of(self) * other
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return _Integrand.of(self) * -1.0
 
     def interpolate(self, v):
         ctx = default_context()
@@ -482,10 +631,29 @@ class DirichletBC:
             self.space, self.block_ids = V, list(range(len(V.blocks)))
 
     def _mark(self, x):
+        if isinstance(self.marker, SubDomain):
+            return bool(self.marker.inside(x, True))
         try:
             return bool(self.marker(x, True))
         except TypeError:
             return bool(self.marker(x))
+
+    def facet_mask(self, fv, owner, oloc):
+        """Which of the given boundary facets (vertex ids fv, owning cell, local index) carry this condition: marker function /
+        SubDomain -> all vertices and the midpoint inside ('topological' marking); MeshFunction + id -> the facets with that value."""
+        mesh = self.space.mesh
+        if isinstance(self.marker, MeshFunction):
+            oc, ol = self.marker.facets_with(self.sub_id)
+            have = set(zip(oc.tolist(), ol.tolist()))
+            return np.array([(int(c), int(k)) in have for c, k in zip(owner, oloc)], dtype=bool)
+        vx = mesh.coords
+        bverts = np.unique(fv.ravel())
+        vin = np.zeros(mesh.num_vertices(), dtype=bool)
+        vin[bverts] = [self._mark(vx[i]) for i in bverts]
+        inside = vin[fv].all(1)
+        for f in np.nonzero(inside)[0]:
+            inside[f] = self._mark(vx[fv[f]].mean(0))
+        return inside
 
     def dofs_and_values(self):
         """-> {block id: (dof indices, values)} in the block's own numbering."""
@@ -598,3 +766,266 @@ class File:
             self._series.write(mesh.coords, mesh.cells, {f._name: data}, t)
         self.count += 1
         return self
+
+
+# ------------------------------------------------------------------ scalar functionals: assemble(c*phi0*dot(u, n)*ds(1)), errornorm, project
+class FacetNormal:
+    """Outward unit normal of the boundary facets; only meaningful inside dot(u, n) under a ds measure."""
+
+    def __init__(self, mesh, sign=1.0):
+        self.mesh, self.sign = mesh, sign
+
+    def __neg__(self):
+        return FacetNormal(self.mesh, -self.sign)
+
+
+class Measure:
+    """Measure("dx") / Measure("ds", subdomain_data=facets) / the 2017-style Measure("ds")[facets]; ds(1) selects a marker value."""
+
+    def __init__(self, kind, domain=None, subdomain_data=None, subdomain_id=None):
+        if kind not in ("dx", "ds"):
+            raise NotImplementedError("measure %r" % (kind,))
+        self.kind, self.data, self.sid = kind, subdomain_data, subdomain_id
+
+    def __getitem__(self, data):
+        return Measure(self.kind, subdomain_data=data, subdomain_id=self.sid)
+
+    def __call__(self, subdomain_id=None, subdomain_data=None, domain=None):
+        return Measure(self.kind, subdomain_data=subdomain_data if subdomain_data is not None else self.data, subdomain_id=subdomain_id)
+
+    def __rmul__(self, integrand):
+        return _Integral(_Integrand.of(integrand), self)
+
+
+dx = Measure("dx")
+ds = Measure("ds")
+
+
+class _Integrand:
+    """coef * prod(scalar Lagrange Functions) * (vector Function . direction): what the in-scope functionals are made of."""
+
+    def __init__(self, coef=1.0, scalars=(), vector=None, direction=None):
+        self.coef, self.scalars, self.vector, self.direction = float(coef), tuple(scalars), vector, direction
+
+    @staticmethod
+    def of(x):
+        if isinstance(x, _Integrand):
+            return x
+        if isinstance(x, (int, float)):
+            return _Integrand(float(x))
+        if isinstance(x, Constant) and x.value.size == 1:
+            return _Integrand(float(x))
+        if isinstance(x, Function):
+            if len(x.blocks) != 1:
+                raise NotImplementedError("a vector Function can enter a functional only through dot(u, n) / dot(u, Constant)")
+            return _Integrand(1.0, (x,))
+        raise NotImplementedError("integrand factor %r" % (x,))
+
+    def __mul__(self, other):
+        if isinstance(other, Measure):
+            return _Integral(self, other)
+        o = _Integrand.of(other)
+        if self.vector is not None and o.vector is not None:
+            raise NotImplementedError("two vector factors in one functional")
+        return _Integrand(self.coef * o.coef, self.scalars + o.scalars, self.vector or o.vector, self.direction if self.vector is not None else o.direction)
+
+    __rmul__ = __mul__
+
+    def __neg__(self):
+        return self * -1.0
+
+
+def dot(u, n):
+    """dot(velocity Function, FacetNormal | Constant vector): the flux factor of a boundary functional."""
+    if isinstance(n, Function) and not isinstance(u, Function):
+        u, n = n, u
+    if not isinstance(u, Function) or len(u.blocks) != u.space.mesh.dim:
+        raise NotImplementedError("dot: first argument must be a vector Function")
+    if isinstance(n, FacetNormal):
+        return _Integrand(n.sign, (), u, None)
+    if isinstance(n, Constant):
+        return _Integrand(1.0, (), u, tuple(float(v) for v in n.value))
+    raise NotImplementedError("dot(u, %r)" % (n,))
+
+
+class _Integral:
+    def __init__(self, integrand, measure):
+        self.integrand, self.measure = integrand, measure
+
+    def __add__(self, other):
+        return _IntegralSum([self, other])
+
+    def __neg__(self):
+        return _Integral(self.integrand * -1.0, self.measure)
+
+    def __sub__(self, other):
+        return _IntegralSum([self, -other])
+
+
+class _IntegralSum:
+    def __init__(self, terms):
+        self.terms = list(terms)
+
+    def __add__(self, other):
+        return _IntegralSum(self.terms + (other.terms if isinstance(other, _IntegralSum) else [other]))
+
+
+_INTEGRATORS = {}
+
+
+def _integrator(mesh):
+    from .functional import Integrator
+    key = id(mesh)
+    if key not in _INTEGRATORS:
+        _INTEGRATORS[key] = (mesh, Integrator(default_context(), mesh))       # the mesh reference keeps id() valid
+    return _INTEGRATORS[key][1]
+
+
+def _assemble_integral(term):
+    ig, ms = term.integrand, term.measure
+    fns = list(ig.scalars) + ([ig.vector] if ig.vector is not None else [])
+    if not fns:
+        raise NotImplementedError("a functional needs at least one Function (the mesh comes from it)")
+    mesh = fns[0].space.mesh
+    it = _integrator(mesh)
+    scal = []
+    for f in ig.scalars:
+        per = f.space.periodic
+        scal.append((f.blocks[0], f.block_degree(0), per.vert2dof if per is not None else None))
+    vec = None
+    if ig.vector is not None:
+        u = ig.vector
+        if u.cell_velocity is not None:
+            vec = ("cell", u.cell_velocity)
+        else:
+            vec = ("lagrange", u.blocks, u.block_degree(0))
+    if ms.kind == "ds" and ms.sid is not None and ms.data is None:
+        raise ValueError("ds(%r) needs subdomain_data (a FacetFunction)" % (ms.sid,))
+    return it.integrate(ms.kind, scal, vec, ig.direction, ig.coef, ms.data, ms.sid)
+
+
+def assemble(form, **kw):
+    """dolfin.assemble for SCALAR functionals (run/CCS2D/CCS_3comp.py:277; run/stokes_ADR_3D/master_advective_stokes.py:232-265),
+    evaluated on the GPU by mp_integrate.  Bilinear / linear forms are assembled inside solve(); use assemble_system for the shims."""
+    if isinstance(form, _IntegralSum):
+        return sum(_assemble_integral(t) for t in form.terms)
+    if isinstance(form, _Integral):
+        return _assemble_integral(form)
+    raise NotImplementedError("assemble: only scalar functionals `integrand*dx` / `integrand*ds(id)` are supported here")
+
+
+def errornorm(u, uh, norm_type="L2", degree_rise=3, mesh=None):
+    """sqrt(int |u - uh|^2 dx) for two Functions of the same space (benchmark/sphere_3D_pure_shear/sphere.py:157-159: both sides are
+    Functions of one space, for which DOLFIN's degree-raised interpolation reproduces the difference exactly); a non-Function `u`
+    is interpolated into uh's space first."""
+    if norm_type.lower() != "l2":
+        raise NotImplementedError("errornorm: only the L2 norm")
+    if not isinstance(u, Function):
+        u = interpolate_like(u, uh)
+    if len(u.blocks) != len(uh.blocks) or any(a.numel() != b.numel() for a, b in zip(u.blocks, uh.blocks)):
+        raise NotImplementedError("errornorm: the two Functions must live in the same space")
+    ctx = default_context()
+    it = _integrator(uh.space.mesh)
+    per = uh.space.periodic
+    v2d = per.vert2dof if per is not None else None
+    tot = 0.0
+    for k, (a, b) in enumerate(zip(u.blocks, uh.blocks)):
+        e = a.clone()
+        ctx.axpby(-1.0, b, 1.0, e)
+        deg = uh.block_degree(k)
+        tot += it.integrate("dx", [(e, deg, v2d), (e, deg, v2d)])
+    return math.sqrt(max(tot, 0.0))
+
+
+def interpolate_like(v, f):
+    """A new Function with f's blocks holding the interpolant of v."""
+    g = Function(f.space, [b.clone() for b in f.blocks], list(f.ids))
+    g.interpolate(v)
+    return g
+
+
+def project(v, V, **kw):
+    """L2 projection onto V.  An Expression is first interpolated into its own element (degree <= V's: the projection of a function
+    that already lies in V is the function itself -- `project(darcy.perm, X)`, run/CCS2D/CCS_3comp.py:293); a Function of another
+    degree goes through the consistent mass system M_V x = int v phi_i (Jacobi-PCG on the GPU)."""
+    f = Function(V)
+    if isinstance(v, Function) and any(a.numel() != b.numel() for a, b in zip(v.blocks, f.blocks)):
+        from . import moder
+        ctx = default_context()
+        if V.periodic is not None:
+            raise NotImplementedError("project between degrees on a periodic space")
+        sp = moder.Spaces(ctx, V.mesh)
+        for k in range(len(f.blocks)):
+            dt_, ds_ = f.block_degree(k), v.block_degree(k)
+            rhs = ctx.zeros(sp.ndof(dt_))
+            sp.assemble("mass", dt_, ds_).spmv(v.blocks[k], rhs)
+            M = sp.assemble("mass", dt_, dt_)
+            r = M.solve("pcg", rhs, f.blocks[k], rtol=1e-13, maxit=5000)
+            if not r.converged:
+                raise RuntimeError("project: mass solve did not converge (%r)" % (r,))
+        return f
+    f.interpolate(v)
+    return f
+
+
+# ------------------------------------------------------------------ assemble_system / KrylovSolver shims
+class Matrix:
+    """Placeholder for dolfin.Matrix(): the scripts only create it to receive assemble_system's result."""
+
+
+class Vector:
+    """Placeholder for dolfin.Vector()."""
+
+
+class _AssembledSystem:
+    def __init__(self, form, rhs_form, bcs):
+        self.form, self.rhs_form, self.bcs = form, rhs_form, bcs
+
+
+def assemble_system(a, L, bcs=None, **kw):
+    """dolfin.assemble_system(a, L, bcs) (modules/mupopp.py:295-297,415-417; run/sphere_archer/sphere.py:199-202,256-258): on the B200
+    path the element kernels, the scatter and the symmetric Dirichlet elimination run inside the solver call, so this only binds the
+    form descriptors and the boundary conditions; KrylovSolver.solve(x, b) executes them."""
+    bcs = [] if bcs is None else (list(bcs) if isinstance(bcs, (list, tuple)) else [bcs])
+    s = _AssembledSystem(a, L, bcs)
+    return s, s
+
+
+class KrylovSolver:
+    """dolfin.KrylovSolver(method, preconditioner) with .parameters, .set_operators(A, P), .solve(x, b)
+    (modules/mupopp.py:289-303,410-425).  A, P, b come from assemble_system; x is `U.vector()`."""
+
+    def __init__(self, method="default", preconditioner="default"):
+        self.method, self.preconditioner = method, preconditioner
+        self.parameters = {"relative_tolerance": 1.0e-6, "absolute_tolerance": 1.0e-15, "maximum_iterations": 10000,
+                           "monitor_convergence": False, "nonzero_initial_guess": False, "error_on_nonconvergence": True, "report": True}
+        self.A = self.P = None
+
+    def set_operators(self, A, P=None):
+        self.A, self.P = A, P
+
+    def set_operator(self, A):
+        self.A, self.P = A, None
+
+    def solve(self, x, b):
+        from . import mupopp as _mp
+        if not isinstance(self.A, _AssembledSystem):
+            raise TypeError("KrylovSolver: operators must come from assemble_system(a, L, bcs)")
+        if not isinstance(x, _VectorView):
+            raise TypeError("KrylovSolver.solve: pass `u.vector()` as the solution vector")
+        return _mp._krylov_dispatch(self.A.form, x.f, self.A.bcs, float(self.parameters["relative_tolerance"]),
+                                    int(self.parameters["maximum_iterations"]), bool(self.parameters["monitor_convergence"]))
+
+
+class LUSolver:
+    def __init__(self, A=None, method="default"):
+        self.A = A
+
+    def solve(self, x, b):
+        from . import mupopp as _mp
+        return _mp._krylov_dispatch(self.A.form, x.f, self.A.bcs, 1.0e-12, 100000, False)
+
+
+import sys as _sys  # noqa: E402
+
+dolfin = _sys.modules[__name__]          # scripts write `dolfin.FunctionSpace(...)` after `from fenics import *`

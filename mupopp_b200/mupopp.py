@@ -70,6 +70,42 @@ def _kvalue(K):
     raise NotImplementedError("mode R on the GPU supports a constant permeability K (P1 K: mode F, mupopp_b200.transport)")
 
 
+# ---- which discretisation runs a multi-component solve
+#   "R": the reference's mixed P2/P1 space, segregated == monolithic LU (parity mode; constant K, no periodic faces yet)
+#   "F": primal P1 pressure operator + cellwise velocity recovery (BASELINE.json north_star (1)-(3); the benchmarked path)
+#   "auto" (default): F when the FunctionSpace has a periodic constrained_domain or K is a P1 field, else R.
+# Set with mupopp_b200.mupopp.set_mode(...), the environment variable MUPOPP_B200_MODE, or per call with
+# solve(..., solver_parameters={"mupopp_b200_mode": "F"}).
+import os as _os
+
+_MODE = _os.environ.get("MUPOPP_B200_MODE", "auto").upper()
+
+
+def set_mode(mode):
+    global _MODE
+    mode = str(mode).upper()
+    if mode not in ("R", "F", "AUTO"):
+        raise ValueError("mode must be 'R', 'F' or 'auto'")
+    _MODE = mode
+
+
+def _k_field(K, W):
+    """Permeability as the forms take it: a float, or the nodal values of a P1 field (Expression / Function, e.g. `K=darcy.perm`,
+    run/CCS2D/CCS_layered_permeability.py:233,250) at the P1 dofs of W.  Evaluated once per (coefficient, attribute fingerprint)."""
+    if isinstance(K, (int, float, Constant)):
+        return float(K)
+    from .modef_api import _value_signature
+    cache = W.__dict__.setdefault("_coef_cache", {})
+    key = ("K", _value_signature(K))
+    if key not in cache:
+        if isinstance(K, Function):
+            cache[key] = (K, K.blocks[0].cpu().numpy().copy())
+        else:
+            from .fenics import _evaluate
+            cache[key] = (K, _evaluate(K, W.dof_coords(1), 1)[:, 0].copy())
+    return cache[key][1]
+
+
 def _pair(kind, **data):
     return Form(kind, "a", **data), Form(kind, "L", **data)
 
@@ -95,7 +131,7 @@ class DarcyAdvection:
     def _multi(self, kind, W, mesh, sol_prev, dt, f1, K, zh, SUPG, gam_rho, rho_0):
         from .transport import TransportModel
         mk = TransportModel.darcy_two_component if kind == 2 else TransportModel.darcy_three_component
-        model = mk(Pe=self.Pe, Da=self.Da, phi=self.phi, alpha=self.alpha, dt=float(getattr(dt, "dt", dt)), K=_kvalue(K),
+        model = mk(Pe=self.Pe, Da=self.Da, phi=self.phi, alpha=self.alpha, dt=float(getattr(dt, "dt", dt)), K=_k_field(K, W),
                    zh=_zhat(zh, mesh.dim), SUPG=SUPG, gam_rho=gam_rho, rho_0=rho_0)
         return _pair("multi_component", W=W, mesh=mesh, sol_prev=sol_prev, f=f1, model=model)
 
@@ -116,7 +152,7 @@ class CCS:
     def advection_diffusion_three_component(self, W, mesh, sol_prev, dt, f_source, K=1.0, zh=Constant((0.0, 1.0)), SUPG=1, gam_rho=1.0):
         from .transport import TransportModel
         model = TransportModel.ccs_three_component(Pe=self.Pe, Da=self.Da, phi=self.phi, alpha=self.alpha, dt=float(getattr(dt, "dt", dt)),
-                                                   K=_kvalue(K), zh=_zhat(zh, mesh.dim), SUPG=SUPG, gam_rho=gam_rho)
+                                                   K=_k_field(K, W), zh=_zhat(zh, mesh.dim), SUPG=SUPG, gam_rho=gam_rho)
         return _pair("multi_component", W=W, mesh=mesh, sol_prev=sol_prev, f=f_source, model=model)
 
 
@@ -152,21 +188,8 @@ class compaction:
     def mass_solver(self, X, a_phi, L_phi, bb_phi, nits=100, tol=1.0e-6, monitor=False):
         """mupopp.py:261-304: assemble the porosity row and solve it (Jacobi-GMRES on the GPU; the reference runs `krylov_method`
         with AMG on this non-symmetric matrix).  Returns the new porosity Function."""
-        from . import compaction as _c, moder
-        d = a_phi.data
-        if d["V"].blocks[0][0] != 1:
-            raise NotImplementedError("compaction.mass_solver: only a P1 porosity space is on the B200 path (P2 needs div(grad(phi)))")
-        ctx = default_context()
-        mesh = d["mesh"]
-        sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
-        key = ("porosity", id(mesh), float(self.da))
-        if key not in _CACHE:
-            _CACHE[key] = _c.PorosityR(ctx, sp, self.da)
         sol = Function(X)
-        dt = float(getattr(d["dt"], "dt", d["dt"]))
-        res = _CACHE[key].solve(d["phi0"].blocks[0].clone(), d["u"].blocks, dt, d["gam"].blocks[0], sol.blocks[0], rtol=tol, maxit=max(nits, 1))
-        if monitor:
-            info("mass_solver: %s" % (res,))
+        _solve_compaction_mass(a_phi, sol, tol, max(nits, 1), monitor)
         return sol
 
     def momentum_conservation(self, W, phi, gam, buyoancy, zh=Constant((0.0, 0.0, 1.0))):
@@ -175,33 +198,10 @@ class compaction:
 
     def momentum_solver(self, W, a, L, b, bcs, pc="amg", tol=1.0e-6, max_its=3000, monitor=False):
         """mupopp.py:383-429: assemble_system(a, L, bcs), assemble_system(b, L, bcs), MINRES -> (u, p, c, niter).
-        On the GPU the preconditioner is the diagonal of the form `b` (the reference hands `b` to hypre AMG)."""
-        from . import compaction as _c, moder
-        d = a.data
-        ctx = default_context()
-        mesh = W.mesh
-        dim = mesh.dim
-        if d["phi"].space.blocks[0][0] != 1:
-            raise NotImplementedError("compaction.momentum_solver: only P1 phi/gam/buoyancy coefficients are on the B200 path")
+        On the GPU the preconditioner is built from the reference's own form `b` (which the reference hands to hypre AMG)."""
         bcs = list(bcs) if isinstance(bcs, (list, tuple)) else [bcs]
-        sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
-        key = ("compaction", id(W), _bc_key(bcs), self.da, self.R, self.B, self.theta, self.dL, tuple(_zhat(d["zh"], dim)))
-        if key not in _CACHE:
-            ub = W.sub_blocks[0]
-            arr = _bc_arrays(W, bcs, list(ub))
-            _CACHE[key] = _c.CompactionMomentumR(ctx, sp, self.da, self.R, self.B, self.theta, self.dL, _zhat(d["zh"], dim),
-                                                 [arr[k][0] for k in ub], [arr[k][1] for k in ub])
-        s = _CACHE[key]
-        s.assemble(d["phi"].blocks[0], d["gam"].blocks[0], d["buoyancy"].blocks[0])
-        x = _c.BlockVector(ctx, dim, sp.n2, sp.n1)
-        niter = s.solve(x, rtol=tol, maxit=max_its)
-        if monitor:
-            info("momentum_solver: %d MINRES iterations, relative residual %.3e" % (niter, s.last_relres))
         sol = Function(W)
-        for k in range(dim):
-            sol.blocks[k].copy_(x.u[k])
-        sol.blocks[dim].copy_(x.p)
-        sol.blocks[dim + 1].copy_(x.c)
+        niter = _solve_compaction_momentum(a, sol, bcs, tol, max_its, monitor)
         u, p, c = sol.split()
         return u, p, c, niter
 
@@ -212,6 +212,78 @@ class compaction:
 
 # ------------------------------------------------------------------ solve dispatch (called by fenics.solve)
 _CACHE = {}
+
+
+def _solve_compaction_mass(form, sol, tol, maxit, monitor=False):
+    """compaction.mass_conservation row (mupopp.py:217-259) -> sol; shared by compaction.mass_solver and the KrylovSolver shim."""
+    from . import compaction as _c, moder
+    d = form.data
+    own = d["owner"]
+    if d["V"].blocks[0][0] != 1:
+        raise NotImplementedError("compaction.mass_solver: only a P1 porosity space is on the B200 path (P2 needs div(grad(phi)))")
+    ctx = default_context()
+    mesh = d["mesh"]
+    sp = _spaces(ctx, mesh)
+    key = ("porosity", id(mesh), float(own.da))
+    if key not in _CACHE:
+        _CACHE[key] = _c.PorosityR(ctx, sp, own.da)
+    dt = float(getattr(d["dt"], "dt", d["dt"]))
+    res = _CACHE[key].solve(d["phi0"].blocks[0].clone(), d["u"].blocks, dt, d["gam"].blocks[0], sol.blocks[0], rtol=tol, maxit=maxit)
+    if monitor:
+        info("mass_solver: %s" % (res,))
+    return res.niter
+
+
+def _solve_compaction_momentum(form, sol, bcs, tol, maxit, monitor=False):
+    """compaction.momentum_conservation system (mupopp.py:306-382) -> sol = [u, p, c]; returns the MINRES iteration count."""
+    from . import compaction as _c
+    d = form.data
+    own = d["owner"]
+    W = d["W"]
+    ctx = default_context()
+    mesh = W.mesh
+    dim = mesh.dim
+    if d["phi"].space.blocks[0][0] != 1:
+        raise NotImplementedError("compaction.momentum_solver: only P1 phi/gam/buoyancy coefficients are on the B200 path")
+    sp = _spaces(ctx, mesh)
+    key = ("compaction", id(W), _bc_sig(bcs), own.da, own.R, own.B, own.theta, own.dL, tuple(_zhat(d["zh"], dim)))
+    if key not in _CACHE:
+        ub = W.sub_blocks[0]
+        arr = _bc_arrays(W, bcs, list(ub))
+        s_ = _c.CompactionMomentumR(ctx, sp, own.da, own.R, own.B, own.theta, own.dL, _zhat(d["zh"], dim),
+                                    [arr[k][0] for k in ub], [arr[k][1] for k in ub])
+        s_._keep = (W, list(bcs))
+        _CACHE[key] = s_
+    s = _CACHE[key]
+    s.assemble(d["phi"].blocks[0], d["gam"].blocks[0], d["buoyancy"].blocks[0])
+    x = _c.BlockVector(ctx, dim, sp.n2, sp.n1)
+    niter = s.solve(x, rtol=tol, maxit=maxit)
+    if monitor:
+        info("momentum_solver: %d MINRES iterations, relative residual %.3e" % (niter, s.last_relres))
+    for k in range(dim):
+        sol.blocks[k].copy_(x.u[k])
+    sol.blocks[dim].copy_(x.p)
+    sol.blocks[dim + 1].copy_(x.c)
+    return niter
+
+
+def _spaces(ctx, mesh):
+    from . import moder
+    key = ("spaces", id(mesh))
+    if key not in _CACHE:
+        sp = moder.Spaces(ctx, mesh)
+        sp._keep = mesh
+        _CACHE[key] = sp
+    return _CACHE[key]
+
+
+def _krylov_dispatch(form, sol, bcs, tol, maxit, monitor):
+    """KrylovSolver(...).solve(U.vector(), b) / LUSolver on operators from assemble_system (run/sphere_archer/sphere.py:193-207,256-286)."""
+    if form.kind == "compaction_momentum":
+        return _solve_compaction_momentum(form, sol, bcs, tol, maxit, monitor)
+    if form.kind == "compaction_mass":
+        return _solve_compaction_mass(form, sol, tol, maxit, monitor)
+    return _dispatch_solve(form, sol, bcs, {"relative_tolerance": tol})
 
 
 def _bc_arrays(space, bcs, block_ids):
@@ -234,6 +306,28 @@ def _bc_key(bcs):
     return tuple(id(b) for b in bcs)
 
 
+def _bc_sig(bcs):
+    from .modef_api import bc_signature
+    return bc_signature(bcs)
+
+
+def _source_nodal(f, W):
+    """Source term (user Expression subclass, Function, Constant, number) at the P1 dofs of W; evaluated once per fingerprint -- the
+    run scripts rebuild the forms every timestep with the same source object (run/CCS2D/CCS_3comp.py:249,260)."""
+    if f is None:
+        return None
+    from .modef_api import _value_signature
+    cache = W.__dict__.setdefault("_coef_cache", {})
+    key = ("f", _value_signature(f))
+    if key not in cache:
+        if isinstance(f, Function):
+            cache[key] = (f, f.blocks[0].cpu().numpy().copy())
+        else:
+            from .fenics import _evaluate
+            cache[key] = (f, _evaluate(f, W.dof_coords(1), 1)[:, 0].copy())
+    return cache[key][1]
+
+
 def _nodal(f, space_mesh):
     """A P1 coefficient given as Function / Expression / Constant / number -> nodal numpy array."""
     from .fenics import _evaluate
@@ -252,13 +346,14 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
     if kind == "darcy_bilinear":
         W, mesh = d["W"], d["mesh"]
         dim = mesh.dim
-        key = ("darcy", id(W), d["K"], _bc_key(bcs))
+        key = ("darcy", id(W), d["K"], _bc_sig(bcs))
         if key not in _CACHE:
-            sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+            sp = _spaces(ctx, mesh)
             arr = _bc_arrays(W, bcs, W.sub_blocks[0])
             isbc = [arr[b][0] for b in W.sub_blocks[0]]
             g = [arr[b][1] for b in W.sub_blocks[0]]
             _CACHE[key] = moder.MixedDarcyR(ctx, sp, K=d["K"], phi=1.0, u_isbc=isbc, u_g=g)
+            _CACHE[key]._keep = (W, list(bcs))
         darcy = _CACHE[key]
         sp = darcy.sp
         import torch
@@ -279,11 +374,15 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
         Q, mesh = d["Q"], d["mesh"]
         key = ("adr", id(Q), d["Pe"], d["Da"], d["dt"], _bc_key(bcs))
         if key not in _CACHE:
-            sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+            sp = _spaces(ctx, mesh)
             arr = _bc_arrays(Q, bcs, [0])
             vdeg = d["velocity"].block_degree(0)
             _CACHE[key] = moder.AdrSolverR(ctx, sp, moder.adr_single_params(d["Pe"], d["Da"], d["dt"]), arr[0][0], arr[0][1], vel_degree=vdeg)
+            _CACHE[key]._keep, _CACHE[key]._bc_sig = (Q, list(bcs)), _bc_sig(bcs)
         adr = _CACHE[key]
+        if _bc_sig(bcs) != adr._bc_sig:              # time-dependent boundary values (Constant.assign / Expression attribute)
+            adr.g.copy_(ctx.to_device(np.asarray(_bc_arrays(Q, bcs, [0])[0][1], dtype=np.float64)))
+            adr._bc_sig = _bc_sig(bcs)
         c_in = d["u0"].blocks[0].clone()             # u0 may alias the solution Function (c0 = sol_c in the script)
         res = adr.solve(d["velocity"].blocks, c_in, u.blocks[0])
         return res.niter
@@ -291,14 +390,39 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
         W, mesh, model = d["W"], d["mesh"], d["model"]
         dim = mesh.dim
         nc = model.ncomp
+        mode = str(solver_parameters.get("mupopp_b200_mode", _MODE)).upper()
+        if mode == "AUTO":
+            mode = "F" if (W.periodic is not None or not np.isscalar(model.K)) else "R"
+        fs = _source_nodal(d["f"], W)
+        if mode == "F":
+            from .modef_api import ModeFStepper
+            key = ("multiF", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.sigma, id(model.K) if not np.isscalar(model.K) else model.K)
+            if key not in _CACHE:
+                _CACHE[key] = ModeFStepper(ctx, W, bcs, model, fs, rtol=float(solver_parameters.get("relative_tolerance", 1e-12)))
+            st = _CACHE[key]
+            st.refresh(bcs, model, fs)
+            return st.step(d["sol_prev"], u)
+        if W.periodic is not None:
+            raise NotImplementedError("mode R has no periodic constrained_domain yet (SURVEY.md section 8 f1); use mode F")
+        if not np.isscalar(model.K):
+            raise NotImplementedError("mode R on the GPU supports a constant permeability K; a P1 K runs in mode F")
         key = ("multi", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.K, model.phi)
-        fs = _nodal(d["f"], mesh)
         if key not in _CACHE:
             ub = W.sub_blocks[0]
             arr = _bc_arrays(W, bcs, list(ub) + [W.sub_blocks[2][0]])
-            _CACHE[key] = moder.TransportSolverR(ctx, mesh, model, [arr[b][0] for b in ub], [arr[b][1] for b in ub],
-                                                 arr[W.sub_blocks[2][0]][0], arr[W.sub_blocks[2][0]][1], f_source=fs)
+            s_ = moder.TransportSolverR(ctx, mesh, model, [arr[b][0] for b in ub], [arr[b][1] for b in ub],
+                                        arr[W.sub_blocks[2][0]][0], arr[W.sub_blocks[2][0]][1], f_source=fs)
+            s_._keep = (W, list(bcs))           # keeps the ids in the cache key valid
+            s_._bc_sig = _bc_sig(bcs)
+            _CACHE[key] = s_
         s = _CACHE[key]
+        if _bc_sig(bcs) != s._bc_sig:           # boundary VALUES are re-evaluated when a Constant / Expression attribute changed
+            ub = W.sub_blocks[0]
+            arr = _bc_arrays(W, bcs, list(ub) + [W.sub_blocks[2][0]])
+            for c, b in enumerate(ub):
+                s.darcy.g[c].copy_(ctx.to_device(np.asarray(arr[b][1], dtype=np.float64)))
+            s.adr.g.copy_(ctx.to_device(np.asarray(arr[W.sub_blocks[2][0]][1], dtype=np.float64)))
+            s._bc_sig = _bc_sig(bcs)
         s.model, s.prm = model, moder.transport_params(model.Pe, model.Da, model.phi, model.alpha, model.dt, model.sigma, model.rho0,
                                                         model.gamma, model.fracs, model.zhat, model.K, model.reaction, model.ncomp, model.SUPG)
         s.adr.prm = s.prm
@@ -323,13 +447,14 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
         return info_
     if kind == "two_component_adaptive":
         Q, mesh, own = d["Q"], d["mesh"], d["owner"]
-        key = ("adaptive", id(Q), own.Pe, own.Da, own.phi, own.alpha, own.dt, _bc_key(bcs))
+        key = ("adaptive", id(Q), own.Pe, own.Da, own.phi, own.alpha, own.dt, _bc_sig(bcs))
         if key not in _CACHE:
-            sp = _CACHE.setdefault(("spaces", id(mesh)), moder.Spaces(ctx, mesh))
+            sp = _spaces(ctx, mesh)
             arr = _bc_arrays(Q, bcs, [Q.sub_blocks[0][0]])
             b0 = Q.sub_blocks[0][0]
             _CACHE[key] = moder.TwoComponentAdaptiveR(ctx, sp, own.Pe, own.Da, own.phi, own.alpha, own.dt, arr[b0][0], arr[b0][1],
                                                       vel_degree=d["velocity"].block_degree(0))
+            _CACHE[key]._keep = (Q, list(bcs))
         s = _CACHE[key]
         prev = d["c_prev"]
         c0n, c1n = prev.blocks[0].clone(), prev.blocks[1].clone()
@@ -341,13 +466,14 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
         dim = mesh.dim
         vdeg = W.blocks[W.sub_blocks[0][0]][0]
         dt = float(getattr(d["dt"], "dt", d["dt"]))
-        key = ("stokes", id(W), _bc_key(bcs), own.Pe, own.Da, dt, d["SUPG"])
+        key = ("stokes", id(W), _bc_sig(bcs), own.Pe, own.Da, dt, d["SUPG"])
         if key not in _CACHE:
             ub = W.sub_blocks[0]
             c0b = W.sub_blocks[2][0]
             arr = _bc_arrays(W, bcs, list(ub) + [c0b])
             _CACHE[key] = _st.StokesAdrR(ctx, mesh, own.Pe, own.Da, dt, d["SUPG"], [arr[k][0] for k in ub], [arr[k][1] for k in ub],
                                          arr[c0b][0], arr[c0b][1], vdeg=vdeg)
+            _CACHE[key]._keep = (W, list(bcs))
         s = _CACHE[key]
         prev = d["sol_prev"]
         uv = s.u_views()

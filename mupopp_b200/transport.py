@@ -129,7 +129,7 @@ class TransportSolverF:
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
                  rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
-                 vert2dof=None, row_ordered=True, p_precond="jacobi", cheb_degree=3, p_guess="extrapolate"):
+                 vert2dof=None, row_ordered=True, p_precond="jacobi", cheb_degree=3, p_guess="previous"):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart

@@ -113,5 +113,70 @@ def test_form_descriptors_pair_up():
     a, L = api.DarcyAdvection().darcy_bilinear(W, mesh)
     eq = (a == L)
     assert isinstance(eq, fx.Equation) and eq.a.kind == "darcy_bilinear" and eq.a.data["K"] == 0.1 and eq.a.data["zhat"] == (0.0, 1.0)
-    with pytest.raises(NotImplementedError):
+
+
+def test_periodic_constrained_domain_from_subdomain():
+    """`FunctionSpace(mesh, element, constrained_domain=pbc)` with the PeriodicBoundary of run/CCS2D/CCS_3comp.py:131-143 (2-D) and the
+    doubly periodic box: the SubDomain.inside/map pair gives the same dof identification as mesh.box_periodic_map."""
+    from mupopp_b200.mesh import box_periodic_map
+    xmax, ymax = 8.0, 2.0
+    mesh = fx.RectangleMesh(fx.Point(0.0, 0.0), fx.Point(xmax, ymax), 8, 4)
+
+    class PeriodicBoundary(fx.SubDomain):
+        def inside(self, x, on_boundary):
+            return bool(fx.near(x[0], 0.0) and on_boundary)
+
+        def map(self, x, y):
+            if fx.near(x[0], xmax):
+                y[0] = x[0] - xmax
+                y[1] = x[1]
+            else:
+                y[0] = -1000
+                y[1] = -1000
+
+    cell = mesh.ufl_cell()
+    Qc = fx.FiniteElement("Lagrange", cell, 1)
+    W = fx.FunctionSpace(mesh, fx.MixedElement([fx.VectorElement("Lagrange", cell, 2), Qc, Qc, Qc, Qc]), constrained_domain=PeriodicBoundary())
+    ref = box_periodic_map(mesh, (0,))
+    assert W.periodic is not None and W.periodic.axes == (0,)
+    assert np.array_equal(W.periodic.vert2dof, ref.vert2dof)
+    assert all(nd == ref.ndof for (_, _, nd) in W.blocks) and len(W.blocks) == 6          # velocity is stored at the P1 dofs too
+    assert W.dim() == 6 * ref.ndof
+    X = fx.FunctionSpace(mesh, "CG", 1, constrained_domain=PeriodicBoundary())
+    assert X.dim() == ref.ndof
+
+    box = fx.BoxMesh(fx.Point(0, 0, 0), fx.Point(2, 2, 1), 3, 3, 2)
+
+    class PB3(fx.SubDomain):
+        def inside(self, x, on_boundary):
+            return bool((fx.near(x[0], 0.0) or fx.near(x[1], 0.0)) and not (fx.near(x[0], 2.0) or fx.near(x[1], 2.0)) and on_boundary)
+
+        def map(self, x, y):
+            y[:] = x
+            if fx.near(x[0], 2.0):
+                y[0] = x[0] - 2.0
+            if fx.near(x[1], 2.0):
+                y[1] = x[1] - 2.0
+
+    P3 = fx.periodic_map_from_subdomain(box, PB3())
+    ref3 = box_periodic_map(box, (0, 1))
+    assert np.array_equal(P3.vert2dof, ref3.vert2dof) and P3.axes == (0, 1)
+    with pytest.raises(AttributeError):
         fx.FunctionSpace(mesh, "CG", 1, constrained_domain=object())
+
+
+def test_facet_function_and_subdomain_marking():
+    """FacetFunction + SubDomain.mark + Measure('ds')[facets] as in run/CCS2D/CCS_3comp.py:112-119."""
+    mesh = fx.RectangleMesh(fx.Point(0.0, 0.0), fx.Point(8.0, 2.0), 8, 4)
+
+    class Plane(fx.SubDomain):
+        def inside(self, x, on_boundary):
+            return x[1] < fx.DOLFIN_EPS
+
+    facets = fx.FacetFunction("size_t", mesh)
+    Plane().mark(facets, 1)
+    ds = fx.Measure("ds")[facets]
+    owner, loc, n, meas = facets.facet_geometry(1)
+    assert len(owner) == 8 and np.allclose(n, [[0.0, -1.0]] * 8) and abs(meas.sum() - 8.0) < 1e-14
+    m1 = ds(1)
+    assert m1.kind == "ds" and m1.sid == 1 and m1.data is facets
