@@ -462,6 +462,10 @@ class ApiProblem:
         self.sol.cell_velocity = torch.zeros(3 * ncell, dtype=torch.float64, device=ctx.device)
         self._init = [saved["p"], saved["c0"], saved["c1"], saved["c2"], saved["u"]]
         self.zh = fx.Constant((0.0, 0.0, 1.0))
+        # one untimed call: solve() builds its GPU operators (scatter plan, constant matrices, boundary data) on first use
+        for t, src in zip(self.device_buffers()[0], self._init):
+            t.copy_(src)
+        self.step()
 
     def device_buffers(self):
         """Input state of a step = blocks [p, c0, c1, c2] of sol_0 + its cellwise velocity; result = the same of sol (+ the nodal velocity

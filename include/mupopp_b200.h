@@ -39,7 +39,11 @@ int64_t mp_ctx_launch_count(const mp_ctx *ctx);
  * enable with a sample capacity, then read (count, summed milliseconds) -- used by bench.py's roofline */
 int mp_ctx_timing(mp_ctx *ctx, int enable, int max_samples);
 int mp_ctx_timing_read(mp_ctx *ctx, int *nsamples, double *total_ms);
-/* tuning knobs for A/B measurements: "spmv_variant" = 0 SELL-32 when mirrored, else CSR CTA-stream (default), 1 CSR CTA-stream, 2 CSR sub-warp-per-row, 3 CSR warp-stream */
+/* tuning knobs for A/B measurements: "spmv_variant" = 0 SELL-32 when mirrored, else CSR CTA-stream (default), 1 CSR CTA-stream, 2 CSR sub-warp-per-row, 3 CSR warp-stream;
+ * "spmv_c8" = 1 (default) use the compressed (slice-uniform) SELL columns when the operator has them, 0 always the int32 columns;
+ * "spmv_lpr" = 0 (default) pick the lanes per row (1, 2 or 4) from the operator size, else force 1 / 2 / 4;
+ * "pcg_variant" = -1 (default: single-reduction CG on several GPUs, classic on one), 0 classic PCG, 1 single-reduction (Chronopoulos-Gear) PCG;
+ * "peer" = 0/1 NCCL or peer-memory collectives (after mp_comm_peer_attach) */
 int mp_ctx_set_option(mp_ctx *ctx, const char *name, int value);
 
 /* ------------------------------------------------------------------ mesh view (device pointers) */
@@ -73,6 +77,9 @@ int mp_plan_export_csr(mp_ctx *ctx, const mp_plan *plan, int32_t *d_rowptr, int3
 int mp_plan_destroy(mp_plan *plan);
 /* SELL-32 layout of the plan's pattern (library-owned device arrays): number of slices, padded entries, pointers */
 int mp_plan_sell_info(const mp_plan *plan, int64_t *nslice, int64_t *nentries, const int32_t **d_sliceptr, const int32_t **d_col);
+/* compressed column indices of the SELL-32 layout (slice-uniform offsets, see mp_csr): number of (slice, j) positions that needed explicit
+ * columns (-1: no compressed mirror) and the library-owned device arrays */
+int mp_plan_sellu_info(const mp_plan *plan, int64_t *nexplicit, const int32_t **d_meta, const int32_t **d_xcol);
 /* d_sell_vals[nentries] <- CSR values permuted into the SELL-32 layout (padding = 0); call after assembly / Dirichlet */
 int mp_csr_to_sell(mp_ctx *ctx, const mp_plan *plan, const double *d_csr_vals, double *d_sell_vals);
 
@@ -219,6 +226,12 @@ typedef struct {
     const int32_t *d_sell_sliceptr;
     const int32_t *d_sell_col;
     const double *d_sell_val;
+    /* optional compressed column indices of the SELL mirror (mp_plan_sellu_info), "slice-uniform offsets": for column position j of
+     * slice s, d_sell_meta[sliceptr[s]/32 + j] = (d << 1) | 1 when every row of the slice has col = row + d there, else (k << 1) with the
+     * 32 explicit columns at d_sell_xcol[32 k ..].  One int32 per (slice, j) instead of 32: SpMV streams ~8.2-9 instead of 12 bytes per
+     * nonzero on mesh-line numberings.  NULL -> d_sell_col is used */
+    const int32_t *d_sell_meta;
+    const int32_t *d_sell_xcol;
 } mp_csr;
 
 int mp_spmv(mp_ctx *ctx, const mp_csr *A, const double *d_x, double *d_y);

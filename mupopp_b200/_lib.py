@@ -52,7 +52,8 @@ class MpFunctional(C.Structure):
 class MpCsr(C.Structure):
     _fields_ = [("nrow", C.c_int64), ("ncol", C.c_int64), ("nnz", C.c_int64), ("max_row_nnz", C.c_int32), ("pad", C.c_int32),
                 ("d_rowptr", C.c_void_p), ("d_colidx", C.c_void_p), ("d_vals", C.c_void_p),
-                ("d_sell_sliceptr", C.c_void_p), ("d_sell_col", C.c_void_p), ("d_sell_val", C.c_void_p)]
+                ("d_sell_sliceptr", C.c_void_p), ("d_sell_col", C.c_void_p), ("d_sell_val", C.c_void_p),
+                ("d_sell_meta", C.c_void_p), ("d_sell_xcol", C.c_void_p)]
 
 
 class MpSolveInfo(C.Structure):
@@ -78,6 +79,7 @@ SIGNATURES = {
     "mp_plan_export_csr": (C.c_int, [_VP, _VP, _VP, _VP]),
     "mp_plan_destroy": (C.c_int, [_VP]),
     "mp_plan_sell_info": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(_VP), C.POINTER(_VP)]),
+    "mp_plan_sellu_info": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(_VP), C.POINTER(_VP)]),
     "mp_csr_to_sell": (C.c_int, [_VP, _VP, _VP, _VP]),
     "mp_scatter_matrix": (C.c_int, [_VP, _VP, _VP, _VP]),
     "mp_scatter_matrix_ordered": (C.c_int, [_VP, _VP, _VP, _VP]),

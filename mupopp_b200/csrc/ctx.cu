@@ -158,6 +158,9 @@ int64_t mp_ctx_launch_count(const mp_ctx *c) { return c ? c->launches : -1; }
 int mp_ctx_set_option(mp_ctx *c, const char *name, int value) {
     MP_CHECK(c && name, "mp_ctx_set_option: null argument");
     if (!strcmp(name, "spmv_variant")) { c->spmv_variant = value; return 0; }
+    if (!strcmp(name, "spmv_c8")) { c->spmv_c8 = value; return 0; }
+    if (!strcmp(name, "pcg_variant")) { MP_CHECK(value >= -1 && value <= 1, "pcg_variant must be -1, 0 or 1"); c->pcg_variant = value; return 0; }
+    if (!strcmp(name, "spmv_lpr")) { MP_CHECK(value == 0 || value == 1 || value == 2 || value == 4, "spmv_lpr must be 0, 1, 2 or 4"); c->spmv_lpr = value; return 0; }
     if (!strcmp(name, "peer")) {   // switch the peer-memory collectives on/off (A/B runs against the NCCL path); needs mp_comm_peer_attach
         MP_CHECK(!value || c->peer_attached, "mp_ctx_set_option: peer windows are not attached");
         return mp::set_peer_mode(c, value != 0);

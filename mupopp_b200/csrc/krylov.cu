@@ -140,39 +140,167 @@ k_spmv_warp(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__r
     if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
 }
 
-// ------------------------------------------------------------------ SpMV, SELL-32 (production kernel for P1 operators)
-// One lane per row; slice entries are stored [j][lane], so the (col,val) loads are perfectly coalesced and at step j the 32
-// lanes gather x at neighbouring columns.  Measured 0.26 ms at 200^3 (6.2 TB/s algorithmic, 94% of the measured copy peak)
-// against 0.34 ms for the best CSR variant (tools/spmv_lab.cu, profiles/r1_spmv_lab.txt).  __launch_bounds__(256, 8) keeps
-// 2048 resident threads per SM: the kernel is latency-bound below that.
-template <int DOT, bool GUARD>
+// ------------------------------------------------------------------ SpMV, SELL-32 (production kernels for P1 operators)
+// Slice entries are stored [j][lane], so the (col,val) loads are perfectly coalesced and at step j the lanes of a warp gather x at
+// neighbouring columns.  Measured 0.25 ms at 200^3 with int32 columns (6.4 TB/s algorithmic, 0.98 of the measured copy peak) against
+// 0.34 ms for the best CSR variant (tools/spmv_lab.cu, profiles/r1_spmv_lab.txt).  __launch_bounds__(256, 8) keeps 2048 resident
+// threads per SM: the kernel is latency-bound below that.  Two refinements, both bit-for-bit neutral for a fixed (C8, LPR) choice:
+//  * C8: compressed column indices ("slice-uniform offsets").  Rows numbered along a mesh line share their stencil offsets, so for most
+//    (slice, j) all 32 rows have col = row + d: ONE int32 per (slice, j) replaces 32 column indices, the rest keep explicit columns
+//    (slices that straddle the end of a mesh line, unstructured parts).  ~8.2-9 instead of 12 bytes per nonzero, and fewer per-lane
+//    instructions than the plain kernel (no column load for uniform positions).  A per-entry dictionary code (1 byte + shared-memory
+//    lookup) was tried first and was SLOWER than int32 columns (0.264 vs 0.254 ms at 200^3): the decode sat on the gather's critical path.
+//  * LPR lanes per row (1, 2, 4): a warp then covers 32/LPR rows of a slice and the lanes of a row take every LPR-th entry; the
+//    work unit shrinks to a half / quarter slice.  Meant for the 1 M-row slabs of an 8-GPU run (3.3 slices per resident warp); it
+//    measured slower than one lane per row at every size, so it is an experiment knob ("spmv_lpr"), not the default.
+template <bool GHOST>
+__device__ __forceinline__ double sell_x(const double *__restrict__ x, int32_t c, int64_t nown, const double *__restrict__ gw) {
+    if constexpr (GHOST) return c < nown ? x[c] : __ldcg(gw + c);     // ghost data arrived during this kernel: read it from L2
+    else return x[c];
+}
+
+// predicated loads (result 0 when the predicate is off; the address is then never dereferenced): they keep the batched inner loop of
+// the compressed kernel free of branches, so that the four gathers of a batch are in flight together
+__device__ __forceinline__ int32_t ld_nc_i32_if(const int32_t *p, bool pred) {
+    int32_t v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.b32 %0, 0;\n\t@q ld.global.nc.b32 %0, [%1];\n\t}" : "=r"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ double ld_nc_f64_if(const double *p, bool pred) {
+    double v;
+    asm("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.nc.f64 %0, [%1];\n\t}" : "=d"(v) : "l"(p), "r"((int)pred));
+    return v;
+}
+__device__ __forceinline__ double ld_cg_f64_if(const double *p, bool pred) {
+    double v;
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\tmov.f64 %0, 0d0000000000000000;\n\t@q ld.global.cg.f64 %0, [%1];\n\t}" : "=d"(v) : "l"(p), "r"((int)pred) : "memory");
+    return v;
+}
+template <bool GHOST>
+__device__ __forceinline__ double sell_x_if(const double *__restrict__ x, int32_t c, bool pred, int64_t nown, const double *__restrict__ gw) {
+    if constexpr (GHOST) {
+        const bool own = c < nown;
+        return ld_nc_f64_if(x + c, pred && own) + ld_cg_f64_if(gw + c, pred && !own);     // exactly one of the two is loaded
+    } else {
+        return ld_nc_f64_if(x + c, pred);
+    }
+}
+
+// Row sums of one work unit.  The loads are issued in explicit batches of four (columns, values, then the four gathers): what bounds
+// this kernel is memory-level parallelism, and a plain `#pragma unroll 4` of a loop with a per-lane trip count compiles to four
+// SERIAL load->gather->FMA chains (seen in the SASS: 0.31 instead of 0.25 ms at 200^3).  The additions keep the sequential order.
+template <bool C8, int LPR, bool GHOST>
+__device__ __forceinline__ double sell_unit(int64_t unit, int lane, int64_t nrow, const int32_t *__restrict__ sliceptr,
+                                            const int32_t *__restrict__ scol, const double *__restrict__ sval,
+                                            const int32_t *__restrict__ meta, const int32_t *__restrict__ xcol,
+                                            const double *__restrict__ x, int64_t nown, const double *__restrict__ gw, int64_t &row_out) {
+    constexpr int RPU = 32 / LPR;                       // rows per unit
+    const int64_t s = unit / LPR;
+    const int rl = (int)(unit % LPR) * RPU + (lane % RPU);   // row inside the slice
+    const int part = lane / RPU;                        // which share of the row's entries this lane sums
+    const int32_t b = sliceptr[s];
+    const int64_t row = (s << 5) + rl;
+    const int wfull = (sliceptr[s + 1] - b) >> 5;
+    const bool live = row < nrow;                       // rows past the end of the last slice do nothing
+    const int32_t kb = b + rl;
+    double sum = 0.0;
+    if constexpr (C8) {
+        // slice-uniform offsets: one int32 per (slice, j); the lanes fetch up to 32 of them with one coalesced load and hand them
+        // around with shuffles, so a uniform position costs NO per-lane column load at all
+        for (int j0 = 0; j0 < wfull; j0 += 32) {
+            const int32_t mine = (j0 + lane < wfull) ? meta[(b >> 5) + j0 + lane] : 0;
+            const int jend = min(wfull - j0, 32);
+            for (int base = 0; base < jend; base += 4 * LPR) {          // warp-uniform trip count: every lane takes part in the shuffles
+                int32_t m[4], c[4];
+                double v[4], xv[4];
+                bool ok[4];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) {
+                    const int jj = base + part + t * LPR;
+                    m[t] = __shfl_sync(0xffffffffu, mine, jj & 31);
+                    ok[t] = live && jj < jend;
+                }
+#pragma unroll
+                for (int t = 0; t < 4; ++t) c[t] = ld_nc_i32_if(xcol + (((int64_t)(m[t] >> 1) << 5) + rl), ok[t] && !(m[t] & 1));
+#pragma unroll
+                for (int t = 0; t < 4; ++t) v[t] = ld_nc_f64_if(sval + (kb + 32 * (j0 + base + part + t * LPR)), ok[t]);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) c[t] = (m[t] & 1) ? (int32_t)row + (m[t] >> 1) : c[t];
+#pragma unroll
+                for (int t = 0; t < 4; ++t) xv[t] = sell_x_if<GHOST>(x, c[t], ok[t], nown, gw);
+#pragma unroll
+                for (int t = 0; t < 4; ++t) sum += v[t] * xv[t];
+            }
+        }
+    } else {
+        const int w = live ? wfull : 0;
+        int j = part;
+        for (; j + 3 * LPR < w; j += 4 * LPR) {
+            const int32_t k = kb + 32 * j;
+            int32_t c[4];
+            double v[4], xv[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) c[t] = scol[k + 32 * LPR * t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) v[t] = sval[k + 32 * LPR * t];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) xv[t] = sell_x<GHOST>(x, c[t], nown, gw);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) sum += v[t] * xv[t];
+        }
+        if (j < w) {                                    // up to three left: one more (predicated) batch
+            const int32_t k = kb + 32 * j;
+            const bool o1 = j + LPR < w, o2 = j + 2 * LPR < w;
+            const int32_t c0 = scol[k], c1 = o1 ? scol[k + 32 * LPR] : c0, c2 = o2 ? scol[k + 64 * LPR] : c0;
+            const double v0 = sval[k], v1 = o1 ? sval[k + 32 * LPR] : 0.0, v2 = o2 ? sval[k + 64 * LPR] : 0.0;
+            const double x0 = sell_x<GHOST>(x, c0, nown, gw), x1 = sell_x<GHOST>(x, c1, nown, gw), x2 = sell_x<GHOST>(x, c2, nown, gw);
+            sum += v0 * x0;
+            if (o1) sum += v1 * x1;
+            if (o2) sum += v2 * x2;
+        }
+    }
+#pragma unroll
+    for (int o = RPU; o < 32; o <<= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    row_out = (part == 0 && live) ? row : -1;           // the lane that owns the row's result (dead lanes: none)
+    return sum;
+}
+
+struct SellArgs {
+    int64_t nrow;
+    const int32_t *sliceptr, *scol;
+    const double *sval;
+    const int32_t *meta, *xcol;
+};
+
+template <int DOT, bool GUARD, bool C8, int LPR>
 __global__ void __launch_bounds__(kThreads, 8)
-k_spmv_sell(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *__restrict__ scol, const double *__restrict__ sval,
-            const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
+k_spmv_sell(SellArgs A, const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
             mp::ReduceCtl *ctl, double *scal, int slot0, int slot1) {
     if (GUARD && !solver_active(scal)) return;
     const int lane = threadIdx.x & 31;
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
-    const int64_t nslice = (nrow + 31) >> 5;
+    const int64_t nunit = ((A.nrow + 31) >> 5) * LPR;
     double acc[DOT == 0 ? 1 : DOT];
 #pragma unroll
     for (int r = 0; r < (DOT == 0 ? 1 : DOT); ++r) acc[r] = 0.0;
     (void)acc;
-    for (int64_t s = warp; s < nslice; s += nwarp) {
-        const int32_t b = sliceptr[s], e = sliceptr[s + 1];
-        double sum = 0.0;
-#pragma unroll 4
-        for (int32_t k = b + lane; k < e; k += 32) sum += sval[k] * x[scol[k]];
-        const int64_t row = (s << 5) + lane;
-        if (row < nrow) {
+    for (int64_t u = warp; u < nunit; u += nwarp) {
+        int64_t row;
+        const double sum = sell_unit<C8, LPR, false>(u, lane, A.nrow, A.sliceptr, A.scol, A.sval, A.meta, A.xcol, x, 0, nullptr, row);
+        if (row >= 0) {
             y[row] = sum;
-            if constexpr (DOT == 1) acc[0] += w[row] * sum;
+            if constexpr (DOT == 1 || DOT == 3) acc[0] += w[row] * sum;
             if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
         }
     }
     if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, ctl, scal, sl_, false); }
     if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
+    if constexpr (DOT == 3) {   // single-reduction CG: w.u plus the vector kernel's rank-local r.u, r.r in ONE exchange; iter++
+        if (blockIdx.x == 0 && threadIdx.x == 0) { acc[1] += scal[S_GLOC]; acc[2] += scal[S_RRLOC]; }
+        const int sl_[3] = {slot0, slot1, S_RR};
+        grid_reduce<3>(acc, partials, ctl, scal, sl_, true);
+    }
 }
 
 // ------------------------------------------------------------------ SELL-32 SpMV fused with the halo exchange over peer memory
@@ -185,10 +313,9 @@ k_spmv_sell(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *_
 //      push s+1 only after its own SpMV s, for which it needed MY push s, which I issue after finishing SpMV s-1.
 // Row sums and dot partials are accumulated in the same fixed order on every run (interior slices ascending, then the boundary
 // list ascending), so results stay bitwise reproducible.
-template <int DOT, bool GUARD>
+template <int DOT, bool GUARD, bool C8, int LPR>
 __global__ void __launch_bounds__(kThreads, 8)
-k_spmv_sell_peer(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32_t *__restrict__ scol, const double *__restrict__ sval,
-                 const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
+k_spmv_sell_peer(SellArgs A, const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ w, double *partials,
                  mp::ReduceCtl *ctl, double *scal, int slot0, int slot1, mp::HaloDev *H) {
     if (GUARD && !solver_active(scal)) return;
     const unsigned long long seq = H->seq;            // bumped by the last block to finish, i.e. after every block has read it
@@ -217,29 +344,26 @@ k_spmv_sell_peer(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32
     // ---- 2. interior slices
     const int64_t warp = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarp = (gridDim.x * (int64_t)blockDim.x) >> 5;
-    const int64_t nslice = (nrow + 31) >> 5;
+    const int64_t nunit = ((A.nrow + 31) >> 5) * LPR;
     const uint8_t *__restrict__ kind = H->slice_kind;
     double acc[DOT == 0 ? 1 : DOT];
 #pragma unroll
     for (int r = 0; r < (DOT == 0 ? 1 : DOT); ++r) acc[r] = 0.0;
     (void)acc;
-    for (int64_t s = warp; s < nslice; s += nwarp) {
-        if (kind[s]) continue;
-        const int32_t b = sliceptr[s], e = sliceptr[s + 1];
-        double sum = 0.0;
-#pragma unroll 4
-        for (int32_t k = b + lane; k < e; k += 32) sum += sval[k] * x[scol[k]];
-        const int64_t row = (s << 5) + lane;
-        if (row < nrow) {
+    for (int64_t u = warp; u < nunit; u += nwarp) {
+        if (kind[u / LPR]) continue;
+        int64_t row;
+        const double sum = sell_unit<C8, LPR, false>(u, lane, A.nrow, A.sliceptr, A.scol, A.sval, A.meta, A.xcol, x, 0, nullptr, row);
+        if (row >= 0) {
             y[row] = sum;
-            if constexpr (DOT == 1) acc[0] += w[row] * sum;
+            if constexpr (DOT == 1 || DOT == 3) acc[0] += w[row] * sum;
             if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
         }
     }
-    // ---- 3. boundary slices (handed to the warps from the top end: those got one interior slice fewer)
+    // ---- 3. boundary slices (handed to the warps from the top end: those got one interior unit fewer)
     const int64_t rwarp = nwarp - 1 - warp;
-    const int32_t nb = H->nbslice;
-    if (rwarp < nb) {
+    const int64_t nbu = (int64_t)H->nbslice * LPR;
+    if (rwarp < nbu) {
         int ok = 1;
         if (lane == 0)
             for (int k = 0; k < nneigh; ++k) ok &= wait_flag(H->flag + 2 * k + par, seq) ? 1 : 0;
@@ -247,20 +371,13 @@ k_spmv_sell_peer(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32
         if (!ok && lane == 0) scal[S_RR] = __longlong_as_double(0x7ff8000000000000ll);   // dead neighbour: the host sees a NaN residual
         const int64_t nown = H->nown;
         const double *__restrict__ gw = H->gwin + (int64_t)par * H->nghost - nown;
-        for (int64_t i = rwarp; i < nb; i += nwarp) {
-            const int64_t s = H->bslices[i];
-            const int32_t b = sliceptr[s], e = sliceptr[s + 1];
-            double sum = 0.0;
-#pragma unroll 2
-            for (int32_t k = b + lane; k < e; k += 32) {
-                const int32_t c = scol[k];
-                const double xv = c < nown ? x[c] : __ldcg(gw + c);      // ghost data arrived during this kernel: read it from L2
-                sum += sval[k] * xv;
-            }
-            const int64_t row = (s << 5) + lane;
-            if (row < nrow) {
+        for (int64_t i = rwarp; i < nbu; i += nwarp) {
+            const int64_t u = (int64_t)H->bslices[i / LPR] * LPR + (i % LPR);
+            int64_t row;
+            const double sum = sell_unit<C8, LPR, true>(u, lane, A.nrow, A.sliceptr, A.scol, A.sval, A.meta, A.xcol, x, nown, gw, row);
+            if (row >= 0) {
                 y[row] = sum;
-                if constexpr (DOT == 1) acc[0] += w[row] * sum;
+                if constexpr (DOT == 1 || DOT == 3) acc[0] += w[row] * sum;
                 if constexpr (DOT == 2) { acc[0] += sum * w[row]; acc[1] += sum * sum; }
             }
         }
@@ -276,6 +393,11 @@ k_spmv_sell_peer(int64_t nrow, const int32_t *__restrict__ sliceptr, const int32
     }
     if constexpr (DOT == 1) { const int sl_[1] = {slot0}; grid_reduce<1>(acc, partials, ctl, scal, sl_, false); }
     if constexpr (DOT == 2) { const int sl_[2] = {slot0, slot1}; grid_reduce<2>(acc, partials, ctl, scal, sl_, false); }
+    if constexpr (DOT == 3) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) { acc[1] += scal[S_GLOC]; acc[2] += scal[S_RRLOC]; }
+        const int sl_[3] = {slot0, slot1, S_RR};
+        grid_reduce<3>(acc, partials, ctl, scal, sl_, true);
+    }
 }
 
 // ------------------------------------------------------------------ BLAS-1
@@ -430,6 +552,74 @@ __global__ void __launch_bounds__(kThreads) k_bicg_x(int64_t n, const double *__
 }
 
 
+// ------------------------------------------------------------------ single-reduction PCG (Chronopoulos & Gear), vector kernel
+// State: x, r, u = D^-1 r, w = A u, p, s = A p (by recurrence).  Per iteration ONE vector kernel and ONE SpMV kernel:
+//   beta = gamma/gamma_old ; alpha = gamma / (delta - beta gamma / alpha_old)           (scalars recomputed by every thread)
+//   p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; u = D^-1 r ; local sums gamma' = r.u, rr = r.r
+// then w = A u with delta' = w.u, and the three sums travel in ONE exchange inside the SpMV kernel (k_spmv_sell* DOT == 3).
+// Standard PCG needs two reduction points and three kernels per iteration; on 8 GPUs with 1 M rows each an iteration is ~50 us of
+// HBM traffic, so every exchange (~4 us over NVLink) and every launch gap counts.
+__global__ void __launch_bounds__(kThreads) k_cgcg_update(int64_t n, int first, const double *__restrict__ w, const double *__restrict__ dinv,
+                                                          double *__restrict__ u, double *__restrict__ p, double *__restrict__ s,
+                                                          double *__restrict__ x, double *__restrict__ r, double *partials,
+                                                          mp::ReduceCtl *ctl, double *scal, int cur, int nxt) {
+    if (!solver_active(scal)) return;
+    const double gamma = scal[S_G0 + cur], delta = scal[S_DELTA];
+    const double beta = first ? 0.0 : safe_div(gamma, scal[S_G0 + nxt]);
+    const double alpha = first ? safe_div(gamma, delta) : safe_div(gamma, delta - beta * safe_div(gamma, scal[S_AL0 + nxt]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_AL0 + cur] = alpha;          // nobody reads AL[cur] in this kernel
+    double acc[2] = {0.0, 0.0};
+    const int64_t stride = gridDim.x * (int64_t)blockDim.x;
+    for (int64_t i0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i0 < n; i0 += 2 * stride) {
+        double uu[2], ww[2], dd[2], pp[2], ss[2], xx[2], rr[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i < n) {
+                uu[k] = u[i]; ww[k] = w[i]; dd[k] = dinv[i]; xx[k] = x[i]; rr[k] = r[i];
+                pp[k] = first ? 0.0 : p[i];
+                ss[k] = first ? 0.0 : s[i];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int64_t i = i0 + k * stride;
+            if (i < n) {
+                const double pi = uu[k] + beta * pp[k], si = ww[k] + beta * ss[k];
+                p[i] = pi;
+                s[i] = si;
+                x[i] = xx[k] + alpha * pi;
+                const double ri = rr[k] - alpha * si;
+                r[i] = ri;
+                const double un = dd[k] * ri;
+                u[i] = un;
+                acc[0] += ri * un;
+                acc[1] += ri * ri;
+            }
+        }
+    }
+    const int sl_[2] = {S_GLOC, S_RRLOC};
+    grid_reduce<2>(acc, partials, ctl, scal, sl_, false, false, /*exchange=*/false);
+}
+
+// r = b - q ; u = dinv r ; dots bb, rr, gamma = r.u  (start of a single-reduction CG cycle)
+__global__ void __launch_bounds__(kThreads) k_cgcg_init(int64_t n, const double *__restrict__ b, const double *__restrict__ q,
+                                                        const double *__restrict__ dinv, double *__restrict__ r, double *__restrict__ u,
+                                                        double *partials, mp::ReduceCtl *ctl, double *scal, int slot_gamma) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += gridDim.x * (int64_t)blockDim.x) {
+        const double bi = b[i], ri = bi - q[i];
+        r[i] = ri;
+        const double ui = dinv[i] * ri;
+        u[i] = ui;
+        acc[0] += bi * bi;
+        acc[1] += ri * ri;
+        acc[2] += ri * ui;
+    }
+    const int sl_[3] = {S_BB, S_RR, slot_gamma};
+    grid_reduce<3>(acc, partials, ctl, scal, sl_, false);
+}
+
 // ------------------------------------------------------------------ Chebyshev polynomial preconditioner (Jacobi-scaled)
 // z = p_k(D^-1 A) D^-1 r on [lmin, lmax]:  the "Chebyshev" option of BASELINE.json's north_star.  k-1 SpMVs per application and
 // no inner products, so a PCG iteration does k SpMVs per pair of reductions (what matters once the allreduce latency dominates).
@@ -524,6 +714,41 @@ int pick_lanes(const mp_csr *A, int64_t nnz_hint) {
     return 32;
 }
 
+// grid / variant choice of the SELL kernels: compressed columns when the operator has them, lanes per row from the unit count
+inline int sell_lpr(const mp_ctx *ctx, int64_t nslice) {
+    // measured (profiles/r2_spmv_variants.md): 2 or 4 lanes per row are SLOWER than one at every size tried, 8 M rows down to the 1 M-row
+    // slab of an 8-GPU run (0.0329 / 0.0386 / 0.0508 ms), so one lane per row is the default and the others stay as an experiment knob
+    (void)nslice;
+    if (ctx->spmv_lpr == 2 || ctx->spmv_lpr == 4) return ctx->spmv_lpr;
+    return 1;
+}
+
+template <int DOT, bool GUARD>
+int launch_sell(mp_ctx *ctx, const mp_csr *A, mp_halo *halo, const double *x, double *y, const double *w, int slot0, int slot1) {
+    const int64_t nslice = (A->nrow + 31) / 32;
+    const int lpr = sell_lpr(ctx, nslice);
+    const bool c8 = ctx->spmv_c8 && A->d_sell_meta && A->d_sell_xcol;
+    const int64_t nunit = nslice * lpr;
+    int64_t nblk = (nunit + (kThreads / 32) - 1) / (kThreads / 32);
+    int64_t cap = (int64_t)ctx->num_sm * 8;
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    const int g = (int)(nblk < cap ? nblk : cap);
+    SellArgs S{A->nrow, A->d_sell_sliceptr, A->d_sell_col, A->d_sell_val, A->d_sell_meta, A->d_sell_xcol};
+#define MP_SELL(C8_, LPR_)                                                                                                              \
+    do {                                                                                                                                \
+        if (halo) k_spmv_sell_peer<DOT, GUARD, C8_, LPR_><<<g, kThreads, 0, ctx->stream>>>(S, x, y, w, ctx->d_partials, ctx->d_ctl,     \
+                                                                                            ctx->d_scalars, slot0, slot1, halo->d_dev); \
+        else k_spmv_sell<DOT, GUARD, C8_, LPR_><<<g, kThreads, 0, ctx->stream>>>(S, x, y, w, ctx->d_partials, ctx->d_ctl,               \
+                                                                                  ctx->d_scalars, slot0, slot1);                        \
+    } while (0)
+    if (c8) { if (lpr == 1) MP_SELL(true, 1); else if (lpr == 2) MP_SELL(true, 2); else MP_SELL(true, 4); }
+    else { if (lpr == 1) MP_SELL(false, 1); else if (lpr == 2) MP_SELL(false, 2); else MP_SELL(false, 4); }
+#undef MP_SELL
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
 constexpr int kStreamCap = 2048;  // products (doubles) parked in shared memory per CTA
 
 template <int DOT, bool GUARD>
@@ -534,19 +759,11 @@ int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double
     if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
     const double avg = (double)A->nnz / (double)A->nrow;
     if (A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0) {
-        const int64_t nslice = (A->nrow + 31) / 32;
-        int64_t nblk = (nslice + (kThreads / 32) - 1) / (kThreads / 32);
-        int64_t cap = (int64_t)ctx->num_sm * 8;
-        if (cap > kMaxBlocks) cap = kMaxBlocks;
-        const int g = (int)(nblk < cap ? nblk : cap);
-        k_spmv_sell<DOT, GUARD><<<g, kThreads, 0, ctx->stream>>>(A->nrow, A->d_sell_sliceptr, A->d_sell_col, A->d_sell_val, x, y, w,
-                                                                  ctx->d_partials, ctx->d_ctl, ctx->d_scalars, slot0, slot1);
+        MP_TRY((launch_sell<DOT, GUARD>(ctx, A, nullptr, x, y, w, slot0, slot1)));
         if (timed) {
             cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
             ctx->tev_used += 2;
         }
-        mp::count_launch(ctx);
-        MP_CUDA(cudaGetLastError());
         return 0;
     }
     if (ctx->spmv_variant == 3 && A->max_row_nnz > 0 && A->max_row_nnz <= 32 && A->max_row_nnz <= 3.0 * avg + 2.0) {
@@ -625,19 +842,11 @@ int spmv_halo(mp_ctx *ctx, const mp_csr *A, mp_halo *halo, int lanes, double *x,
         MP_TRY(mp::halo_classify(ctx, halo, A->nrow, A->d_sell_sliceptr, A->d_sell_col));
         const bool timed = ctx->timing && ctx->tev_used + 2 <= ctx->tev.size();
         if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
-        const int64_t nslice = (A->nrow + 31) / 32;
-        int64_t nblk = (nslice + (kThreads / 32) - 1) / (kThreads / 32);
-        int64_t cap = (int64_t)ctx->num_sm * 8;
-        if (cap > kMaxBlocks) cap = kMaxBlocks;
-        const int g = (int)(nblk < cap ? nblk : cap);
-        k_spmv_sell_peer<DOT, GUARD><<<g, kThreads, 0, ctx->stream>>>(A->nrow, A->d_sell_sliceptr, A->d_sell_col, A->d_sell_val, x, y, w,
-                                                                       ctx->d_partials, ctx->d_ctl, ctx->d_scalars, slot0, slot1, halo->d_dev);
+        MP_TRY((launch_sell<DOT, GUARD>(ctx, A, halo, x, y, w, slot0, slot1)));
         if (timed) {
             cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
             ctx->tev_used += 2;
         }
-        mp::count_launch(ctx);
-        MP_CUDA(cudaGetLastError());
         return 0;
     }
     MP_TRY(mp_halo_exchange(ctx, halo, x));
@@ -973,10 +1182,64 @@ extern "C" int mp_jacobi_setup(mp_ctx *ctx, const mp_csr *A, double *d_dinv) {
     return 0;
 }
 
+namespace {
+// Single-reduction PCG driver (see k_cgcg_update).  Needs the SELL mirror (the fused three-sum exchange lives in the SELL kernels) and,
+// on several GPUs, the peer-memory transport; mp_solve_pcg falls back to the classic recurrence otherwise.
+int solve_pcg_single_reduction(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
+                               mp_solve_info *info) {
+    const int64_t n = A->nrow, nc = A->ncol;
+    const bool use_halo = halo && halo->peer && halo->nneigh > 0 && ctx->nranks > 1;
+    if (use_halo) MP_TRY(mp::halo_classify(ctx, halo, A->nrow, A->d_sell_sliceptr, A->d_sell_col));
+    mp_halo *H = use_halo ? halo : nullptr;
+    double *wk = nullptr;
+    MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(5 * n + nc + 8), (void **)&wk));
+    double *r = wk, *w = wk + n, *p = wk + 2 * n, *s = wk + 3 * n, *q = wk + 4 * n, *u = wk + 5 * n;   // u carries ghost entries
+    const int g1 = grid_for(ctx, n);
+    const int every = info->check_every > 0 ? info->check_every : 20;
+    int total = 0;
+    for (int restart = 0; restart <= kMaxRestart + 1; ++restart) {
+        // true residual r = b - A x, u = D^-1 r, gamma = r.u
+        MP_TRY((launch_sell<0, false>(ctx, A, H, d_x, q, nullptr, 0, 0)));
+        k_cgcg_init<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, u, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_G0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        bool done = false, zero_rhs = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done, &zero_rhs));
+        if (zero_rhs) return zero_solution(ctx, d_x, n, info);
+        if (done || total >= info->maxit || restart > kMaxRestart) break;
+        // w = A u, delta = w.u
+        MP_TRY((launch_sell<1, true>(ctx, A, H, u, w, u, S_DELTA, 0)));
+        int cur = 0, nxt = 1;
+        for (int it = 0; total < info->maxit; ++it) {
+            k_cgcg_update<<<g1, kThreads, 0, ctx->stream>>>(n, it == 0 ? 1 : 0, w, d_dinv, u, p, s, d_x, r, ctx->d_partials, ctx->d_ctl,
+                                                             ctx->d_scalars, cur, nxt);
+            mp::count_launch(ctx);
+            MP_TRY((launch_sell<3, true>(ctx, A, H, u, w, u, S_DELTA, S_G0 + nxt)));
+            int tmp = cur; cur = nxt; nxt = tmp;
+            ++total;
+            if (total % every == 0 || total == info->maxit) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_pcg: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
+            }
+        }
+    }
+    return finish_solve(ctx, info);
+}
+}  // namespace
+
 extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
                             mp_solve_info *info) {
     MP_CHECK(ctx && d_dinv && d_b && d_x && info, "mp_solve_pcg: null argument");
     MP_TRY(check_csr(A));
+    {
+        const bool sell = A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0 && A->nrow > 0;
+        const bool multi = ctx->nranks > 1 && halo && halo->nneigh > 0;
+        const bool comm_ok = !multi || (ctx->peer && halo->peer && halo->nown == A->nrow);
+        const int variant = ctx->pcg_variant < 0 ? (multi ? 1 : 0) : ctx->pcg_variant;    // default: single reduction on several GPUs
+        if (variant == 1 && sell && comm_ok && (ctx->nranks == 1 || ctx->peer)) return solve_pcg_single_reduction(ctx, A, d_dinv, d_b, d_x, halo, info);
+    }
     const int64_t n = A->nrow, nc = A->ncol;
     int64_t nnz = 0;
     MP_TRY(nnz_of(ctx, A, &nnz));
@@ -989,15 +1252,16 @@ extern "C" int mp_solve_pcg(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, 
     int total = 0;
     // outer loop = residual replacement: after the recurrence says "converged" the TRUE residual b - A x is
     // evaluated and the iteration restarted from x if it is not below the tolerance yet.
-    for (int restart = 0; restart <= kMaxRestart; ++restart) {
+    for (int restart = 0; restart <= kMaxRestart + 1; ++restart) {   // the last pass only re-evaluates the TRUE residual
         MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, q, nullptr, 0, 0)));
         k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, p, nullptr, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_RZ0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
         MP_TRY(reduce_slots(ctx, S_RZ0, 1));
-        bool done = false;
-        MP_TRY(start_solve(ctx, info, restart == 0, &done));
-        if (done || total >= info->maxit) break;
+        bool done = false, zero_rhs = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done, &zero_rhs));
+        if (zero_rhs) return zero_solution(ctx, d_x, n, info);
+        if (done || total >= info->maxit || restart > kMaxRestart) break;
         int cur = S_RZ0, nxt = S_RZ1;
         for (; total < info->maxit;) {
             MP_TRY((spmv_halo<1, true>(ctx, A, halo, lanes, p, q, p, S_PQ, 0)));
@@ -1033,15 +1297,16 @@ extern "C" int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_d
     const int g1 = grid_for(ctx, n);
     const int every = info->check_every > 0 ? info->check_every : 10;   // rank-independent (collective control flow)
     int total = 0;
-    for (int restart = 0; restart <= kMaxRestart; ++restart) {   // residual replacement, see mp_solve_pcg
+    for (int restart = 0; restart <= kMaxRestart + 1; ++restart) {   // the last pass only re-evaluates the TRUE residual   // residual replacement, see mp_solve_pcg
         MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, v, nullptr, 0, 0)));
         k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, v, d_dinv, r, nullptr, rhat, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_RHO0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
         MP_TRY(reduce_slots(ctx, S_RHO0, 1));
-        bool done = false;
-        MP_TRY(start_solve(ctx, info, restart == 0, &done));
-        if (done || total >= info->maxit) break;
+        bool done = false, zero_rhs = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done, &zero_rhs));
+        if (zero_rhs) return zero_solution(ctx, d_x, n, info);
+        if (done || total >= info->maxit || restart > kMaxRestart) break;
         int cur = S_RHO0, nxt = S_RHO1;
         for (int it = 0; total < info->maxit; ++it) {
             k_bicg_p<<<g1, kThreads, 0, ctx->stream>>>(n, it == 0 ? 1 : 0, r, v, d_dinv, p, y, ctx->d_scalars, cur);
@@ -1114,14 +1379,15 @@ extern "C" int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double
     };
     const int every = info->check_every > 0 ? info->check_every : 10;
     int total = 0;
-    for (int restart = 0; restart <= kMaxRestart; ++restart) {
+    for (int restart = 0; restart <= kMaxRestart + 1; ++restart) {   // the last pass only re-evaluates the TRUE residual
         MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, q, nullptr, 0, 0)));
         k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_dinv, r, nullptr, nullptr, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_TMP0);
         mp::count_launch(ctx);
         MP_CUDA(cudaGetLastError());
-        bool done = false;
-        MP_TRY(start_solve(ctx, info, restart == 0, &done));
-        if (done || total >= info->maxit) break;
+        bool done = false, zero_rhs = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done, &zero_rhs));
+        if (zero_rhs) return zero_solution(ctx, d_x, n, info);
+        if (done || total >= info->maxit || restart > kMaxRestart) break;
         int cur = S_RZ0, nxt = S_RZ1;
         MP_TRY(precond());
         k_cgp_rz<<<g1, kThreads, 0, ctx->stream>>>(n, r, z, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, cur);

@@ -21,7 +21,11 @@ enum {
     S_TS = 7, S_TT = 8,                 // BiCGStab t.s, t.t
     S_TMP0 = 9,
     S_NCOL = 10,                        // GMRES: Givens columns completed in the current cycle
-    S_COUNT = 16
+    S_DELTA = 11,                       // single-reduction CG: w.u
+    S_G0 = 12, S_G1 = 13,               // single-reduction CG: gamma = r.u, ping-pong (current / previous)
+    S_AL0 = 14, S_AL1 = 15,             // single-reduction CG: alpha, ping-pong
+    S_COUNT = 16,
+    S_GLOC = 40, S_RRLOC = 41           // single-reduction CG: rank-local r.u and r.r of the vector kernel, folded into the SpMV's exchange
 };
 constexpr int S_RZ0 = S_A0, S_RZ1 = S_A1, S_RHO0 = S_A0, S_RHO1 = S_A1, S_RV = S_PQ;
 
@@ -67,7 +71,8 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
 //    the allreduce idempotent when the producing kernel has become a no-op after convergence.
 template <int NR>
 __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restrict__ partials, mp::ReduceCtl *ctl,
-                                            double *__restrict__ scal, const int (&slots)[NR], bool bump_iter, bool use_off = true) {
+                                            double *__restrict__ scal, const int (&slots)[NR], bool bump_iter, bool use_off = true,
+                                            bool exchange = true) {
     static_assert(NR <= mp::kMboxVals, "mailbox too small");
     __shared__ double sm[NR][kThreads / 32];
     __shared__ double res[NR];
@@ -98,7 +103,8 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restric
     __syncthreads();
     if (!last) return;
     __threadfence();
-    mp::CommDev *comm = ctl->comm;
+    mp::CommDev *comm = exchange ? ctl->comm : nullptr;      // exchange == false: keep the rank-local sums (folded into a later exchange)
+    if (!exchange) use_off = false;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         double v = 0.0;

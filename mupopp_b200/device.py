@@ -190,6 +190,12 @@ class Plan:
             self._csr = (rowptr, colidx[: self.nnz])
         return self._csr
 
+    def sellu_info(self):
+        """(number of (slice, column-position) pairs that need explicit columns, or -1; meta pointer; explicit-column pointer)."""
+        nx, me, xc = C.c_int64(), C.c_void_p(), C.c_void_p()
+        check(self.ctx.lib.mp_plan_sellu_info(self.h, C.byref(nx), C.byref(me), C.byref(xc)), "mp_plan_sellu_info")
+        return nx.value, me.value, xc.value
+
     def sell_info(self):
         ns, ne, sp, sc = C.c_int64(), C.c_int64(), C.c_void_p(), C.c_void_p()
         check(self.ctx.lib.mp_plan_sell_info(self.h, C.byref(ns), C.byref(ne), C.byref(sp), C.byref(sc)), "mp_plan_sell_info")
@@ -218,13 +224,16 @@ class CsrMatrix:
         self.nnz = int(vals.numel())
         self.plan = plan
         self.sell_vals, self.sell_dirty = None, True
-        sp = sc = sv = None
+        sp = sc = sv = me = xc = None
+        self.sell_entries, self.sell_explicit = 0, -1
         if plan is not None and plan.lc > 0:
             _, nent, sp, sc = plan.sell_info()
             self.sell_vals = ctx.zeros(max(nent, 1))
             sv = self.sell_vals.data_ptr()
+            self.sell_entries = int(nent)
+            self.sell_explicit, me, xc = plan.sellu_info()
         self.c = MpCsr(self.nrow, self.ncol, self.nnz, int(max_row_nnz), 0, rowptr.data_ptr(), colidx.data_ptr(), vals.data_ptr(),
-                       sp, sc, sv)
+                       sp, sc, sv, me, xc)
         self.dinv = None
 
     def sync_sell(self):

@@ -53,6 +53,6 @@ def test_struct_sizes_match_header():
     from mupopp_b200 import _lib
     assert C.sizeof(_lib.MpMesh) == 56
     assert C.sizeof(_lib.MpTransportParams) == 8 * 15 + 16
-    assert C.sizeof(_lib.MpCsr) == 80
+    assert C.sizeof(_lib.MpCsr) == 96
     assert C.sizeof(_lib.MpSolveInfo) == 40
     assert C.sizeof(_lib.MpFunctional) == 184
