@@ -226,6 +226,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device; mupopp_b200 has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local)
     ctx = Context(local)
+    if args.pcg_variant >= 0:
+        ctx.set_option("pcg_variant", args.pcg_variant)
     if nranks > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
         ids = [ctx.unique_id() if rank == 0 else None]
@@ -365,7 +367,16 @@ def run_b200(args):
     if rank == 0:
         peak, peak_src = measured_peak()
         N, nnz = s.L.nrow, s.L.nnz
-        spmv_bytes = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N        # vals+cols, rowptr, x read once + y write
+        # ALGORITHMIC bytes of one SpMV launch.  SURVEY.md 8(d) writes them for CSR with int32 columns: 12 nnz + 4 (N+1) + 16 N.  The
+        # production kernel streams the SELL-32 mirror with slice-uniform column offsets: 8 bytes per stored value,
+        # ONE int32 per (slice, column position) and explicit int32 columns only where the 32 rows of a slice disagree -- so its own
+        # compulsory traffic is smaller; `achieved` / `frac` use the bytes the kernel must actually stream, the survey figure is kept beside.
+        survey_bytes = 12.0 * nnz + 4.0 * (N + 1) + 16.0 * N
+        E, X = s.L.sell_entries, s.L.sell_explicit
+        compressed = X >= 0
+        nslice = (N + 31) // 32
+        spmv_bytes = (8.0 * E + 4.0 * (E / 32) + 128.0 * X + 4.0 * (nslice + 1) + 16.0 * N) if compressed else \
+                     (12.0 * E + 4.0 * (nslice + 1) + 16.0 * N)
         avg_ms = spmv_ms / max(n_spmv, 1)
         achieved = spmv_bytes / (avg_ms * 1e-3) / 1e9 if n_spmv else None
         traffic, traffic_src = ncu_traffic(args, nranks)
@@ -385,7 +396,14 @@ def run_b200(args):
                             "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                             "frac": (achieved / peak) if achieved else None,
                             "traffic": traffic, "traffic_source": traffic_src,
-                            "algorithmic_bytes_per_launch": spmv_bytes, "launches_timed": n_spmv, "avg_launch_ms": avg_ms,
+                            "algorithmic_bytes_per_launch": spmv_bytes,
+                            "bytes_model": ("SELL-32 with slice-uniform column offsets: 8 B/value + 4 B per (slice, position) + 128 B per explicit "
+                                            "(slice, position) [%d of %d] + slice pointers + x read once + y written once" % (X, E // 32))
+                                           if compressed else "SELL-32 with int32 columns: 12 B per stored entry + slice pointers + 16 N",
+                            "survey_formula_bytes_per_launch": survey_bytes,
+                            "achieved_by_survey_formula": (survey_bytes / (avg_ms * 1e-3) / 1e9) if n_spmv else None,
+                            "frac_by_survey_formula": (survey_bytes / (avg_ms * 1e-3) / 1e9 / peak) if n_spmv else None,
+                            "launches_timed": n_spmv, "avg_launch_ms": avg_ms,
                             "timed_in": "separate pass of %d steps from the same saved state (%.1f ms/step with per-launch events)"
                                         % (nroof, ms_roof / nroof),
                             "share_of_step": spmv_ms / ms_roof}}
@@ -502,10 +520,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="ccs200", choices=["ccs200", "darcy128", "compaction", "stokes"],
+                    help="ccs200 = the contract line (BASELINE configs[2]); the others are the secondary lines of bench_workloads.py")
     ap.add_argument("--size", dest="n", type=int, default=200, help="hexes per direction (200 -> 8 120 601 dofs/field, the metric's size)")
     ap.add_argument("--ref-n", type=int, default=28, help="sample size of the CPU oracle leg")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer-memory windows over NVLink (in-kernel allreduce, halo push fused into SpMV) or plain NCCL")
+    ap.add_argument("--pcg-variant", type=int, default=-1, help="-1 auto (single-reduction CG on N > 1 GPUs, classic on one), 0 classic, 1 single-reduction")
     ap.add_argument("--p-guess", default="previous", choices=["extrapolate", "previous"],
                     help="initial iterate of the pressure PCG: p^n (default) or 2 p^n - p^(n-1) (measured: no fewer iterations, "
                          "profiles/r2_pressure_guess.md -- the tolerance is relative to ||b||, and the front moves non-smoothly)")
@@ -528,6 +549,12 @@ def main():
         signal.alarm(args.hard_timeout)
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload != "ccs200":
+        import torch
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; mupopp_b200 has no CPU path")
+        import bench_workloads
+        return bench_workloads.RUNNERS[args.workload](args, sys.modules[__name__])
     return run_b200(args)
 
 

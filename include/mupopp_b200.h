@@ -210,6 +210,12 @@ typedef struct {
 int mp_integrate(mp_ctx *ctx, int32_t dim, const mp_functional *f, int64_t nent, const int32_t *d_ent_cell, const int32_t *d_ent_tab,
                  const double *d_ent_weight, const double *d_ent_g, const double *g_const, double *result);
 
+/* max over cells of the cell average of |u| (core.u_max, modules/core.py:23-39; compute_dt = cfl*h_min/max(1e-6, u_max), :43-48).
+ * vec_kind 1: Lagrange components d_u0..d_u2 with the cell dofmap d_vdofs[ncell][nbv] and the basis table d_vtab[nq][nbv] at the points of
+ * a rule with weights d_w (sum 1); vec_kind 2: d_u0 = [ncell][dim] cellwise constant velocity (mode F).  Max over ranks. */
+int mp_max_cell_speed(mp_ctx *ctx, int32_t dim, int64_t ncell, int32_t vec_kind, const double *d_u0, const double *d_u1, const double *d_u2,
+                      const int32_t *d_vdofs, int32_t nbv, const double *d_vtab, int32_t nq, const double *d_w, double *result);
+
 /* ------------------------------------------------------------------ linear algebra (PETSc Mat/Vec/KSP replacement)
  * Call sites replaced: KrylovSolver(...).solve modules/mupopp.py:289-303,410-425; the LU inside solve(a==L,..). */
 typedef struct {
@@ -265,6 +271,46 @@ int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const 
  * device.  The robust choice for the SUPG transport rows (non-normal at large CFL).  restart_m <= 0 -> 50. */
 int mp_solve_gmres(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,
                    int restart_m, mp_solve_info *info);
+
+/* ------------------------------------------------------------------ block operators and MINRES (saddle-point systems)
+ * Replaces KrylovSolver("minres", "amg") on assemble_system(a, L, bcs) / assemble_system(b, L, bcs) of compaction.momentum_solver
+ * (modules/mupopp.py:383-429), the MUMPS solve of the Stokes block (run/stokes_ADR_3D/master_advective_stokes.py:213) and the mixed Darcy
+ * saddle system (modules/mupopp.py:804-807).  The operator is a sum of CSR blocks on a flat vector [block 0 | block 1 | ...]:
+ *     y[rb] += scale * A x[cb]          and, with d_mask (1 free / 0 Dirichlet dof), y = M A M x + (I - M) x  (symmetric elimination). */
+typedef struct {
+    int32_t rb, cb;          /* row block, column block */
+    const mp_csr *A;         /* nrow = size of block rb, ncol = size of block cb (CSR arrays are used; a SELL mirror is ignored) */
+    double scale;
+} mp_block_term;
+typedef struct {
+    int32_t nblk, nterm;     /* 1..8 blocks */
+    int64_t off[9];          /* block offsets in the flat vector, off[nblk] = n */
+    const mp_block_term *terms;
+    const double *d_mask;    /* [n] or NULL */
+} mp_block_op;
+/* block-diagonal SPD preconditioner: per block z = p_k(D^-1 P) D^-1 v, the Chebyshev polynomial of degree k on [lmin, lmax]
+ * (P == NULL or degree <= 1: Jacobi).  d_dinv[n] = inverse diagonal of the preconditioner blocks (1 on Dirichlet dofs). */
+typedef struct {
+    const mp_csr *P[8];
+    int32_t degree[8];
+    double lmin[8], lmax[8];
+    const double *d_dinv;
+} mp_block_prec;
+int mp_block_apply(mp_ctx *ctx, const mp_block_op *op, const double *d_x, double *d_y);
+/* preconditioned MINRES, all recurrence scalars on the device (no per-iteration host synchronisation); stops when the
+ * preconditioned residual norm is <= max(rtol * ||b||_{P^-1}, atol), then re-evaluates the TRUE residual and restarts if it drifted.
+ * d_x: initial guess in (Dirichlet dofs must already hold their values), solution out. */
+int mp_solve_minres(mp_ctx *ctx, const mp_block_op *op, const mp_block_prec *prec, const double *d_b, double *d_x, mp_solve_info *info);
+/* Mixed Darcy saddle system of DarcyAdvection.darcy_bilinear (modules/mupopp.py:595-625) and of the Darcy rows of the multi-component
+ * forms (:804-807, :1201-1204) for a constant K, symmetrised by scaling the continuity row with -K:
+ *     [ M_a      -K B_a^T ] [u_a]   [f_a]          M_a = phi * P2 mass (per velocity component), B_a = (q, d_a u)
+ *     [ -K B_a      0     ] [ p ] = [ 0 ]
+ * solved by mp_solve_minres with the block preconditioner diag(Chebyshev(M), Chebyshev(Sp)), Sp = the P1 operator (K^2/phi) grad.grad
+ * that is spectrally equivalent to the pressure Schur complement B M^-1 K^2 B^T.
+ * d_x = [u_0 .. u_{dim-1} | p]; d_mask / d_dinv as in mp_block_op / mp_block_prec (length dim*n2 + n1). */
+int mp_schur_darcy_solve(mp_ctx *ctx, int32_t dim, const mp_csr *M, const mp_csr *const *BT, const mp_csr *const *B, const mp_csr *Sp,
+                         double K, const double *d_mask, const double *d_dinv, int32_t deg_u, double lmin_u, double lmax_u, int32_t deg_p,
+                         double lmin_p, double lmax_p, const double *d_b, double *d_x, mp_solve_info *info);
 
 /* ------------------------------------------------------------------ multi-GPU (replaces PETSc VecScatter / MPI_Allreduce)
  * One process per GPU.  The NCCL unique id is created on rank 0 and broadcast by the host (torch.distributed). */

@@ -56,6 +56,19 @@ class MpCsr(C.Structure):
                 ("d_sell_meta", C.c_void_p), ("d_sell_xcol", C.c_void_p)]
 
 
+class MpBlockTerm(C.Structure):
+    _fields_ = [("rb", C.c_int32), ("cb", C.c_int32), ("A", C.POINTER(MpCsr)), ("scale", C.c_double)]
+
+
+class MpBlockOp(C.Structure):
+    _fields_ = [("nblk", C.c_int32), ("nterm", C.c_int32), ("off", C.c_int64 * 9), ("terms", C.POINTER(MpBlockTerm)), ("d_mask", C.c_void_p)]
+
+
+class MpBlockPrec(C.Structure):
+    _fields_ = [("P", C.POINTER(MpCsr) * 8), ("degree", C.c_int32 * 8), ("lmin", C.c_double * 8), ("lmax", C.c_double * 8),
+                ("d_dinv", C.c_void_p)]
+
+
 class MpSolveInfo(C.Structure):
     _fields_ = [("rtol", C.c_double), ("atol", C.c_double), ("maxit", C.c_int32), ("check_every", C.c_int32),
                 ("niter", C.c_int32), ("converged", C.c_int32), ("relres", C.c_double)]
@@ -106,6 +119,8 @@ SIGNATURES = {
                                            _VP, _VP, _VP, _VP]),
     "mp_integrate": (C.c_int, [_VP, C.c_int32, C.POINTER(MpFunctional), C.c_int64, _VP, _VP, _VP, _VP, C.POINTER(C.c_double),
                                C.POINTER(C.c_double)]),
+    "mp_max_cell_speed": (C.c_int, [_VP, C.c_int32, C.c_int64, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP,
+                                    C.POINTER(C.c_double)]),
     "mp_spmv": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP]),
     "mp_dot": (C.c_int, [_VP, C.c_int64, _VP, _VP, C.POINTER(C.c_double)]),
     "mp_axpby": (C.c_int, [_VP, C.c_int64, C.c_double, _VP, C.c_double, _VP]),
@@ -116,6 +131,11 @@ SIGNATURES = {
     "mp_solve_pcg_chebyshev": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.POINTER(MpSolveInfo)]),
     "mp_solve_bicgstab": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_solve_gmres": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.c_int, C.POINTER(MpSolveInfo)]),
+    "mp_block_apply": (C.c_int, [_VP, C.POINTER(MpBlockOp), _VP, _VP]),
+    "mp_solve_minres": (C.c_int, [_VP, C.POINTER(MpBlockOp), C.POINTER(MpBlockPrec), _VP, _VP, C.POINTER(MpSolveInfo)]),
+    "mp_schur_darcy_solve": (C.c_int, [_VP, C.c_int32, C.POINTER(MpCsr), C.POINTER(C.POINTER(MpCsr)), C.POINTER(C.POINTER(MpCsr)),
+                                       C.POINTER(MpCsr), C.c_double, _VP, _VP, C.c_int32, C.c_double, C.c_double, C.c_int32, C.c_double,
+                                       C.c_double, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_nccl_unique_id": (C.c_int, [_VP]),
     "mp_comm_init": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "mp_comm_destroy": (C.c_int, [_VP]),

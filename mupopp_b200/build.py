@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmupopp_b200.so")
-SOURCES = ["ctx.cu", "plan.cu", "assemble.cu", "krylov.cu", "functional.cu"]
+SOURCES = ["ctx.cu", "plan.cu", "assemble.cu", "krylov.cu", "functional.cu", "minres.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

@@ -161,10 +161,39 @@ class CompactionMomentumR:
             ctx.axpby(-1.0, self.xm.u[a], 1.0, y.u[a])                        # + (1 - mask) x
 
     # ---- MINRES -------------------------------------------------------------------
-    def solve(self, x: BlockVector, rtol=1e-6, maxit=3000):
-        """Preconditioned MINRES (M = diag of the reference's preconditioner form).  x: initial guess in, solution out.
-        Returns the iteration count (compaction.momentum_solver returns niter too, mupopp.py:424-429)."""
-        from .minres import minres
+    def _block_system(self):
+        """The momentum system as an mp_block_op: blocks [u_0 .. u_{d-1}, p, c] (the same terms `_apply_raw` sequences by hand)."""
+        from .blocksolve import BlockSystem
+        ctx, d = self.ctx, self.d
+        if getattr(self, "_bs", None) is None:
+            terms = []
+            for a in range(d):
+                for b in range(d):
+                    terms.append((a, b, self.Auu[a][b], 1.0))
+                terms.append((a, d, self.BdivT[a], -1.0))           # -(p + c) div v
+                terms.append((a, d + 1, self.BdivT[a], -1.0))
+                terms.append((d, a, self.Bdiv[a], -1.0))            # -q div u, -omega div u
+                terms.append((d + 1, a, self.Bdiv[a], -1.0))
+            terms.append((d, d, self.App, 1.0))
+            terms.append((d + 1, d + 1, self.Acc, 1.0))
+            self._maskflat = ctx.zeros(d * self.n2 + 2 * self.n1)
+            self._maskflat.fill_(1.0)
+            for a in range(d):
+                self._maskflat[a * self.n2:(a + 1) * self.n2].copy_(self.mask[a])
+            self._bs = BlockSystem(ctx, [self.n2] * d + [self.n1, self.n1], terms, mask=self._maskflat)
+        return self._bs
+
+    def solve(self, x: BlockVector, rtol=1e-6, maxit=3000, cheb=(8, 4, 4), ratio=30.0, precond="mass"):
+        """Device-resident preconditioned MINRES (mp_solve_minres), block-diagonal preconditioner applied with Chebyshev-Jacobi
+        polynomials of degrees `cheb` = (velocity, pressure, compaction); (1, 1, 1) is plain Jacobi.
+          precond="form_b": the reference's own preconditioner form `b` (mupopp.py:379-380): (1-phi) grad u:grad v, dL/phi grad p.grad q + p q,
+                            0.5 eta c omega.  Its pressure block is a LAPLACIAN, while the pressure Schur complement of this system is
+                            mass-like (the Darcy term dL*phi*phi^(1/phi^3) of mupopp.py:365 underflows to 0 for phi < 1): iteration counts
+                            grow like 1/h whatever solves the blocks (the reference gives the form to hypre AMG).
+          precond="mass"  (default): velocity block as in `b`; pressure and compaction blocks = the operator's own diagonal blocks plus the
+                            viscosity-scaled pressure mass matrix 2 M (the Stokes Schur-complement approximation B A^-1 B^T ~ M / mu,
+                            mu = (1-phi)/2): mesh-independent on the multiplier blocks.  Same linear system, same solution.
+        x: initial guess in, solution out.  Returns the iteration count (mupopp.py:424-429)."""
         ctx, d = self.ctx, self.d
         n2, n1 = self.n2, self.n1
         # right-hand side with Dirichlet lifting: b <- mask (b - A g), b[D] = g
@@ -178,15 +207,24 @@ class CompactionMomentumR:
             ctx.vmul(1.0, self.mask[a], b.u[a], b.u[a])
             ctx.axpby(1.0, self.g[a], 1.0, b.u[a])
             self.Auu[a][a].apply_dirichlet(x.u[a], self.isbc[a], self.g[a], matrix=False)     # x[D] = g
-        xv, yv = BlockVector(ctx, d, n2, n1, buf=None), BlockVector(ctx, d, n2, n1, buf=None)
-
-        def op(xb, yb):
-            xv.rebind(xb)
-            yv.rebind(yb)
-            self.apply(xv, yv)
-
-        it, self.last_relres = minres(ctx, op, self.dinv.buf, b.buf, x.buf, rtol=rtol, maxit=maxit)
-        return it
+        bs = self._block_system()
+        if precond == "mass":
+            if getattr(self, "Spp", None) is None:
+                self.Spp, self.Scc = self.p11.new_matrix(sell=False), self.p11.new_matrix(sell=False)
+                self.dinv_mass = BlockVector(ctx, d, n2, n1)
+            self.Spp.vals.copy_(self.App.vals)
+            ctx.axpby(2.0, self.M1.vals, 1.0, self.Spp.vals)             # App + M / mu
+            self.Scc.vals.copy_(self.M1.vals)
+            ctx.axpby(-1.0, self.Acc.vals, 2.0, self.Scc.vals)            # eta M + M / mu   (Acc = -eta M)
+            self.dinv_mass.buf.copy_(self.dinv.buf)
+            self.dinv_mass.p.copy_(self.Spp.jacobi_setup())
+            self.dinv_mass.c.copy_(self.Scc.jacobi_setup())
+            bs.set_preconditioner(self.dinv_mass.buf, [(self.Puu, cheb[0], ratio)] * d + [(self.Spp, cheb[1], 10.0), (self.Scc, cheb[2], 10.0)])
+        else:
+            bs.set_preconditioner(self.dinv.buf, [(self.Puu, cheb[0], ratio)] * d + [(self.Ppp, cheb[1], ratio), (self.Pcc, cheb[2], ratio)])
+        res = bs.minres(b.buf, x.buf, rtol=rtol, maxit=maxit)
+        self.last_relres, self.last_result = res.relres, res
+        return res.niter
 
 
 class PorosityR:

@@ -66,7 +66,64 @@ k_integrate(int dim, mp_functional F, int64_t nent, const int32_t *__restrict__ 
     grid_reduce<1>(acc, partials, ctl, scal, sl_, false);
 }
 
+// max over cells of the cell average of |u|: core.u_max (/root/reference/src/modules/core.py:23-39) behind compute_dt (:43-48).
+// vec_kind 1: Lagrange components tabulated at the quadrature points; 2: one constant vector per cell (mode F).  The maximum of
+// non-negative doubles is taken on their bit patterns (order independent, hence deterministic).
+__global__ void __launch_bounds__(kThreads)
+k_max_cell_speed(int dim, int64_t ncell, int vec_kind, const double *__restrict__ u0, const double *__restrict__ u1, const double *__restrict__ u2,
+                 const int32_t *__restrict__ vdofs, int nbv, const double *__restrict__ vtab, int nq, const double *__restrict__ w,
+                 unsigned long long *out) {
+    double best = 0.0;
+    for (int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < ncell; c += gridDim.x * (int64_t)blockDim.x) {
+        double mean = 0.0;
+        if (vec_kind == 2) {
+            double s = 0.0;
+            for (int a = 0; a < dim; ++a) s += u0[c * dim + a] * u0[c * dim + a];
+            mean = sqrt(s);
+        } else {
+            for (int q = 0; q < nq; ++q) {
+                double v[3] = {0.0, 0.0, 0.0};
+                for (int b = 0; b < nbv; ++b) {
+                    const int32_t d = vdofs[c * nbv + b];
+                    const double t = vtab[q * nbv + b];
+                    v[0] += t * u0[d];
+                    v[1] += t * u1[d];
+                    if (dim == 3) v[2] += t * u2[d];
+                }
+                mean += w[q] * sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            }
+        }
+        best = fmax(best, mean);
+    }
+    for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(best));
+}
+
 }  // namespace
+
+extern "C" int mp_max_cell_speed(mp_ctx *ctx, int32_t dim, int64_t ncell, int32_t vec_kind, const double *d_u0, const double *d_u1,
+                                 const double *d_u2, const int32_t *d_vdofs, int32_t nbv, const double *d_vtab, int32_t nq, const double *d_w,
+                                 double *result) {
+    MP_CHECK(ctx && result && d_u0 && (dim == 2 || dim == 3) && ncell >= 0, "mp_max_cell_speed: bad argument");
+    MP_CHECK(vec_kind == 2 || (vec_kind == 1 && d_u1 && (dim == 2 || d_u2) && d_vdofs && d_vtab && d_w && nbv > 0 && nq > 0),
+             "mp_max_cell_speed: bad vector description");
+    unsigned long long *d_out = reinterpret_cast<unsigned long long *>(ctx->d_scalars + 62);     // scratch at the end of the scalar block
+    MP_CUDA(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), ctx->stream));
+    if (ncell > 0) {
+        int64_t g = cdiv(ncell, kThreads);
+        const int64_t cap = (int64_t)ctx->num_sm * 8;
+        if (g > cap) g = cap;
+        k_max_cell_speed<<<(unsigned)g, kThreads, 0, ctx->stream>>>(dim, ncell, vec_kind, d_u0, d_u1, d_u2, d_vdofs, nbv, d_vtab, nq, d_w, d_out);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+    }
+    double h = 0.0;
+    MP_CUDA(cudaMemcpyAsync(&h, d_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    MP_TRY(mp::allreduce_max_host(ctx, &h));
+    *result = h;
+    return 0;
+}
 
 extern "C" int mp_integrate(mp_ctx *ctx, int32_t dim, const mp_functional *f, int64_t nent, const int32_t *d_ent_cell,
                             const int32_t *d_ent_tab, const double *d_ent_weight, const double *d_ent_g, const double *g_const,

@@ -734,6 +734,8 @@ int launch_sell(mp_ctx *ctx, const mp_csr *A, mp_halo *halo, const double *x, do
     if (cap > kMaxBlocks) cap = kMaxBlocks;
     const int g = (int)(nblk < cap ? nblk : cap);
     SellArgs S{A->nrow, A->d_sell_sliceptr, A->d_sell_col, A->d_sell_val, A->d_sell_meta, A->d_sell_xcol};
+    const bool timed = ctx->timing && ctx->tev_used + 2 <= ctx->tev.size();
+    if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
 #define MP_SELL(C8_, LPR_)                                                                                                              \
     do {                                                                                                                                \
         if (halo) k_spmv_sell_peer<DOT, GUARD, C8_, LPR_><<<g, kThreads, 0, ctx->stream>>>(S, x, y, w, ctx->d_partials, ctx->d_ctl,     \
@@ -744,6 +746,10 @@ int launch_sell(mp_ctx *ctx, const mp_csr *A, mp_halo *halo, const double *x, do
     if (c8) { if (lpr == 1) MP_SELL(true, 1); else if (lpr == 2) MP_SELL(true, 2); else MP_SELL(true, 4); }
     else { if (lpr == 1) MP_SELL(false, 1); else if (lpr == 2) MP_SELL(false, 2); else MP_SELL(false, 4); }
 #undef MP_SELL
+    if (timed) {
+        cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
+        ctx->tev_used += 2;
+    }
     mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
     return 0;
@@ -755,17 +761,11 @@ template <int DOT, bool GUARD>
 int launch_spmv(mp_ctx *ctx, const mp_csr *A, int lanes, const double *x, double *y, const double *w, int slot0, int slot1) {
     if (A->nrow == 0) return 0;
     int grid = grid_for(ctx, A->nrow * lanes);
+    const double avg = (double)A->nnz / (double)A->nrow;
+    if (A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0)
+        return launch_sell<DOT, GUARD>(ctx, A, nullptr, x, y, w, slot0, slot1);
     const bool timed = ctx->timing && ctx->tev_used + 2 <= ctx->tev.size();
     if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
-    const double avg = (double)A->nnz / (double)A->nrow;
-    if (A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0) {
-        MP_TRY((launch_sell<DOT, GUARD>(ctx, A, nullptr, x, y, w, slot0, slot1)));
-        if (timed) {
-            cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
-            ctx->tev_used += 2;
-        }
-        return 0;
-    }
     if (ctx->spmv_variant == 3 && A->max_row_nnz > 0 && A->max_row_nnz <= 32 && A->max_row_nnz <= 3.0 * avg + 2.0) {
         // warp-stream kernel: MAXJ = row-length bound rounded up to 8/16/32
         const int maxj = A->max_row_nnz <= 8 ? 8 : (A->max_row_nnz <= 16 ? 16 : 32);
@@ -840,14 +840,7 @@ int spmv_halo(mp_ctx *ctx, const mp_csr *A, mp_halo *halo, int lanes, double *x,
     const bool sell = A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0;
     if (halo && halo->peer && halo->nneigh > 0 && ctx->nranks > 1 && ctx->peer && sell && A->nrow > 0 && halo->nown == A->nrow) {
         MP_TRY(mp::halo_classify(ctx, halo, A->nrow, A->d_sell_sliceptr, A->d_sell_col));
-        const bool timed = ctx->timing && ctx->tev_used + 2 <= ctx->tev.size();
-        if (timed) cudaEventRecord(ctx->tev[ctx->tev_used], ctx->stream);
-        MP_TRY((launch_sell<DOT, GUARD>(ctx, A, halo, x, y, w, slot0, slot1)));
-        if (timed) {
-            cudaEventRecord(ctx->tev[ctx->tev_used + 1], ctx->stream);
-            ctx->tev_used += 2;
-        }
-        return 0;
+        return launch_sell<DOT, GUARD>(ctx, A, halo, x, y, w, slot0, slot1);
     }
     MP_TRY(mp_halo_exchange(ctx, halo, x));
     return launch_spmv<DOT, GUARD>(ctx, A, lanes, x, y, w, slot0, slot1);

@@ -14,7 +14,6 @@ import torch
 
 from ._lib import check, ptr
 from .device import Context, transport_params
-from .minres import minres
 from .moder import AdrSolverR, Spaces
 
 PHI_FOLD = 0.5
@@ -29,8 +28,9 @@ def stokes_adr_params(Pe, Da, dt, SUPG=2, dim=3):
 class StokesSolverR:
     """[L, B^T; B, 0] with Dirichlet velocity data, velocity degree `vdeg` (3 in the reference), pressure P1."""
 
-    def __init__(self, ctx: Context, spaces: Spaces, u_isbc, u_g, vdeg=3):
+    def __init__(self, ctx: Context, spaces: Spaces, u_isbc, u_g, vdeg=3, cheb=(8, 4), ratio=30.0):
         self.ctx, self.sp, self.vdeg = ctx, spaces, vdeg
+        self.cheb, self.ratio = cheb, ratio
         d = spaces.mesh.dim
         self.d = d
         self.nv, self.n1 = spaces.ndof(vdeg), spaces.n1
@@ -38,6 +38,7 @@ class StokesSolverR:
         self.B = [spaces.assemble("grad", 1, vdeg, direction=a) for a in range(d)]
         self.BT = [spaces.assemble("gradT", vdeg, 1, direction=a) for a in range(d)]
         Mp = spaces.assemble("mass", 1, 1)
+        self.Mp = Mp
         self.mask = [ctx.to_device(1.0 - np.asarray(u_isbc[a], dtype=np.float64)) for a in range(d)]
         self.g = [ctx.to_device(np.asarray(u_g[a], dtype=np.float64)) for a in range(d)]
         n = d * self.nv + self.n1
@@ -82,8 +83,24 @@ class StokesSolverR:
             ctx.axpby(1.0, xu[a], 1.0, yu[a])
             ctx.axpby(-1.0, mu[a], 1.0, yu[a])
 
+    def _block_system(self):
+        from .blocksolve import BlockSystem
+        if getattr(self, "_bs", None) is None:
+            d = self.d
+            terms = []
+            for a in range(d):
+                terms += [(a, a, self.L, 1.0), (a, d, self.BT[a], 1.0), (d, a, self.B[a], 1.0)]
+            self._maskflat = self.ctx.zeros(d * self.nv + self.n1)
+            self._maskflat.fill_(1.0)
+            for a in range(d):
+                self._maskflat[a * self.nv:(a + 1) * self.nv].copy_(self.mask[a])
+            self._bs = BlockSystem(self.ctx, [self.nv] * d + [self.n1], terms, mask=self._maskflat)
+            self._bs.set_preconditioner(self.dinv, [(self.L, self.cheb[0], self.ratio)] * d + [(self.Mp, self.cheb[1], self.ratio)])
+        return self._bs
+
     def solve(self, x, rtol=1e-12, maxit=50000):
-        """x = [u_0..u_{d-1}, p] flat device tensor: initial guess in, solution out.  Returns MINRES iterations."""
+        """x = [u_0..u_{d-1}, p] flat device tensor: initial guess in, solution out.  Returns MINRES iterations (device-resident
+        mp_solve_minres; block preconditioner diag(Chebyshev(L), Chebyshev(pressure mass)))."""
         ctx = self.ctx
         n = x.numel()
         gfull, b = ctx.zeros(n), ctx.zeros(n)
@@ -99,8 +116,9 @@ class StokesSolverR:
             ctx.axpby(1.0, self.g[a], 1.0, bu[a])
             ctx.vmul(1.0, self.mask[a], xu[a], xu[a])
             ctx.axpby(1.0, self.g[a], 1.0, xu[a])                # x[D] = g
-        it, self.last_relres = minres(ctx, self.apply, self.dinv, b, x, rtol=rtol, maxit=maxit)
-        return it
+        res = self._block_system().minres(b, x, rtol=rtol, maxit=maxit)
+        self.last_relres, self.last_result = res.relres, res
+        return res.niter
 
 
 class StokesAdrR:

@@ -107,3 +107,16 @@ def boundary_flux(asm, facets, factors, vel, direction=None, coef=1.0):
             un = sum(np.einsum("fb,qb->fq", np.asarray(vel[1][a], dtype=float)[sp.cell_dofs[cellk]], phi) * g[:, a][:, None] for a in range(d))
         total += float(np.einsum("f,q,fq->", meas[m], w, val * un))
     return float(coef) * total
+
+
+def cell_mean_speed_max(asm, vel, qdeg=4):
+    """core.u_max (/root/reference/src/modules/core.py:23-39): max over cells of (1/|cell|) int_cell |u| dx with the degree-`qdeg` rule.
+    vel = ("DG0", (C, d)) | ("P1"|"P2"|"P3", [component dof vectors])."""
+    if vel[0] == "DG0":
+        return float(np.sqrt((np.asarray(vel[1]) ** 2).sum(1)).max())
+    deg = int(vel[0][1])
+    w, phi, _ = asm.tab(deg, qdeg)
+    sp = asm.space(deg)
+    comps = [fem.eval_at_quad(sp, np.asarray(v, dtype=float), phi) for v in vel[1]]
+    speed = np.sqrt(sum(c * c for c in comps))
+    return float((speed @ (w / w.sum())).max())

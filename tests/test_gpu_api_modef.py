@@ -160,6 +160,11 @@ def test_scalar_functionals_and_errornorm(ctx, dim):
     e = fx.errornorm(u3, w3, "L2")
     assert abs(e - ofn.l2_error(asm, h["u3"], h["w3"], 3)) < 1e-12 * e
     assert fx.errornorm(c0, c0, "L2") == 0.0
+    # CFL time step (core.compute_dt, modules/core.py:23-48)
+    from mupopp_b200 import core
+    um = core.u_max(u2)
+    assert abs(um - ofn.cell_mean_speed_max(asm, ("P2", h["u2"]))) < 1e-12 * um
+    assert abs(core.compute_dt(u2, 0.5, mesh.hmin()) - 0.5 * mesh.hmin() / um) < 1e-15
     # known answer: the linear field u = E.r is reproduced exactly by its own interpolant
     E = fx.Expression(("0.05*x[0]", "-0.05*x[1]") if dim == 2 else ("0.05*x[0]", "0.05*x[1]", "-0.1*x[2]"), degree=2)
     ue = fx.Function(V2)

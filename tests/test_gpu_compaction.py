@@ -70,15 +70,27 @@ def test_momentum_blocks_and_solve(ctx, dim):
     x.buf.copy_(ctx.to_device(xr))
     s.apply(x, y)
     assert rel(y.buf.cpu().numpy(), Abc @ xr) < 1e-12
+    yb = ctx.zeros(y.buf.numel())
+    s._block_system().apply(x.buf, yb)                       # the same operator as an mp_block_op (what mp_solve_minres iterates on)
+    assert rel(yb.cpu().numpy(), Abc @ xr) < 1e-12
     # MINRES vs LU.  The reference runs MINRES to rtol 1e-6 (mupopp.py:410-413); run tighter to expose the discretisation parity
     uo, po, co = oc.momentum_solve(asm, prm, phi, gam, buoy, [side] * dim, [g[a][side] for a in range(dim)])
     x.buf.zero_()
-    its = s.solve(x, rtol=1e-11, maxit=20000)
-    assert s.last_relres <= 1e-11, (its, s.last_relres)
+    its = s.solve(x, rtol=1e-12, maxit=20000)
     xo = np.concatenate(list(uo) + [po, co])
-    assert rel(x.buf.cpu().numpy(), xo) < 1e-6
+    res_main = s.last_result
+    x1 = BlockVector(ctx, dim, n2, n1)
+    its_jacobi = s.solve(x1, rtol=1e-12, maxit=20000, cheb=(1, 1, 1), precond="form_b")     # the round-1 preconditioner: diagonal of the form b
+    x2 = BlockVector(ctx, dim, n2, n1)
+    its_formb = s.solve(x2, rtol=1e-12, maxit=20000, precond="form_b")                     # Chebyshev on the blocks of the form b
+    print("compaction MINRES dim %d: mass-Schur blocks + Chebyshev %d iterations (relres %.2e, err %.2e); form b + Chebyshev %d (err %.2e); "
+          "diagonal of form b %d (err %.2e)" % (dim, its, res_main.relres, rel(x.buf.cpu().numpy(), xo), its_formb, rel(x2.buf.cpu().numpy(), xo),
+                                               its_jacobi, rel(x1.buf.cpu().numpy(), xo)))
+    assert res_main.converged
+    assert its < its_jacobi
+    assert rel(x.buf.cpu().numpy(), xo) < 1e-8
     for a in range(dim):
-        assert rel(x.u[a].cpu().numpy(), uo[a]) < 1e-6 or np.linalg.norm(uo[a]) < 1e-12
+        assert rel(x.u[a].cpu().numpy(), uo[a]) < 1e-8 or np.linalg.norm(uo[a]) < 1e-12
 
 
 @pytest.mark.parametrize("dim", [2, 3])

@@ -16,7 +16,7 @@ def rel(a, b):
 @pytest.fixture
 def reset_options(ctx):
     yield
-    for k, v in (("spmv_variant", 0), ("spmv_c8", 1), ("spmv_lpr", 0)):
+    for k, v in (("spmv_variant", 0), ("spmv_c8", 1), ("spmv_lpr", 0), ("pcg_variant", -1)):
         ctx.set_option(k, v)
 
 
@@ -108,3 +108,41 @@ def test_solvers_on_every_sell_variant(ctx, reset_options, c8, lpr):
         assert res.converged, (method, res)
         xo = spla.splu(A.to_scipy().tocsc()).solve(b.cpu().numpy())
         assert rel(x.cpu().numpy(), xo) < 1e-10, method
+
+
+@pytest.mark.parametrize("c8", [0, 1])
+def test_single_reduction_pcg_matches_direct(ctx, reset_options, c8):
+    """The Chronopoulos-Gear single-reduction PCG (the multi-GPU default: one exchange of three sums per iteration, two kernels) solves
+    the same SPD systems as the classic two-reduction PCG, with a similar iteration count."""
+    import scipy.sparse.linalg as spla
+    import mupopp_b200 as mp
+    from mupopp_b200._lib import check, ptr
+    from mupopp_b200.device import DeviceMesh, Plan
+    mesh = mp.BoxMesh((0, 0, 0), (2, 2, 1), 14, 14, 14)
+    dm = DeviceMesh(ctx, mesh)
+    plan = Plan(ctx, dm.cells, dm.cells, dm.nvert, dm.nvert)
+    emat = ctx.empty(dm.ncell * 16)
+    rng = np.random.default_rng(8)
+    K = ctx.to_device(np.exp(2.0 * rng.standard_normal(dm.nvert)))            # a rough coefficient: a few hundred iterations
+    check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(dm.c), ptr(K), 0.0, 1.0, ptr(emat)))
+    A = plan.new_matrix()
+    plan.scatter_matrix(emat, A)
+    isbc = np.zeros(dm.nvert, dtype=np.uint8)
+    isbc[mesh.coords[:, 2] < 1e-12] = 1
+    b = ctx.to_device(rng.standard_normal(dm.nvert))
+    A.apply_dirichlet(b, ctx.to_device(isbc), ctx.to_device(rng.random(dm.nvert)))
+    xo = spla.splu(A.to_scipy().tocsc()).solve(b.cpu().numpy())
+    ctx.set_option("spmv_c8", c8)
+    its = {}
+    for variant in (0, 1):
+        ctx.set_option("pcg_variant", variant)
+        x = ctx.zeros(dm.nvert)
+        res = A.solve("pcg", b, x, rtol=1e-12, maxit=20000)
+        assert res.converged, (variant, res)
+        assert rel(x.cpu().numpy(), xo) < 1e-9, variant
+        its[variant] = res.niter
+    assert its[1] <= 1.3 * its[0] + 10, its
+    # zero right-hand side: x = 0 whatever the initial guess
+    x = ctx.to_device(rng.standard_normal(dm.nvert))
+    res = A.solve("pcg", ctx.zeros(dm.nvert), x, rtol=1e-12)
+    assert res.converged and res.niter == 0 and float(x.abs().max()) == 0.0

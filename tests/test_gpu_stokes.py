@@ -55,10 +55,12 @@ def test_p3_blocks_and_stokes_adr_step(ctx, dim, n):
         s.up.copy_(ctx.to_device(np.concatenate(list(prev.u) + [prev.p])))
         s.c0.copy_(ctx.to_device(prev.c0)); s.c1.copy_(ctx.to_device(prev.c1)); s.c2.copy_(ctx.to_device(prev.c2))
         info = s.step()
-        assert info["c0"].converged and s.stokes.last_relres <= 1e-12
+        assert info["c0"].converged and s.stokes.last_result.converged, s.stokes.last_result
         assert rel(s.c1.cpu().numpy(), mono.c1) < 1e-10 and rel(s.c2.cpu().numpy(), mono.c2) < 1e-9
         assert rel(s.c0.cpu().numpy(), mono.c0) < 1e-9
         uu = np.concatenate([v.cpu().numpy() for v in s.u_views()])
-        assert rel(uu, np.concatenate(mono.u)) < 1e-7
-        assert rel(s.p.cpu().numpy(), mono.p) < 1e-6
+        print("stokes dim %d step %d: %d MINRES iterations, relres %.2e, u err %.2e, p err %.2e"
+              % (dim, k, info["stokes_its"], s.stokes.last_relres, rel(uu, np.concatenate(mono.u)), rel(s.p.cpu().numpy(), mono.p)))
+        assert rel(uu, np.concatenate(mono.u)) < 1e-10            # BASELINE.json: <= 1e-10 per solve (the reference solves with MUMPS)
+        assert rel(s.p.cpu().numpy(), mono.p) < 1e-9
         prev = mono
