@@ -185,6 +185,13 @@ int mp_elem_p1_porosity_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *qu
                              const double *d_vel0, const double *d_vel1, const double *d_vel2, const double *d_phi0, const double *d_gam,
                              double *d_elem_mat, double *d_elem_vec);
 
+/* the same row with a P2 porosity space (X = CG2: benchmark/soliton/soliton.py:120, benchmark/sphere_3D_pure_shear/sphere.py:76): porosity, melting
+ * rate and velocity all use the P2 dofmap d_p2_dofs[ncell][nb2]; elem_mat [ncell][nb2][nb2] (cell-ordered), elem_vec [ncell][nb2].  Includes the
+ * -div(grad(phi_mid)) term of the SUPG residual (mupopp.py:250-251), which vanishes for P1 only.  One warp per cell. */
+int mp_elem_p2_porosity_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, double da, double dt, const int32_t *d_p2_dofs,
+                             const double *d_vel0, const double *d_vel1, const double *d_vel2, const double *d_phi0, const double *d_gam,
+                             double *d_elem_mat, double *d_elem_vec);
+
 /* ------------------------------------------------------------------ scalar functionals (dolfin.assemble(<scalar form>), errornorm)
  * J = sum_e weight[e] * sum_q w[q] * prod_{k<nfield} F_k(x_q) * (V(x_q) . g_e)      e = cells (dx) or boundary facets (ds(id))
  * Call sites replaced: assemble(c00*phi0*dot(u0, n)*ds(1)) run/CCS2D/CCS_3comp.py:277; assemble(c02*dx), assemble(f*Da*c00*c01*dx),

@@ -117,6 +117,8 @@ SIGNATURES = {
                                          _VP, _VP, _VP, _VP]),
     "mp_elem_p1_porosity_quad": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.c_double, C.c_double, _VP, _VP, _VP, _VP,
                                            _VP, _VP, _VP, _VP]),
+    "mp_elem_p2_porosity_quad": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.c_double, C.c_double, _VP, _VP, _VP, _VP,
+                                           _VP, _VP, _VP, _VP]),
     "mp_integrate": (C.c_int, [_VP, C.c_int32, C.POINTER(MpFunctional), C.c_int64, _VP, _VP, _VP, _VP, C.POINTER(C.c_double),
                                C.POINTER(C.c_double)]),
     "mp_max_cell_speed": (C.c_int, [_VP, C.c_int32, C.c_int64, C.c_int32, _VP, _VP, _VP, _VP, C.c_int32, _VP, C.c_int32, _VP,

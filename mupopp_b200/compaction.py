@@ -228,26 +228,34 @@ class CompactionMomentumR:
 
 
 class PorosityR:
-    """compaction.mass_conservation / mass_solver (mupopp.py:217-304) with X = P1: assemble by quadrature, solve with Jacobi-GMRES
-    (the reference runs MINRES on this non-symmetric matrix to rtol 1e-6)."""
+    """compaction.mass_conservation / mass_solver (mupopp.py:217-304) with X = P1 or P2 (`degree`): assemble by quadrature, solve with
+    Jacobi-GMRES (the reference runs MINRES on this non-symmetric matrix to rtol 1e-6).  With X = P2 (soliton,
+    sphere and cavity benchmarks) phi0 and gam are P2 fields and the SUPG residual keeps its -div(grad(phi)) term."""
 
-    def __init__(self, ctx: Context, spaces: Spaces, da, qdeg=QDEG_COMPACTION):
-        self.ctx, self.sp, self.da = ctx, spaces, float(da)
+    def __init__(self, ctx: Context, spaces: Spaces, da, qdeg=QDEG_COMPACTION, degree=1):
+        if degree not in (1, 2):
+            raise NotImplementedError("porosity space of degree %d" % degree)
+        self.ctx, self.sp, self.da, self.degree = ctx, spaces, float(da), degree
         self.quad, self._qt = _quad(ctx, spaces.mesh.dim, qdeg, with_grad=True)
-        self.plan = spaces.plan(1, 1)
+        self.plan = spaces.plan(degree, degree)
         self.A = self.plan.new_matrix(sell=True)
-        l = spaces.nb1
+        l = spaces.nb(degree)
         self.emat = ctx.empty(spaces.dm.ncell * l * l)
         self.evec = ctx.empty(spaces.dm.ncell * l)
-        self.rhs = ctx.zeros(spaces.n1)
+        self.rhs = ctx.zeros(spaces.ndof(degree))
 
-    def solve(self, phi0, u, dt, gam, phi1, rtol=1e-6, maxit=100, method="gmres"):
+    def solve(self, phi0, u, dt, gam, phi1, rtol=1e-6, maxit=100, method="gmres", restart=50):
         ctx = self.ctx
         u2 = u[2] if len(u) > 2 else None
-        check(ctx.lib.mp_elem_p1_porosity_quad(ctx.h, C.byref(self.sp.dm.c), C.byref(self.quad), self.da, float(dt), ptr(self.sp.cd2),
-                                               ptr(u[0]), ptr(u[1]), ptr(u2), ptr(phi0), ptr(gam), ptr(self.emat), ptr(self.evec)),
-              "mp_elem_p1_porosity_quad")
+        if self.degree == 1:
+            check(ctx.lib.mp_elem_p1_porosity_quad(ctx.h, C.byref(self.sp.dm.c), C.byref(self.quad), self.da, float(dt), ptr(self.sp.cd2),
+                                                   ptr(u[0]), ptr(u[1]), ptr(u2), ptr(phi0), ptr(gam), ptr(self.emat), ptr(self.evec)),
+                  "mp_elem_p1_porosity_quad")
+        else:
+            check(ctx.lib.mp_elem_p2_porosity_quad(ctx.h, C.byref(self.sp.dm.c), C.byref(self.quad), self.da, float(dt), ptr(self.sp.cd2),
+                                                   ptr(u[0]), ptr(u[1]), ptr(u2), ptr(phi0), ptr(gam), ptr(self.emat), ptr(self.evec)),
+                  "mp_elem_p2_porosity_quad")
         self.plan.scatter_matrix(self.emat, self.A)
         self.plan.scatter_vector(self.evec, self.rhs)
         phi1.copy_(phi0)
-        return self.A.solve(method, self.rhs, phi1, rtol=rtol, maxit=maxit)
+        return self.A.solve(method, self.rhs, phi1, rtol=rtol, maxit=maxit, restart=restart)

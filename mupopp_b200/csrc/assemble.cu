@@ -942,6 +942,128 @@ __global__ void __launch_bounds__(kThreads) k_p1_porosity_quad(mp_mesh m, QuadVi
     if (evec) store_vec<D>(m, evec, c, b);
 }
 
+// porosity row with a P2 porosity space (X = CG2: benchmark/soliton/soliton.py:120, benchmark/sphere_3D_pure_shear/sphere.py:76), P2 velocity.
+// Same form as above plus the second-derivative term of the SUPG residual, -div(grad(phi_mid)) (mupopp.py:250-251), which does not
+// vanish for P2: the Laplacian of a P2 basis function is constant on an affine cell (vertex i: 4 |grad lam_i|^2, edge (a,b):
+// 8 grad lam_a . grad lam_b).  ONE WARP PER CELL: the element matrix has up to 10 x 10 entries, far too many accumulators for a
+// thread per cell; lane e owns entries e, e+32, ... and the per-point basis values live in the warp's shared-memory strip.
+template <int D>
+__global__ void __launch_bounds__(256) k_p2_porosity_quad(mp_mesh m, QuadView Q, const double *__restrict__ vdphi, double da, double dt,
+                                                          const int32_t *__restrict__ dofs2, const double *__restrict__ v0,
+                                                          const double *__restrict__ v1, const double *__restrict__ v2,
+                                                          const double *__restrict__ phi0, const double *__restrict__ gam,
+                                                          double *__restrict__ emat, double *__restrict__ evec) {
+    constexpr int NB = D == 2 ? 6 : 10;
+    constexpr int NE = NB * NB;
+    constexpr int EPL = (NE + 31) / 32;                 // matrix entries per lane
+    __shared__ double s_psi[8][NB], s_ug[8][NB], s_lap[8][NB];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (c >= m.ncell) return;                            // warp-uniform
+    Geom<D> G;
+    load_geom<D>(m, c, G);
+    double detJ = G.vol;
+#pragma unroll
+    for (int k = 2; k <= D; ++k) detJ *= k;
+    // local coefficients of basis function `lane` (lanes >= NB carry zeros)
+    const bool has = lane < NB;
+    const int32_t dof = has ? dofs2[c * (int64_t)NB + lane] : 0;
+    const double ub[3] = {has ? v0[dof] : 0.0, has ? v1[dof] : 0.0, (has && D == 3) ? v2[dof] : 0.0};
+    const double p0b = has ? phi0[dof] : 0.0, gab = has ? gam[dof] : 0.0;
+    // Laplacian of the P2 basis (constant per cell)
+    if (has) {
+        double l;
+        if (lane <= D) {
+            l = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) l += G.g[lane][a] * G.g[lane][a];
+            l *= 4.0;
+        } else {
+            int ea, eb;
+            const int e = lane - (D + 1);
+            if (D == 2) { ea = e == 0 ? 1 : 0; eb = e == 2 ? 1 : 2; }                     // UFC triangle edges (1,2) (0,2) (0,1)
+            else { const int ta[6] = {2, 1, 1, 0, 0, 0}, tb[6] = {3, 3, 2, 3, 2, 1}; ea = ta[e]; eb = tb[e]; }   // UFC tetrahedron edges
+            l = 0.0;
+#pragma unroll
+            for (int a = 0; a < D; ++a) l += G.g[ea][a] * G.g[eb][a];
+            l *= 8.0;
+        }
+        s_lap[wib][lane] = l;
+    }
+    __syncwarp();
+    double lap0 = has ? s_lap[wib][lane] * p0b : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lap0 += __shfl_xor_sync(0xffffffffu, lap0, o);
+    double A[EPL], bi = 0.0;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) A[k] = 0.0;
+    for (int q = 0; q < Q.nq; ++q) {
+        const double w = Q.w[q] * detJ;
+        double psi = 0.0, gk[D];
+#pragma unroll
+        for (int a = 0; a < D; ++a) gk[a] = 0.0;
+        if (has) {
+            psi = Q.vphi[q * NB + lane];
+#pragma unroll
+            for (int a = 0; a < D; ++a) {
+                double t = 0.0;
+#pragma unroll
+                for (int al = 0; al < D; ++al) t += vdphi[(q * NB + lane) * D + al] * G.g[al + 1][a];
+                gk[a] = t;
+            }
+        }
+        // u, div u, phi0, gam at the point: warp sums over the basis
+        double r[D + 3];
+#pragma unroll
+        for (int a = 0; a < D; ++a) r[a] = psi * ub[a];
+        r[D] = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) r[D] += gk[a] * ub[a];
+        r[D + 1] = psi * p0b;
+        r[D + 2] = psi * gab;
+#pragma unroll
+        for (int k = 0; k < D + 3; ++k)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) r[k] += __shfl_xor_sync(0xffffffffu, r[k], o);
+        const double divu = r[D], ph0 = r[D + 1], gq = r[D + 2];
+        double un2 = 0.0, ug = 0.0;
+#pragma unroll
+        for (int a = 0; a < D; ++a) { un2 += r[a] * r[a]; ug += r[a] * gk[a]; }
+        const double keff = fmax(0.5 * G.h * sqrt(un2) - 1.0, 0.0);
+        const double st = keff > 0.0 ? keff / un2 : 0.0;
+        double ugp0 = ug * p0b;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ugp0 += __shfl_xor_sync(0xffffffffu, ugp0, o);
+        __syncwarp();
+        if (has) { s_psi[wib][lane] = psi; s_ug[wib][lane] = ug; }
+        __syncwarp();
+        if (emat) {
+#pragma unroll
+            for (int k = 0; k < EPL; ++k) {
+                const int e = lane + 32 * k;
+                if (e < NE) {
+                    const int i = e / NB, j = e % NB;
+                    const double pi = s_psi[wib][i], pj = s_psi[wib][j], ui = s_ug[wib][i], uj = s_ug[wib][j];
+                    A[k] += w * (pi * pj * (1.0 + 0.5 * dt * divu) + 0.5 * dt * pi * uj + st * ui * (pj + 0.5 * dt * (uj - s_lap[wib][j])));
+                }
+            }
+        }
+        if (evec && has) {
+            const double gal = ph0 - 0.5 * dt * ugp0 + dt * divu - 0.5 * dt * ph0 * divu + dt * da * gq;
+            const double rk = -ph0 + 0.5 * dt * (ugp0 - lap0) - dt * da * gq;
+            bi += w * (psi * gal - st * ug * rk);
+        }
+    }
+    if (emat) {
+#pragma unroll
+        for (int k = 0; k < EPL; ++k) {
+            const int e = lane + 32 * k;
+            if (e < NE) emat[c * (int64_t)NE + e] = A[k];
+        }
+    }
+    if (evec && has) evec[c * (int64_t)NB + lane] = bi;
+}
+
 // Symmetric Dirichlet elimination, 8 lanes per row, fixed reduction order.
 __global__ void __launch_bounds__(256) k_dirichlet(int64_t nrow, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colidx,
                                                    double *__restrict__ vals, double *__restrict__ rhs,
@@ -1140,5 +1262,23 @@ extern "C" int mp_elem_p1_porosity_quad(mp_ctx *ctx, const mp_mesh *mesh, const 
     QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
     DISPATCH_DIM(mesh, k_p1_porosity_quad, Q, quad->d_vdphi, da, dt, d_vel_dofs, d_vel0, d_vel1, d_vel2 ? d_vel2 : d_vel1, d_phi0, d_gam,
                  d_elem_mat, d_elem_vec);
+    return 0;
+}
+
+extern "C" int mp_elem_p2_porosity_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_quad *quad, double da, double dt, const int32_t *d_p2_dofs,
+                                        const double *d_vel0, const double *d_vel1, const double *d_vel2, const double *d_phi0,
+                                        const double *d_gam, double *d_elem_mat, double *d_elem_vec) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(quad && quad->d_w && quad->d_vphi && quad->d_vdphi && quad->nq > 0, "mp_elem_p2_porosity_quad: quadrature tables (incl. gradients) required");
+    MP_CHECK(quad->nbv == (mesh->dim == 2 ? 6 : 10), "mp_elem_p2_porosity_quad: the tables must be those of the P2 basis");
+    MP_CHECK(d_p2_dofs && d_vel0 && d_vel1 && (mesh->dim == 2 || d_vel2) && d_phi0 && d_gam, "mp_elem_p2_porosity_quad: null argument");
+    MP_CHECK(d_elem_mat || d_elem_vec, "mp_elem_p2_porosity_quad: nothing to compute");
+    QuadView Q{quad->nq, quad->nbv, quad->d_w, quad->d_lam, quad->d_vphi};
+    const unsigned grid = (unsigned)cdiv(mesh->ncell * 32, 256);
+    if (grid == 0) return 0;
+    if (mesh->dim == 2) k_p2_porosity_quad<2><<<grid, 256, 0, ctx->stream>>>(*mesh, Q, quad->d_vdphi, da, dt, d_p2_dofs, d_vel0, d_vel1, d_vel1, d_phi0, d_gam, d_elem_mat, d_elem_vec);
+    else k_p2_porosity_quad<3><<<grid, 256, 0, ctx->stream>>>(*mesh, Q, quad->d_vdphi, da, dt, d_p2_dofs, d_vel0, d_vel1, d_vel2, d_phi0, d_gam, d_elem_mat, d_elem_vec);
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
     return 0;
 }

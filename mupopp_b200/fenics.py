@@ -85,9 +85,12 @@ def BoxMesh(p0, p1, nx, ny, nz):
     return _mesh.BoxMesh(p0, p1, nx, ny, nz)
 
 
-def Mesh(source, cells=None):
+def Mesh(source=None, cells=None):
     """dolfin.Mesh: from a DOLFIN-XML file (optionally .gz; triangles or tetrahedra) as in
-    /root/reference/src/run/fenics_demo/demo_advection-diffusion.py:33, or from (coords, cells) arrays."""
+    /root/reference/src/run/fenics_demo/demo_advection-diffusion.py:33, from (coords, cells) arrays, or empty -- to be filled by
+    `HDF5File(...).read(mesh, "/mesh", False)` (run/stokes_ADR_3D/master_advective_stokes.py:77-80)."""
+    if source is None:
+        return _mesh.Mesh(np.zeros((0, 3)), np.zeros((0, 4), dtype=np.int32))
     if cells is not None:
         return _mesh.Mesh(source, cells)
     import gzip
@@ -172,6 +175,27 @@ class MeshFunction:
         n = n / np.linalg.norm(n, axis=1, keepdims=True)
         n[((x[:, 0] - opp) * n).sum(1) < 0] *= -1.0
         return owner, loc, n, meas
+
+
+class HDF5File:
+    """dolfin.HDF5File(comm, filename, "r") with .read(mesh, "/mesh", use_partition) and .read(mesh_function, "/boundaries")
+    (run/stokes_ADR_3D/master_advective_stokes.py:77-85), on the pure-Python reader of mupopp_b200/hdf5.py (h5py is not in the image)."""
+
+    def __init__(self, comm, filename, mode="r"):
+        if mode != "r":
+            raise NotImplementedError("HDF5File: only reading is supported")
+        self.filename = filename
+
+    def read(self, obj, name, use_partition_from_file=False):
+        from . import hdf5
+        if isinstance(obj, MeshFunction):
+            obj.entries = hdf5.read_facet_markers(self.filename, obj.mesh, name)
+            return
+        coords, cells = hdf5.read_mesh(self.filename, name)
+        obj.reset(coords, cells)
+
+    def close(self):
+        pass
 
 
 def FacetFunction(kind, mesh, value=0):

@@ -14,6 +14,14 @@ TRI_EDGES = np.array([[1, 2], [0, 2], [0, 1]], dtype=np.int64)                  
 TET_EDGES = np.array([[2, 3], [1, 3], [1, 2], [0, 3], [0, 2], [0, 1]], dtype=np.int64)
 
 
+class _Topology:
+    def __init__(self, dim):
+        self._dim = dim
+
+    def dim(self):
+        return self._dim
+
+
 class Mesh:
     """Simplicial mesh: coords (V,d) float64, cells (C,d+1) int32 with ascending vertex ids per cell."""
 
@@ -28,6 +36,20 @@ class Mesh:
     # -- DOLFIN-like accessors -------------------------------------------------
     def coordinates(self):
         return self.coords
+
+    def mpi_comm(self):
+        return None                      # one process per GPU: there is no MPI communicator behind a mesh
+
+    def topology(self):
+        return _Topology(self.dim)
+
+    def reset(self, coords, cells):
+        """Replace the mesh data in place (HDF5File.read(mesh, "/mesh", False) fills an empty Mesh())."""
+        self.coords = np.ascontiguousarray(coords, dtype=np.float64)
+        self.cells = np.ascontiguousarray(cells, dtype=np.int32)
+        self._edges = self._cell_edges = self._bfacets = None
+        self._faces = None
+        self.box = None
 
     def num_vertices(self):
         return self.coords.shape[0]

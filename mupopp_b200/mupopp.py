@@ -219,14 +219,17 @@ def _solve_compaction_mass(form, sol, tol, maxit, monitor=False):
     from . import compaction as _c, moder
     d = form.data
     own = d["owner"]
-    if d["V"].blocks[0][0] != 1:
-        raise NotImplementedError("compaction.mass_solver: only a P1 porosity space is on the B200 path (P2 needs div(grad(phi)))")
+    deg = d["V"].blocks[0][0]
+    if deg not in (1, 2):
+        raise NotImplementedError("compaction.mass_solver: the porosity space must be CG1 or CG2")
+    if d["phi0"].block_degree(0) != deg or d["gam"].block_degree(0) != deg:
+        raise NotImplementedError("compaction.mass_solver: phi0 and gam must live in the porosity space X (as in the reference's scripts)")
     ctx = default_context()
     mesh = d["mesh"]
     sp = _spaces(ctx, mesh)
-    key = ("porosity", id(mesh), float(own.da))
+    key = ("porosity", id(mesh), float(own.da), deg)
     if key not in _CACHE:
-        _CACHE[key] = _c.PorosityR(ctx, sp, own.da)
+        _CACHE[key] = _c.PorosityR(ctx, sp, own.da, degree=deg)
     dt = float(getattr(d["dt"], "dt", d["dt"]))
     res = _CACHE[key].solve(d["phi0"].blocks[0].clone(), d["u"].blocks, dt, d["gam"].blocks[0], sol.blocks[0], rtol=tol, maxit=maxit)
     if monitor:

@@ -120,17 +120,30 @@ def momentum_solve(asm, prm, phi, gam, buoy, u_dofs, u_vals, qdeg=QDEG_COMPACTIO
     return [x[a * n2:(a + 1) * n2] for a in range(d)], x[d * n2:d * n2 + n1], x[d * n2 + n1:]
 
 
-def porosity_system(asm: Assembler, da, dt, phi0, u, gam, qdeg=QDEG_COMPACTION):
-    """mupopp.py:217-259 with a P1 porosity space X and a P2 velocity u (list of component dof arrays):
+def p2_basis_laplacians(asm: Assembler):
+    """Laplacian of every P2 basis function on every (affine) cell, constant per cell: vertex i -> 4 |grad lam_i|^2, edge (a, b) ->
+    8 grad lam_a . grad lam_b (UFC edge order).  Returns (C, nb2)."""
+    _, _, dref1 = asm.tab(1, 1)
+    g = fem.phys_grads(dref1, asm.Jinv)[:, 0]                                   # (C, d+1, d) gradients of the barycentric coordinates
+    d = asm.mesh.dim
+    le = fem.TRI_EDGES if d == 2 else fem.TET_EDGES
+    vert = 4.0 * np.einsum("cia,cia->ci", g, g)
+    edge = np.stack([8.0 * np.einsum("ca,ca->c", g[:, a], g[:, b]) for (a, b) in le], 1)
+    return np.concatenate([vert, edge], 1)
+
+
+def porosity_system(asm: Assembler, da, dt, phi0, u, gam, qdeg=QDEG_COMPACTION, pdeg=1):
+    """mupopp.py:217-259 with a P1 (pdeg=1) or P2 (pdeg=2) porosity space X and a P2 velocity u (list of component dof arrays):
        F = w (phi1 - phi0 + dt (u.grad(phi_mid) - (1 - phi_mid) div u) - dt da gam)
-           + (keff/|u|^2) (u.grad w) (phi1 - phi0 + dt (u.grad(phi_mid) - da gam)),   keff = max(h|u|/2 - 1, 0)
-    (div grad of a P1 field vanishes).  Where keff == 0 the stabilisation is dropped (the reference would evaluate 0/0 for u == 0)."""
-    w, p1, dref1 = asm.tab(1, qdeg)
+           + (keff/|u|^2) (u.grad w) (phi1 - phi0 + dt (u.grad(phi_mid) - div(grad(phi_mid)) - da gam)),   keff = max(h|u|/2 - 1, 0)
+    (div grad of a P1 field vanishes; for P2 it is constant per cell).  Where keff == 0 the stabilisation is dropped (the reference would
+    evaluate 0/0 for u == 0).  phi0 and gam live in X."""
+    w, p1, dref1 = asm.tab(pdeg, qdeg)
     _, p2, dref2 = asm.tab(2, qdeg)
     g1 = fem.phys_grads(dref1, asm.Jinv)
     g2 = fem.phys_grads(dref2, asm.Jinv)
     wd = w[None, :] * asm.detJ[:, None]
-    s1, s2 = asm.P1, asm.P2
+    s1, s2 = asm.space(pdeg), asm.P2
     d = asm.mesh.dim
     uq = np.stack([fem.eval_at_quad(s2, np.asarray(u[a]), p2) for a in range(d)], -1)           # (C,q,d)
     divu = sum(np.einsum("cb,cqb->cq", np.asarray(u[a])[s2.cell_dofs], g2[..., a], optimize=True) for a in range(d))
@@ -140,18 +153,20 @@ def porosity_system(asm: Assembler, da, dt, phi0, u, gam, qdeg=QDEG_COMPACTION):
     keff = np.maximum(aval - 1.0, 0.0)
     with np.errstate(divide="ignore", invalid="ignore"):
         st = np.where(keff > 0.0, keff / un2, 0.0)
-    ug = np.einsum("cqd,cqbd->cqb", uq, g1, optimize=True)                                        # u.grad(lambda_b)
+    ug = np.einsum("cqd,cqbd->cqb", uq, g1, optimize=True)                                        # u.grad(psi_b)
+    lap = p2_basis_laplacians(asm) if pdeg == 2 else np.zeros((asm.mesh.nc, p1.shape[1]))        # (C, nb) Laplacian of psi_b
     ph0 = fem.eval_at_quad(s1, phi0, p1)
     ugp0 = np.einsum("cqb,cb->cq", ug, phi0[s1.cell_dofs], optimize=True)
+    lap0 = np.einsum("cb,cb->c", lap, phi0[s1.cell_dofs])[:, None]
     gaq = fem.eval_at_quad(s1, gam, p1)
     Ae = np.einsum("cq,qi,qj->cij", wd, p1, p1, optimize=True)
     Ae += 0.5 * dt * np.einsum("cq,qi,cqj->cij", wd, p1, ug, optimize=True)
     Ae += 0.5 * dt * np.einsum("cq,cq,qi,qj->cij", wd, divu, p1, p1, optimize=True)
     Ae += np.einsum("cq,cq,cqi,qj->cij", wd, st, ug, p1, optimize=True)
-    Ae += 0.5 * dt * np.einsum("cq,cq,cqi,cqj->cij", wd, st, ug, ug, optimize=True)
+    Ae += 0.5 * dt * np.einsum("cq,cq,cqi,cqj->cij", wd, st, ug, ug - lap[:, None, :], optimize=True)
     A = fem.scatter_matrix(Ae, s1.cell_dofs, s1.cell_dofs, (s1.ndof, s1.ndof))
     gal = ph0 - 0.5 * dt * ugp0 + dt * divu - 0.5 * dt * ph0 * divu + dt * da * gaq
-    rk = -ph0 + 0.5 * dt * ugp0 - dt * da * gaq
+    rk = -ph0 + 0.5 * dt * (ugp0 - lap0) - dt * da * gaq
     be = np.einsum("cq,cq,qi->ci", wd, gal, p1, optimize=True) - np.einsum("cq,cq,cqi,cq->ci", wd, st, ug, rk, optimize=True)
     b = fem.scatter_vector(be, s1.cell_dofs, s1.ndof)
     return A, b

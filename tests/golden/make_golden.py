@@ -46,5 +46,25 @@ def main():
     print("wrote", OUT, os.path.getsize(OUT), "bytes;", n, "dofs")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(os.sys.argv) == 1:
     main()
+
+
+def stokes_sample_mesh():
+    """tests/golden/stokes_sample_mesh.npz from the reference's HDF5 mesh of config 5 (a DATA file):
+    /root/reference/src/run/stokes_ADR_3D/hdf5_sample_mesh.xml.h5 -- /mesh (1582 vertices, 5203 tetrahedra) and /boundaries (facet
+    ids 1 inflow, 2 outflow, 3 walls; run/stokes_ADR_3D/master_advective_stokes.py:77-85,119-130), read with mupopp_b200/hdf5.py."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+    from mupopp_b200 import hdf5
+    from mupopp_b200.mesh import Mesh
+    src = "/root/reference/src/run/stokes_ADR_3D/hdf5_sample_mesh.xml.h5"
+    coords, cells = hdf5.read_mesh(src)
+    markers = hdf5.read_facet_markers(src, Mesh(coords, cells))
+    out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stokes_sample_mesh.npz")
+    np.savez_compressed(out, coords=coords, cells=cells, facet_markers=markers.astype(np.int32))
+    print("wrote", out, os.path.getsize(out), "bytes;", coords.shape[0], "vertices,", cells.shape[0], "cells,", markers.shape[0], "marked facets")
+
+
+if __name__ == "__main__" and len(os.sys.argv) > 1 and os.sys.argv[1] == "stokes":
+    stokes_sample_mesh()

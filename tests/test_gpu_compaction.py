@@ -110,3 +110,30 @@ def test_porosity_row(ctx, dim):
         assert r.converged
         assert abs(s.A.to_scipy() - Ao).max() <= 1e-11 * abs(Ao).max()
         assert rel(ph1.cpu().numpy(), ph1o) < 1e-10
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_porosity_row_p2_space(ctx, dim):
+    """X = CG2 (benchmark/soliton/soliton.py:120, benchmark/sphere_3D_pure_shear/sphere.py:76): P2 porosity / melting rate, with the
+    -div(grad(phi_mid)) term of the SUPG residual (mupopp.py:250-251)."""
+    from mupopp_b200.compaction import PorosityR
+    pm, om, asm, sp, zh, phi, gam, buoy = _setup(ctx, dim)
+    X2 = asm.P2.dof_coords()
+    n2 = asm.P2.ndof
+    rng = np.random.default_rng(3)
+    phi2 = 0.1 + 0.05 * np.exp(-((X2 - X2.mean(0)) ** 2).sum(1)) + 0.01 * rng.random(n2)
+    gam2 = 0.2 * np.sin(X2[:, 0]) * np.cos(X2[:, -1])
+    # scale 60: keff > 0, the SUPG branch (with the Laplacian term) is active.  That matrix is indefinite (negative diagonal entries from
+    # the -div(grad) term at |u| h >> 1), so Jacobi-GMRES needs a long recurrence: restart 200, and dt small enough for it to converge
+    for scale, dt in ((0.05, 0.05), (60.0, 0.005)):
+        u = [scale * (0.3 + 0.2 * np.sin(X2[:, 0] + a) * np.cos(X2[:, -1])) for a in range(dim)]
+        Ao, bo = oc.porosity_system(asm, 1e-2, dt, phi2, u, gam2, pdeg=2)
+        ph1o = spla.splu(Ao.tocsc()).solve(bo)
+        s = PorosityR(ctx, sp, 1e-2, degree=2)
+        ph1 = ctx.zeros(n2)
+        r = s.solve(ctx.to_device(phi2), [ctx.to_device(v) for v in u], dt, ctx.to_device(gam2), ph1, rtol=1e-13, maxit=4000, restart=200)
+        assert abs(s.A.to_scipy() - Ao).max() <= 1e-11 * abs(Ao).max()
+        assert rel(s.rhs.cpu().numpy(), bo) < 1e-12
+        print("P2 porosity dim %d scale %g: %r, err %.2e" % (dim, scale, r, rel(ph1.cpu().numpy(), ph1o)))
+        assert r.converged or r.relres < 1e-11, r
+        assert rel(ph1.cpu().numpy(), ph1o) < 1e-9

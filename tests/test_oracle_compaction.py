@@ -54,3 +54,15 @@ def test_momentum_solve_and_porosity_step():
     # u = 0, Gamma = 0: the porosity is unchanged
     A, b = oc.porosity_system(asm, 1e-4, 0.1, phi, [np.zeros(asm.P2.ndof)] * 3, np.zeros(m.nv))
     assert np.abs(spla.splu(A.tocsc()).solve(b) - phi).max() < 1e-13
+
+
+def test_p2_basis_laplacians_known_answer():
+    """The cellwise Laplacians of the P2 basis reproduce the Laplacian of any quadratic exactly: f = x^2 + 2 y^2 (+ 3 z^2) + x y -> 6 (12)."""
+    from oracle import compaction as oc
+    from oracle import fem, forms
+    for om, want in ((fem.rectangle_mesh(0, 0, 2, 1, 3, 2), 6.0), (fem.box_mesh((0, 0, 0), (2, 1, 1), 2, 2, 2), 12.0)):
+        asm = forms.Assembler(om)
+        X = asm.P2.dof_coords()
+        f = X[:, 0] ** 2 + 2 * X[:, 1] ** 2 + X[:, 0] * X[:, 1] + (3 * X[:, 2] ** 2 if om.dim == 3 else 0.0)
+        lap = np.einsum("cb,cb->c", oc.p2_basis_laplacians(asm), f[asm.P2.cell_dofs])
+        assert np.allclose(lap, want, rtol=1e-12, atol=1e-12)
