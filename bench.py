@@ -497,7 +497,7 @@ class ApiProblem:
     def step(self):
         a, L = self.ccs.advection_diffusion_three_component(self.W, self.mesh, self.sol_0, PHYS["dt"], f_source=self.S, K=PHYS["K"], zh=self.zh,
                                                             gam_rho=PHYS["gam_rho"])
-        return self.fx.solve(a == L, self.sol, self.bc, solver_parameters={"relative_tolerance": self.args.rtol})
+        return self.fx.solve(a == L, self.sol, self.bc, solver_parameters={"relative_tolerance": self.args.rtol, "preconditioner": self.args.p_precond})
 
 
 def ncu_traffic(args, nranks):
@@ -535,7 +535,8 @@ def main():
     ap.add_argument("--c0-method", default="bicgstab", choices=["gmres", "bicgstab"],
                     help="transport-row solver; bicgstab falls back to GMRES if it breaks down (TransportSolverF._solve_c0)")
     ap.add_argument("--gmres-restart", type=int, default=30)
-    ap.add_argument("--p-precond", default="jacobi", choices=["jacobi", "chebyshev"], help="pressure PCG preconditioner")
+    ap.add_argument("--p-precond", default="line", choices=["jacobi", "chebyshev", "line"],
+                    help="pressure PCG preconditioner: point Jacobi, Chebyshev-Jacobi polynomial, or lattice-line block Jacobi (tridiagonal z-lines)")
     ap.add_argument("--cheb-degree", type=int, default=3)
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-api", dest="no_api", action="store_true", help="e2e through TransportSolverF.step instead of the mupopp/fenics plugin call")

@@ -1409,3 +1409,302 @@ extern "C" int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double
     }
     return finish_solve(ctx, info);
 }
+
+// ------------------------------------------------------------------ line (block-tridiagonal) Jacobi preconditioner
+// Rows are numbered plane by plane on structured lattices (BoxMesh: vertex id iz*npl + iy*(nx+1) + ix, mesh.py), so the dofs of the
+// grid line through in-plane position l are the rows l, l+stride, l+2 stride, ...  M = the tridiagonal part of A along those lines
+// (diagonal + the (i, i -+ stride) entries): "block Jacobi" with one block per line.  The reference's boxes are thin in z
+// ([0,4]x[0,4]x[0,1] cut into n^3 hexes, run/CCS/CCS_3D_top_source.py), i.e. the z-coupling of div(k grad p) is 16x the in-plane
+// coupling and point Jacobi leaves exactly that direction unpreconditioned; solving the z-lines exactly removes the 1/hz^2 part of
+// the condition number (2.5-3x fewer PCG iterations for the same tolerance, measured in profiles/).
+// M = L D L^T is factored once (the pressure operator is constant in time): invw = 1/D, and the two sweeps are fused with the CG
+// vector updates so that a line-PCG iteration moves FEWER bytes than a Jacobi-PCG iteration (104 N against 116 N):
+//   forward  (k_line_fwd):  x += alpha p ; r -= alpha q ; rr ; s = D^-1 L^-1 r ; rz = (L^-1 r)^T D^-1 (L^-1 r)
+//   backward (k_line_bwd):  z = L^-T s   ; p = z + beta p          (z is never stored)
+// One thread per line, lanes of a warp on neighbouring lines => every access is a coalesced 256-byte row of a plane; the recurrence
+// along the line is two dependent DFMAs per plane, the loads of two 4-plane batches are kept in flight per thread.
+namespace {
+// One warp per CTA and at most 224 registers: 9 CTAs per SM = 1332 slots, so the 1250 warps of a 200^3 sweep (40 000 lines) run as ONE
+// wave with 8 or 9 warps per SM.  (64-thread CTAs at 255 registers gave 4 per SM = 592 slots for 625 CTAs: a second wave of 33 CTAs
+// doubled the kernel time, ncu launch__waves_per_multiprocessor 1.06, profiles/r2_ncu_line_kernels.md.)
+constexpr int kLineThreads = 32;
+constexpr int kLineCtasPerSm = 9;
+constexpr int kLineU = 4;           // planes per batch
+
+// one thread per 128-byte line asks L2 for a row of a plane that the sweep reaches `pd` planes later: the registers of a thread hold
+// only two batches of loads, too few bytes in flight for HBM with 40 000 threads; the prefetches cost no registers
+__device__ __forceinline__ void prefetch_l2(const double *a) { asm volatile("prefetch.global.L2 [%0];" ::"l"(a)); }
+
+__global__ void __launch_bounds__(kThreads) k_line_extract(int64_t nrow, int64_t stride, const int32_t *__restrict__ rowptr,
+                                                           const int32_t *__restrict__ colidx, const double *__restrict__ vals,
+                                                           double *__restrict__ lo, double *__restrict__ diag) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nrow) return;
+    double l = 0.0, d = 0.0;
+    const int64_t want = i - stride;
+    for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+        const int64_t c = colidx[k];
+        if (c == want) l = vals[k];
+        if (c == i) d = vals[k];
+    }
+    lo[i] = l;
+    diag[i] = d;
+}
+
+// invw (in: diagonal of A, out: 1 / pivot), mb[i] = invw[i] * lo[i + stride] (the backward multiplier); *bad |= a pivot <= 0
+__global__ void __launch_bounds__(kLineThreads) k_line_factor(int64_t stride, int64_t nplanes, const double *__restrict__ lo,
+                                                              double *__restrict__ invw, double *__restrict__ mb, int *bad) {
+    for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < stride; l += gridDim.x * (int64_t)blockDim.x) {
+        double ip = 0.0;
+        for (int64_t k = 0; k < nplanes; ++k) {
+            const int64_t i = k * stride + l;
+            const double a = lo[i];
+            const double w = invw[i] - a * a * ip;
+            if (!(w > 0.0)) *bad = 1;
+            if (k > 0) mb[i - stride] = ip * a;
+            ip = 1.0 / w;
+            invw[i] = ip;
+        }
+        mb[(nplanes - 1) * stride + l] = 0.0;
+    }
+}
+
+template <bool UPDATE>
+__global__ void __launch_bounds__(kLineThreads, kLineCtasPerSm) k_line_fwd(int stride, int nplanes, const double *__restrict__ p,
+                                                           const double *__restrict__ q, double *__restrict__ x, double *__restrict__ r,
+                                                           const double *__restrict__ lo, const double *__restrict__ invw,
+                                                           double *__restrict__ s, double *partials, mp::ReduceCtl *ctl, double *scal,
+                                                           int rz_cur, int rz_nxt, int pd) {
+    if (!solver_active(scal)) return;
+    const double alpha = UPDATE ? safe_div(scal[rz_cur], scal[S_PQ]) : 0.0;
+    double acc[2] = {0.0, 0.0};
+    const bool pf_lane = pd > 0 && (threadIdx.x & 15) == 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < stride; l += gridDim.x * blockDim.x) {
+        double sp = 0.0;     // s of the plane below
+        auto prefetch = [&](int k0) {
+            if (!pf_lane) return;
+#pragma unroll
+            for (int u = 0; u < kLineU; ++u) {
+                const int k = k0 + pd + u;
+                if (k < nplanes) {
+                    const int i = k * stride + l;
+                    if (UPDATE) { prefetch_l2(p + i); prefetch_l2(q + i); prefetch_l2(x + i); }
+                    prefetch_l2(r + i); prefetch_l2(lo + i); prefetch_l2(invw + i);
+                }
+            }
+        };
+        double pa[kLineU], qa[kLineU], xa[kLineU], ra[kLineU], la[kLineU], wa[kLineU];
+        double pb[kLineU], qb[kLineU], xb[kLineU], rb[kLineU], lb[kLineU], wb[kLineU];
+        auto load = [&](int k0, double (&pp)[kLineU], double (&qq)[kLineU], double (&xx)[kLineU], double (&rr)[kLineU],
+                        double (&ll)[kLineU], double (&ww)[kLineU]) {
+#pragma unroll
+            for (int u = 0; u < kLineU; ++u) {
+                const int k = k0 + u;
+                if (k < nplanes) {
+                    const int i = k * stride + l;
+                    if (UPDATE) { pp[u] = p[i]; qq[u] = q[i]; xx[u] = x[i]; }
+                    rr[u] = r[i]; ll[u] = lo[i]; ww[u] = invw[i];
+                }
+            }
+        };
+        auto work = [&](int k0, double (&pp)[kLineU], double (&qq)[kLineU], double (&xx)[kLineU], double (&rr)[kLineU],
+                        double (&ll)[kLineU], double (&ww)[kLineU]) {
+#pragma unroll
+            for (int u = 0; u < kLineU; ++u) {
+                const int k = k0 + u;
+                if (k < nplanes) {
+                    const int i = k * stride + l;
+                    double ri = rr[u];
+                    if (UPDATE) {
+                        x[i] = xx[u] + alpha * pp[u];
+                        ri -= alpha * qq[u];
+                        r[i] = ri;
+                        acc[1] += ri * ri;
+                    }
+                    const double y = ri - ll[u] * sp;
+                    sp = ww[u] * y;
+                    s[i] = sp;
+                    acc[0] += y * sp;
+                }
+            }
+        };
+        if (pf_lane)
+            for (int k0 = -pd; k0 < 0; k0 += kLineU) prefetch(k0);     // the first pd planes
+        load(0, pa, qa, xa, ra, la, wa);
+        for (int k0 = 0; k0 < nplanes; k0 += 2 * kLineU) {
+            prefetch(k0);
+            load(k0 + kLineU, pb, qb, xb, rb, lb, wb);
+            work(k0, pa, qa, xa, ra, la, wa);
+            prefetch(k0 + kLineU);
+            load(k0 + 2 * kLineU, pa, qa, xa, ra, la, wa);
+            work(k0 + kLineU, pb, qb, xb, rb, lb, wb);
+        }
+    }
+    if (UPDATE) {
+        const int sl_[2] = {rz_nxt, S_RR};
+        grid_reduce<2, kLineThreads>(acc, partials, ctl, scal, sl_, true);
+    } else {
+        double a1[1] = {acc[0]};
+        const int sl_[1] = {rz_nxt};
+        grid_reduce<1, kLineThreads>(a1, partials, ctl, scal, sl_, false);
+    }
+}
+
+// OUT == 0: p = z + beta p (FIRST: p = z), the CG direction update;  OUT == 1: z stored to p (plain application z = M^-1 r)
+template <bool FIRST>
+__global__ void __launch_bounds__(kLineThreads, kLineCtasPerSm) k_line_bwd(int stride, int nplanes, const double *__restrict__ s,
+                                                           const double *__restrict__ mb, double *__restrict__ p, const double *scal,
+                                                           int rz_cur, int rz_nxt, int guarded, int pd) {
+    if (guarded && !solver_active(scal)) return;
+    const double beta = FIRST ? 0.0 : safe_div(scal[rz_nxt], scal[rz_cur]);
+    constexpr int U = 2 * kLineU;
+    const bool pf_lane = pd > 0 && (threadIdx.x & 15) == 0;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < stride; l += gridDim.x * blockDim.x) {
+        double zn = 0.0;     // z of the plane above
+        auto prefetch = [&](int k0) {        // planes k0 - pd, k0 - pd - 1, ...
+            if (!pf_lane) return;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 - pd - u;
+                if (k >= 0 && k < nplanes) {
+                    const int i = k * stride + l;
+                    prefetch_l2(s + i); prefetch_l2(mb + i);
+                    if (!FIRST) prefetch_l2(p + i);
+                }
+            }
+        };
+        double sa[U], ma[U], pa[U], sb[U], mbb[U], pb[U];
+        auto load = [&](int k0, double (&ss)[U], double (&mm)[U], double (&pp)[U]) {   // planes k0, k0-1, ...
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 - u;
+                if (k >= 0) {
+                    const int i = k * stride + l;
+                    ss[u] = s[i]; mm[u] = mb[i];
+                    if (!FIRST) pp[u] = p[i];
+                }
+            }
+        };
+        auto work = [&](int k0, double (&ss)[U], double (&mm)[U], double (&pp)[U]) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 - u;
+                if (k >= 0) {
+                    const int i = k * stride + l;
+                    zn = ss[u] - mm[u] * zn;
+                    p[i] = FIRST ? zn : zn + beta * pp[u];
+                }
+            }
+        };
+        if (pf_lane)
+            for (int k0 = nplanes - 1 + pd; k0 > nplanes - 1; k0 -= U) prefetch(k0);     // the last pd planes
+        load(nplanes - 1, sa, ma, pa);
+        for (int k0 = nplanes - 1; k0 >= 0; k0 -= 2 * U) {
+            prefetch(k0);
+            load(k0 - U, sb, mbb, pb);
+            work(k0, sa, ma, pa);
+            prefetch(k0 - U);
+            load(k0 - 2 * U, sa, ma, pa);
+            work(k0 - U, sb, mbb, pb);
+        }
+    }
+}
+
+int line_grid(const mp_ctx *ctx, int64_t stride) {
+    int64_t g = cdiv(stride, kLineThreads);
+    int64_t cap = (int64_t)ctx->num_sm * kLineCtasPerSm;     // beyond one wave the lines are spread evenly by the grid-stride loop
+    if (cap > kMaxBlocks) cap = kMaxBlocks;
+    if (g > cap) g = cap;
+    return (int)(g < 1 ? 1 : g);
+}
+}  // namespace
+
+extern "C" int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, double *d_lo, double *d_invw, double *d_mb) {
+    MP_CHECK(ctx && d_lo && d_invw && d_mb, "mp_line_setup: null argument");
+    MP_TRY(check_csr(A));
+    MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_line_setup: the row count must be a positive multiple of the line stride");
+    const int64_t n = A->nrow, nplanes = n / stride;
+    int *d_bad = reinterpret_cast<int *>(ctx->d_scalars + S_COUNT + mp::kLocalOff);   // scratch slot (as mp_spectral_bound)
+    MP_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
+    k_line_extract<<<(unsigned)cdiv(n, kThreads), kThreads, 0, ctx->stream>>>(n, stride, A->d_rowptr, A->d_colidx, A->d_vals, d_lo, d_invw);
+    k_line_factor<<<line_grid(ctx, stride), kLineThreads, 0, ctx->stream>>>(stride, nplanes, d_lo, d_invw, d_mb, d_bad);
+    mp::count_launch(ctx, 2);
+    MP_CUDA(cudaGetLastError());
+    int bad = 0;
+    MP_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    MP_CHECK(!bad, "mp_line_setup: a line block is not positive definite (the operator must be SPD)");
+    return 0;
+}
+
+/* z = M^-1 r for the factors of mp_line_setup (tests, other drivers); d_work: nrow doubles */
+extern "C" int mp_line_apply(mp_ctx *ctx, int64_t nrow, int64_t stride, const double *d_lo, const double *d_invw, const double *d_mb,
+                             const double *d_r, double *d_z, double *d_work) {
+    MP_CHECK(ctx && d_lo && d_invw && d_mb && d_r && d_z && d_work, "mp_line_apply: null argument");
+    MP_CHECK(stride > 0 && nrow > 0 && nrow % stride == 0, "mp_line_apply: the row count must be a positive multiple of the line stride");
+    MP_CHECK(nrow < (int64_t)1 << 31, "mp_line_apply: row count beyond 32-bit indexing");
+    // the sweeps are guarded by the solver-active flag: make it true for a stand-alone application
+    const double hs[2] = {1.0, 0.0};
+    MP_CUDA(cudaMemcpyAsync(ctx->d_scalars + S_RR, &hs[0], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MP_CUDA(cudaMemcpyAsync(ctx->d_scalars + S_TOL2, &hs[1], sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    MP_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int g = line_grid(ctx, stride);
+    k_line_fwd<false><<<g, kLineThreads, 0, ctx->stream>>>((int)stride, (int)(nrow / stride), nullptr, nullptr, nullptr, const_cast<double *>(d_r), d_lo,
+                                                            d_invw, d_work, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_TMP0, S_TMP0, ctx->line_prefetch);
+    k_line_bwd<true><<<g, kLineThreads, 0, ctx->stream>>>((int)stride, (int)(nrow / stride), d_work, d_mb, d_z, ctx->d_scalars, S_TMP0, S_TMP0, 0, ctx->line_prefetch);
+    mp::count_launch(ctx, 2);
+    MP_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mp_solve_pcg_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, const double *d_lo, const double *d_invw,
+                                 const double *d_mb, const double *d_b, double *d_x, mp_halo *halo, mp_solve_info *info) {
+    MP_CHECK(ctx && d_lo && d_invw && d_mb && d_b && d_x && info, "mp_solve_pcg_line: null argument");
+    MP_TRY(check_csr(A));
+    MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_solve_pcg_line: the row count must be a positive multiple of the line stride");
+    MP_CHECK(A->nrow < (int64_t)1 << 31, "mp_solve_pcg_line: row count beyond 32-bit indexing");
+    const int64_t n = A->nrow, nc = A->ncol, nplanes = n / stride;
+    int64_t nnz = 0;
+    MP_TRY(nnz_of(ctx, A, &nnz));
+    const int lanes = pick_lanes(A, nnz);
+    double *w = nullptr;
+    MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(3 * n + nc + 8), (void **)&w));
+    double *r = w, *q = w + n, *s = w + 2 * n, *p = w + 3 * n;   // p carries ghost entries
+    const int g1 = grid_for(ctx, n), gl = line_grid(ctx, stride), pd = ctx->line_prefetch;
+    const int every = info->check_every > 0 ? info->check_every : 10;   // must not depend on the rank-local size
+    int total = 0;
+    for (int restart = 0; restart <= kMaxRestart + 1; ++restart) {   // residual replacement, see mp_solve_pcg
+        MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, q, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_invw, r, nullptr, nullptr, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_TMP0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        bool done = false, zero_rhs = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done, &zero_rhs));
+        if (zero_rhs) return zero_solution(ctx, d_x, n, info);
+        if (done || total >= info->maxit || restart > kMaxRestart) break;
+        int cur = S_RZ0, nxt = S_RZ1;
+        k_line_fwd<false><<<gl, kLineThreads, 0, ctx->stream>>>((int)stride, (int)nplanes, nullptr, nullptr, nullptr, r, d_lo, d_invw, s, ctx->d_partials,
+                                                                 ctx->d_ctl, ctx->d_scalars, cur, cur, pd);
+        MP_TRY(reduce_slots(ctx, cur, 1));
+        k_line_bwd<true><<<gl, kLineThreads, 0, ctx->stream>>>((int)stride, (int)nplanes, s, d_mb, p, ctx->d_scalars, cur, cur, 1, pd);
+        mp::count_launch(ctx, 2);
+        for (; total < info->maxit;) {
+            MP_TRY((spmv_halo<1, true>(ctx, A, halo, lanes, p, q, p, S_PQ, 0)));
+            MP_TRY(reduce_slots(ctx, S_PQ, 1));
+            k_line_fwd<true><<<gl, kLineThreads, 0, ctx->stream>>>((int)stride, (int)nplanes, p, q, d_x, r, d_lo, d_invw, s, ctx->d_partials, ctx->d_ctl,
+                                                                    ctx->d_scalars, cur, nxt, pd);
+            MP_TRY(reduce_slots(ctx, (nxt < S_RR ? nxt : S_RR), 2));
+            k_line_bwd<false><<<gl, kLineThreads, 0, ctx->stream>>>((int)stride, (int)nplanes, s, d_mb, p, ctx->d_scalars, cur, nxt, 1, pd);
+            mp::count_launch(ctx, 2);
+            int tmp = cur; cur = nxt; nxt = tmp;
+            ++total;
+            if (total % every == 0 || total == info->maxit) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_pcg_line: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
+            }
+        }
+    }
+    return finish_solve(ctx, info);
+}

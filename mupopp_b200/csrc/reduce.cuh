@@ -69,12 +69,12 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long *flag, unsign
 //  * NCCL mode: rank-local sums go to the LOCAL copy of the scalar block (offset ctl->local_off = kLocalOff) and an out-of-place
 //    ncclAllReduce(local -> global) follows on the host side (reduce_slots); kernels only ever READ the global copy.  This keeps
 //    the allreduce idempotent when the producing kernel has become a no-op after convergence.
-template <int NR>
+template <int NR, int BT = kThreads>   // BT = blockDim.x of the calling kernel (a multiple of 32)
 __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restrict__ partials, mp::ReduceCtl *ctl,
                                             double *__restrict__ scal, const int (&slots)[NR], bool bump_iter, bool use_off = true,
                                             bool exchange = true) {
     static_assert(NR <= mp::kMboxVals, "mailbox too small");
-    __shared__ double sm[NR][kThreads / 32];
+    __shared__ double sm[NR][BT / 32];
     __shared__ double res[NR];
     __shared__ double xin[mp::kMaxRanks][NR];
     __shared__ bool last;
@@ -92,7 +92,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restric
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             double v = 0.0;
-            for (int k = 0; k < kThreads / 32; ++k) v += sm[r][k];
+            for (int k = 0; k < BT / 32; ++k) v += sm[r][k];
             partials[r * kMaxBlocks + blockIdx.x] = v;
         }
         __threadfence();
@@ -108,7 +108,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restric
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         double v = 0.0;
-        for (int k = threadIdx.x; k < (int)gridDim.x; k += kThreads) v += __ldcg(&partials[r * kMaxBlocks + k]);
+        for (int k = threadIdx.x; k < (int)gridDim.x; k += BT) v += __ldcg(&partials[r * kMaxBlocks + k]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         __syncthreads();
@@ -116,7 +116,7 @@ __device__ __forceinline__ void grid_reduce(double (&acc)[NR], double *__restric
         __syncthreads();
         if (threadIdx.x == 0) {
             double s = 0.0;
-            for (int k = 0; k < kThreads / 32; ++k) s += sm[r][k];
+            for (int k = 0; k < BT / 32; ++k) s += sm[r][k];
             if (comm) res[r] = s;
             else scal[slots[r] + (use_off ? (int)ctl->local_off : 0)] = s;
         }

@@ -253,6 +253,20 @@ class CsrMatrix:
         check(self.ctx.lib.mp_jacobi_setup(self.ctx.h, C.byref(self.c), ptr(self.dinv)), "mp_jacobi_setup")
         return self.dinv
 
+    def line_setup(self, stride):
+        """Factor the line (block-tridiagonal) Jacobi preconditioner: rows i, i + stride, ... form one line (mp_line_setup)."""
+        stride = int(stride)
+        lo, invw, mb = (self.ctx.empty(self.nrow) for _ in range(3))
+        check(self.ctx.lib.mp_line_setup(self.ctx.h, C.byref(self.c), stride, ptr(lo), ptr(invw), ptr(mb)), "mp_line_setup")
+        self._line = (stride, lo, invw, mb)
+        return self._line
+
+    def line_apply(self, r, z):
+        st, lo, invw, mb = self._line
+        work = self.ctx.empty(self.nrow)
+        check(self.ctx.lib.mp_line_apply(self.ctx.h, self.nrow, st, ptr(lo), ptr(invw), ptr(mb), ptr(r), ptr(z), ptr(work)), "mp_line_apply")
+        return z
+
     def apply_dirichlet(self, rhs, isbc, g, matrix=True):
         check(self.ctx.lib.mp_apply_dirichlet_sym(self.ctx.h, self.nrow, ptr(self.rowptr), ptr(self.colidx),
                                                   ptr(self.vals) if matrix else None, ptr(rhs), ptr(isbc), ptr(g)),
@@ -267,7 +281,16 @@ class CsrMatrix:
                              shape=(self.nrow, self.ncol))
 
     def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True, restart=50,
-              cheb_degree=3, cheb_ratio=30.0):
+              cheb_degree=3, cheb_ratio=30.0, line_stride=0):
+        if method == "pcg_line":
+            if getattr(self, "_line", None) is None or self._line[0] != int(line_stride) or refresh_jacobi:
+                self.line_setup(line_stride)
+            self.sync_sell()
+            info = MpSolveInfo(rtol, atol, int(maxit), int(check_every), 0, 0, 0.0)
+            st, lo, invw, mb = self._line
+            check(self.ctx.lib.mp_solve_pcg_line(self.ctx.h, C.byref(self.c), st, ptr(lo), ptr(invw), ptr(mb), ptr(b), ptr(x),
+                                                 halo.h if halo is not None else None, C.byref(info)), "mp_solve_pcg_line")
+            return SolveResult(info.niter, bool(info.converged), info.relres)
         if self.dinv is None or refresh_jacobi:
             self.jacobi_setup()
         self.sync_sell()

@@ -102,13 +102,13 @@ def boundary_data_from_bcs(W, bcs):
 class ModeFStepper:
     """One mode-F problem behind `solve(a == L, sol, bcs)`: owns the TransportSolverF, moves Function blocks in and out."""
 
-    def __init__(self, ctx, W, bcs, model, f_nodal, rtol=1e-12, maxit=50000):
+    def __init__(self, ctx, W, bcs, model, f_nodal, rtol=1e-12, maxit=50000, p_precond="line"):
         self.ctx, self.W, self.bcs = ctx, W, list(bcs)       # references keep the ids used in cache keys alive
         per = W.periodic
         self.sig = bc_signature(bcs)
         bd = boundary_data_from_bcs(W, bcs)
         self.s = TransportSolverF(ctx, W.mesh, model, bd, f_source=f_nodal, rtol=rtol, maxit=maxit,
-                                  vert2dof=per.vert2dof if per is not None else None, p_guess="previous")
+                                  vert2dof=per.vert2dof if per is not None else None, p_guess="previous", p_precond=p_precond)
         self._lump = None
         self._edges = None
         self._tmp = ctx.zeros(self.s.nown)

@@ -399,9 +399,13 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
         fs = _source_nodal(d["f"], W)
         if mode == "F":
             from .modef_api import ModeFStepper
-            key = ("multiF", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.sigma, id(model.K) if not np.isscalar(model.K) else model.K)
+            # "preconditioner" (dolfin's solver_parameters key): "jacobi" | "chebyshev" | "line" (lattice-line block Jacobi on structured
+            # meshes, point Jacobi elsewhere) | "default" (= "line")
+            pc = str(solver_parameters.get("preconditioner", "default")).lower()
+            pc = "line" if pc in ("default", "none") else pc
+            key = ("multiF", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.sigma, id(model.K) if not np.isscalar(model.K) else model.K, pc)
             if key not in _CACHE:
-                _CACHE[key] = ModeFStepper(ctx, W, bcs, model, fs, rtol=float(solver_parameters.get("relative_tolerance", 1e-12)))
+                _CACHE[key] = ModeFStepper(ctx, W, bcs, model, fs, rtol=float(solver_parameters.get("relative_tolerance", 1e-12)), p_precond=pc)
             st = _CACHE[key]
             st.refresh(bcs, model, fs)
             return st.step(d["sol_prev"], u)

@@ -124,18 +124,39 @@ def make_boundary_data(mesh, u_marker, u_value, c0_marker=None, c0_value=0.0, pe
     return BoundaryDataF(p_isbc, flux, c0_isbc, c0_g)
 
 
+def lattice_line_stride(mesh, vert2dof=None, n_owned=None):
+    """Rows per lattice plane of a structured mesh (`mesh.grid`): the dofs of the grid line through in-plane position l are
+    l, l + stride, l + 2 stride, ...  (BoxMesh numbers vertices iz*npl + iy*(nx+1) + ix, periodic x/y faces leave nx*ny dofs per
+    plane, slab partitions keep the owned planes first).  0 when the mesh has no such structure."""
+    grid = getattr(mesh, "grid", None)
+    if grid is None:
+        return 0
+    nv = mesh.num_vertices()
+    nplanes_v = None
+    per_plane_v = int(np.prod([g + 1 for g in grid[:-1]]))
+    if nv % per_plane_v != 0:
+        return 0
+    nplanes_v = nv // per_plane_v
+    ndof = nv if vert2dof is None else int(np.max(vert2dof)) + 1
+    if ndof % nplanes_v != 0:
+        return 0
+    stride = ndof // nplanes_v
+    nown = ndof if n_owned is None else int(n_owned)
+    return stride if nown % stride == 0 else 0
+
+
 class TransportSolverF:
     """GPU state + operators of one mode-F problem.  Fields are torch fp64 tensors on the device."""
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
                  rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
-                 vert2dof=None, row_ordered=True, p_precond="jacobi", cheb_degree=3, p_guess="previous"):
+                 vert2dof=None, row_ordered=True, p_precond="line", cheb_degree=3, p_guess="previous"):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
         # pressure PCG preconditioner: "jacobi" (default) or "chebyshev" (degree-k Chebyshev-Jacobi polynomial: same time on one GPU at
         # 200^3, 3-4x fewer reduction points per SpMV -- meant for multi-GPU runs; not yet the default there, see DESIGN.md section 5)
-        self.p_method = "pcg_chebyshev" if p_precond == "chebyshev" else "pcg"
+        self.p_method = {"chebyshev": "pcg_chebyshev", "line": "pcg_line"}.get(p_precond, "pcg")
         self.cheb_degree = cheb_degree
         self.p_guess = p_guess          # "extrapolate" (2 p^n - p^(n-1)) or "previous" (p^n) as the pressure PCG's initial iterate
         self._p_hist = 0                # pressure solutions of the current time series held in (p, p_old)
@@ -174,6 +195,15 @@ class TransportSolverF:
         self.plan.scatter_matrix(self.emat, self.L)
         self.L.apply_dirichlet(None, self.p_isbc, self.zeros_loc)          # p = 0: homogeneous, matrix eliminated once
         self.L.jacobi_setup()
+        # "line": block-tridiagonal Jacobi along the lattice lines of the LAST coordinate (rows are numbered plane by plane on a
+        # BoxMesh / RectangleMesh, also inside a z-slab); falls back to point Jacobi on meshes without that structure
+        self.line_stride = 0
+        if self.p_method == "pcg_line":
+            self.line_stride = lattice_line_stride(mesh, vert2dof, self.nown)
+            if self.line_stride > 0:
+                self.L.line_setup(self.line_stride)
+            else:
+                self.p_method = "pcg"
         self.A = self.plan.new_matrix()
         # state
         self.u = ctx.zeros(Cn * d)
@@ -286,7 +316,7 @@ class TransportSolverF:
             self.p, self.p_old = self.p_old, self.p
         else:
             self.p_old.copy_(self.p)
-        rp = self.L.solve(self.p_method, self.rhs, self.p, cheb_degree=self.cheb_degree, **kw)
+        rp = self.L.solve(self.p_method, self.rhs, self.p, cheb_degree=self.cheb_degree, line_stride=self.line_stride, **kw)
         self._p_hist += 1
         self._exchange(self.p)
         # 4. velocity recovery, then rotate the state

@@ -261,3 +261,87 @@ def test_chebyshev_pressure_preconditioner_gives_the_same_fields(ctx):
         out.append((s.p.cpu().numpy().copy(), s.c0.cpu().numpy().copy(), its))
     assert rel(out[1][0], out[0][0]) < 1e-10 and rel(out[1][1], out[0][1]) < 1e-10
     assert sum(out[1][2]) < sum(out[0][2])          # fewer (but more expensive) outer iterations
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_line_preconditioner_and_line_pcg(ctx, dim):
+    """Block-tridiagonal (lattice line) Jacobi: mp_line_setup/mp_line_apply == SciPy's solve with the tridiagonal part of the operator along
+    the lines of the last coordinate, mp_solve_pcg_line == LU, and fewer iterations than point Jacobi on the thin boxes of the reference
+    (run/CCS/CCS_3D_top_source.py: [0,4]x[0,4]x[0,1])."""
+    import ctypes as C
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import mupopp_b200 as mp
+    from mupopp_b200._lib import check, ptr
+    from mupopp_b200.device import DeviceMesh, Plan
+    from mupopp_b200.transport import lattice_line_stride
+    if dim == 3:
+        pm, om = mp.BoxMesh((0, 0, 0), (4, 4, 1), 9, 8, 11), fem.box_mesh((0, 0, 0), (4, 4, 1), 9, 8, 11)
+        stride = 10 * 9
+    else:
+        pm, om = mp.RectangleMesh((0, 0), (4, 1), 13, 21), fem.rectangle_mesh(0, 0, 4, 1, 13, 21)
+        stride = 14
+    assert lattice_line_stride(pm) == stride
+    dm = DeviceMesh(ctx, pm)
+    plan = Plan(ctx, dm.cells, dm.cells, dm.nvert, dm.nvert)
+    rng = np.random.default_rng(5)
+    K = 0.5 + rng.random(om.nv)
+    emat = ctx.empty(dm.ncell * (dim + 1) ** 2)
+    A = plan.new_matrix()
+    check(ctx.lib.mp_elem_p1_stiffness(ctx.h, C.byref(dm.c), ptr(ctx.to_device(K)), 0.0, 1.0, ptr(emat)))
+    plan.scatter_matrix(emat, A)
+    isbc = (om.coords[:, -1] < 1e-12).astype(np.uint8)
+    b = rng.standard_normal(om.nv)
+    bd_ = ctx.to_device(b)
+    A.apply_dirichlet(bd_, ctx.to_device(isbc), ctx.to_device(rng.random(om.nv)))
+    Ao = A.to_scipy().tocsr()
+    bo = bd_.cpu().numpy()
+    # the preconditioner alone
+    A.line_setup(stride)
+    n = om.nv
+    lo = np.asarray(Ao[np.arange(stride, n), np.arange(0, n - stride)]).ravel()
+    T = sp.diags([lo, Ao.diagonal(), lo], [-stride, 0, stride]).tocsc()
+    r = rng.standard_normal(n)
+    z = ctx.zeros(n)
+    A.line_apply(ctx.to_device(r), z)
+    assert rel(z.cpu().numpy(), spla.splu(T).solve(r)) < 1e-13
+    # line PCG against LU and against point Jacobi
+    xo = spla.splu(Ao.tocsc()).solve(bo)
+    x = ctx.zeros(n)
+    res = A.solve("pcg_line", bd_, x, rtol=1e-13, maxit=5000, line_stride=stride)
+    xj = ctx.zeros(n)
+    resj = A.solve("pcg", bd_, xj, rtol=1e-13, maxit=5000)
+    print("line PCG dim %d: %d iterations (point Jacobi %d), err %.2e" % (dim, res.niter, resj.niter, rel(x.cpu().numpy(), xo)))
+    assert res.converged and rel(x.cpu().numpy(), xo) < 1e-10
+    assert res.niter < 0.7 * resj.niter
+    # a row count that is not a multiple of the stride is refused, loudly
+    from mupopp_b200._lib import MpError
+    with pytest.raises(MpError):
+        A.line_setup(stride + 1)
+
+
+def test_mode_f_step_with_line_preconditioned_pressure(ctx):
+    """TransportSolverF(p_precond="line") gives the same fields as the Jacobi-PCG default (the preconditioner changes the iteration count,
+    not the converged answer), also with periodic side faces (nx*ny dofs per plane)."""
+    import mupopp_b200 as mp
+    from mupopp_b200.mesh import box_periodic_map
+    from mupopp_b200.transport import TransportModel, TransportSolverF, make_boundary_data
+    pm = mp.BoxMesh((0, 0, 0), (4, 4, 1), 8, 8, 10)
+    top = lambda x: x[2] > 1.0 - 1e-12
+    model = TransportModel.ccs_three_component(Pe=500.0, Da=0.1, phi=0.05, alpha=1e-8, dt=0.1, K=1.0, zh=(0.0, 0.0, 1.0))
+    for periodic in (False, True):
+        pmap = box_periodic_map(pm, (0, 1)) if periodic else None
+        bd = make_boundary_data(pm, top, lambda x: np.array([0.0, 0.0, -0.5]), top, 0.1, periodic=pmap)
+        out = {}
+        for pc in ("jacobi", "line"):
+            s = TransportSolverF(ctx, pm, model, bd, rtol=1e-13, vert2dof=None if pmap is None else pmap.vert2dof, p_precond=pc)
+            nd = s.nloc
+            s.set_state(c1=0.1 * np.ones(nd))
+            its = 0
+            for _ in range(3):
+                its += s.step()["p"].niter
+            assert pc != "line" or (s.p_method == "pcg_line" and s.line_stride == (64 if periodic else 81))
+            out[pc] = (s.p.cpu().numpy().copy(), s.c0.cpu().numpy().copy(), its)
+        print("mode F periodic=%s: pressure iterations jacobi %d, line %d" % (periodic, out["jacobi"][2], out["line"][2]))
+        assert rel(out["line"][0], out["jacobi"][0]) < 1e-10 and rel(out["line"][1], out["jacobi"][1]) < 1e-10
+        assert out["line"][2] < out["jacobi"][2]
