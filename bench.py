@@ -171,7 +171,8 @@ def workload_config(args, nranks):
     return {"workload": "CCS 3-component reactive transport (mupopp CCS.advection_diffusion_three_component), mode F, "
                         "BoxMesh [0,4]x[0,4]x[0,1] %d^3 x 6 tets, P1, %d dofs/field" % (args.n, ndofs_field(args)),
             "n": args.n, "dofs_per_field": ndofs_field(args), "cells": 6 * args.n ** 3,
-            "physics": PHYS, "krylov_rtol": args.rtol, "c0_solver": args.c0_method + ("(%d)" % args.gmres_restart if args.c0_method == "gmres" else ""), "preconditioner": args.p_precond + ("(%d)" % args.cheb_degree if args.p_precond == "chebyshev" else ""), "side_walls": args.sides,
+            "physics": PHYS, "krylov_rtol": args.rtol, "c0_solver": args.c0_method + ("(%d)" % args.gmres_restart if args.c0_method == "gmres" else ""), "preconditioner": args.p_precond + ("(%d)" % args.cheb_degree if args.p_precond == "chebyshev" else ""),
+            "c0_preconditioner": "line" if (args.p_precond == "line" and args.c0_precond == "auto" and args.c0_method == "bicgstab") else "jacobi", "side_walls": args.sides,
             "partition": "z-slabs x%d" % nranks if nranks > 1 else "single GPU",
             "l2_policy": "inputs larger than L2 (CSR operators 1.6 GB each at n=200 vs 126 MB L2)"}
 
@@ -200,7 +201,7 @@ def build_problem(ctx, args, rank, nranks):
         fs = source_term(mesh.coords)
         solver = TransportSolverF(ctx, mesh, model, bd, f_source=pmap.restrict(fs) if per else fs, rtol=args.rtol, maxit=args.maxit,
                                   c0_method=args.c0_method, gmres_restart=args.gmres_restart, vert2dof=pmap.vert2dof if per else None,
-                                  p_precond=args.p_precond, cheb_degree=args.cheb_degree, p_guess=args.p_guess)
+                                  p_precond=args.p_precond, cheb_degree=args.cheb_degree, p_guess=args.p_guess, c0_precond=args.c0_precond)
         c1 = 0.1 * np.ones(solver.dm.ndof)
     else:
         part = partition.slab_partition(BOX, (n, n, n), rank, nranks, periodic_xy=per)
@@ -209,7 +210,7 @@ def build_problem(ctx, args, rank, nranks):
         fs = source_term(part.mesh.coords)
         solver = TransportSolverF(ctx, part.mesh, model, bd, f_source=part.periodic.restrict(fs) if per else fs, rtol=args.rtol,
                                   maxit=args.maxit, c0_method=args.c0_method, gmres_restart=args.gmres_restart, halo=halo, n_owned=part.n_owned,
-                                  vert2dof=part.vert2dof, p_precond=args.p_precond, cheb_degree=args.cheb_degree, p_guess=args.p_guess)
+                                  vert2dof=part.vert2dof, p_precond=args.p_precond, cheb_degree=args.cheb_degree, p_guess=args.p_guess, c0_precond=args.c0_precond)
         c1 = 0.1 * np.ones(part.n_local)
     solver.set_state(c1=c1)
     return solver
@@ -537,6 +538,7 @@ def main():
     ap.add_argument("--gmres-restart", type=int, default=30)
     ap.add_argument("--p-precond", default="line", choices=["jacobi", "chebyshev", "line"],
                     help="pressure PCG preconditioner: point Jacobi, Chebyshev-Jacobi polynomial, or lattice-line block Jacobi (tridiagonal z-lines)")
+    ap.add_argument("--c0-precond", default="auto", choices=["auto", "jacobi"], help="transport-row BiCGStab preconditioner: auto = the pressure's lattice lines when --p-precond line, else Jacobi")
     ap.add_argument("--cheb-degree", type=int, default=3)
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-api", dest="no_api", action="store_true", help="e2e through TransportSolverF.step instead of the mupopp/fenics plugin call")

@@ -275,14 +275,18 @@ int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, c
  * RectangleMesh lattices, also z-slab partitions of them): M = diag(A) + the (i, i -+ stride) entries of A, i.e. one tridiagonal block
  * per grid line l = i mod stride.  Replaces what the reference gets from PETSc's LU / AMG on the thin boxes of
  * run/CCS/CCS_3D_top_source.py, run/LVL_3D/LVL_RII3D.py ([0,4]x[0,4]x[0,1]: the z-coupling is 16x the in-plane coupling).
- * mp_line_setup factors M = L D L^T once (d_lo, d_invw, d_mb: nrow doubles each, caller-allocated; fails if a block is not SPD),
+ * mp_line_setup factors every block M_l = L D U (d_lo, d_invw, d_mb: nrow doubles each, caller-allocated; spd != 0: fails unless every
+ * pivot is positive -- PCG needs that; spd == 0: general tridiagonal blocks for the non-symmetric transport row),
  * mp_line_apply computes z = M^-1 r (d_work: nrow doubles), mp_solve_pcg_line runs PCG with the two sweeps fused into the CG vector
- * updates.  A->nrow must be a multiple of stride. */
-int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, double *d_lo, double *d_invw, double *d_mb);
+ * updates, mp_solve_bicgstab_line runs right-preconditioned BiCGStab with the forward sweeps fused into the p / s updates.
+ * A->nrow must be a multiple of stride. */
+int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, int spd, double *d_lo, double *d_invw, double *d_mb);
 int mp_line_apply(mp_ctx *ctx, int64_t nrow, int64_t stride, const double *d_lo, const double *d_invw, const double *d_mb,
                   const double *d_r, double *d_z, double *d_work);
 int mp_solve_pcg_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, const double *d_lo, const double *d_invw, const double *d_mb,
                       const double *d_b, double *d_x, mp_halo *halo, mp_solve_info *info);
+int mp_solve_bicgstab_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, const double *d_lo, const double *d_invw, const double *d_mb,
+                           const double *d_b, double *d_x, mp_halo *halo, mp_solve_info *info);
 
 /* Jacobi-preconditioned BiCGStab (non-symmetric transport rows). */
 int mp_solve_bicgstab(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, const double *d_b, double *d_x, mp_halo *halo,

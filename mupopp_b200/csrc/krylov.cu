@@ -1437,35 +1437,37 @@ __device__ __forceinline__ void prefetch_l2(const double *a) { asm volatile("pre
 
 __global__ void __launch_bounds__(kThreads) k_line_extract(int64_t nrow, int64_t stride, const int32_t *__restrict__ rowptr,
                                                            const int32_t *__restrict__ colidx, const double *__restrict__ vals,
-                                                           double *__restrict__ lo, double *__restrict__ diag) {
+                                                           double *__restrict__ lo, double *__restrict__ diag, double *__restrict__ up) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= nrow) return;
-    double l = 0.0, d = 0.0;
-    const int64_t want = i - stride;
+    double l = 0.0, d = 0.0, u = 0.0;
+    const int64_t below = i - stride, above = i + stride;
     for (int32_t k = rowptr[i]; k < rowptr[i + 1]; ++k) {
         const int64_t c = colidx[k];
-        if (c == want) l = vals[k];
+        if (c == below) l = vals[k];
         if (c == i) d = vals[k];
+        if (c == above && above < nrow) u = vals[k];      // columns >= nrow are ghosts of a neighbouring slab: outside the block
     }
     lo[i] = l;
     diag[i] = d;
+    up[i] = u;
 }
 
-// invw (in: diagonal of A, out: 1 / pivot), mb[i] = invw[i] * lo[i + stride] (the backward multiplier); *bad |= a pivot <= 0
+// LU of every line block: invw (in: diagonal of A, out: 1 / pivot), mb (in: the (i, i + stride) entries, out: invw[i] * upper[i], the
+// backward multiplier); *bad |= a pivot that is not positive (spd) / zero or NaN (general)
 __global__ void __launch_bounds__(kLineThreads) k_line_factor(int64_t stride, int64_t nplanes, const double *__restrict__ lo,
-                                                              double *__restrict__ invw, double *__restrict__ mb, int *bad) {
+                                                              double *__restrict__ invw, double *__restrict__ mb, int spd, int *bad) {
     for (int64_t l = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; l < stride; l += gridDim.x * (int64_t)blockDim.x) {
-        double ip = 0.0;
+        double ip = 0.0, up_prev = 0.0;
         for (int64_t k = 0; k < nplanes; ++k) {
             const int64_t i = k * stride + l;
-            const double a = lo[i];
-            const double w = invw[i] - a * a * ip;
-            if (!(w > 0.0)) *bad = 1;
-            if (k > 0) mb[i - stride] = ip * a;
+            const double w = invw[i] - lo[i] * up_prev * ip;
+            if (spd ? !(w > 0.0) : !(w != 0.0)) *bad = 1;
             ip = 1.0 / w;
             invw[i] = ip;
+            up_prev = mb[i];
+            mb[i] = ip * up_prev;
         }
-        mb[(nplanes - 1) * stride + l] = 0.0;
     }
 }
 
@@ -1610,6 +1612,66 @@ __global__ void __launch_bounds__(kLineThreads, kLineCtasPerSm) k_line_bwd(int s
     }
 }
 
+
+// BiCGStab with the line preconditioner (right preconditioning: v = A M^-1 p, t = A M^-1 s).  The forward sweep is fused with the
+// vector update that produces its input:  MODE 0: e = r + beta (p - omega v), stored to p (first: e = r);  MODE 1: e = r - alpha v,
+// stored to s.  out <- D^-1 L^-1 e; the plain backward sweep (k_line_bwd<true>) then gives y = M^-1 p / z = M^-1 s.
+template <int MODE>
+__global__ void __launch_bounds__(kLineThreads, kLineCtasPerSm) k_line_fwd_bicg(int stride, int nplanes, int first, const double *__restrict__ r,
+                                                                                const double *__restrict__ v, double *__restrict__ e,
+                                                                                const double *__restrict__ lo, const double *__restrict__ invw,
+                                                                                double *__restrict__ out, const double *scal, int rho_cur) {
+    if (!solver_active(scal)) return;
+    double cb = 0.0, cv = 0.0;     // e = r + cb e_old + cv v
+    if (MODE == 0) {
+        if (!first) {
+            const double omega = safe_div(scal[S_TS], scal[S_TT]);
+            cb = safe_div(scal[rho_cur], scal[S_RV]) * safe_div(scal[S_TT], scal[S_TS]);
+            cv = -cb * omega;
+        }
+    } else {
+        cv = -safe_div(scal[rho_cur], scal[S_RV]);
+    }
+    const bool use_e = MODE == 0 && !first, use_v = MODE == 1 || !first;
+    constexpr int U = kLineU;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < stride; l += gridDim.x * blockDim.x) {
+        double sp = 0.0;
+        double ra[U], va[U], ea[U], la[U], wa[U], rb[U], vb[U], eb[U], lb[U], wb[U];
+        auto load = [&](int k0, double (&rr)[U], double (&vv)[U], double (&ee)[U], double (&ll)[U], double (&ww)[U]) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + u;
+                if (k < nplanes) {
+                    const int i = k * stride + l;
+                    rr[u] = r[i]; ll[u] = lo[i]; ww[u] = invw[i];
+                    vv[u] = use_v ? v[i] : 0.0;
+                    ee[u] = use_e ? e[i] : 0.0;
+                }
+            }
+        };
+        auto work = [&](int k0, double (&rr)[U], double (&vv)[U], double (&ee)[U], double (&ll)[U], double (&ww)[U]) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int k = k0 + u;
+                if (k < nplanes) {
+                    const int i = k * stride + l;
+                    const double ei = rr[u] + cb * ee[u] + cv * vv[u];
+                    e[i] = ei;
+                    sp = ww[u] * (ei - ll[u] * sp);
+                    out[i] = sp;
+                }
+            }
+        };
+        load(0, ra, va, ea, la, wa);
+        for (int k0 = 0; k0 < nplanes; k0 += 2 * U) {
+            load(k0 + U, rb, vb, eb, lb, wb);
+            work(k0, ra, va, ea, la, wa);
+            load(k0 + 2 * U, ra, va, ea, la, wa);
+            work(k0 + U, rb, vb, eb, lb, wb);
+        }
+    }
+}
+
 int line_grid(const mp_ctx *ctx, int64_t stride) {
     int64_t g = cdiv(stride, kLineThreads);
     int64_t cap = (int64_t)ctx->num_sm * kLineCtasPerSm;     // beyond one wave the lines are spread evenly by the grid-stride loop
@@ -1619,21 +1681,22 @@ int line_grid(const mp_ctx *ctx, int64_t stride) {
 }
 }  // namespace
 
-extern "C" int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, double *d_lo, double *d_invw, double *d_mb) {
+extern "C" int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, int spd, double *d_lo, double *d_invw, double *d_mb) {
     MP_CHECK(ctx && d_lo && d_invw && d_mb, "mp_line_setup: null argument");
     MP_TRY(check_csr(A));
     MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_line_setup: the row count must be a positive multiple of the line stride");
     const int64_t n = A->nrow, nplanes = n / stride;
     int *d_bad = reinterpret_cast<int *>(ctx->d_scalars + S_COUNT + mp::kLocalOff);   // scratch slot (as mp_spectral_bound)
     MP_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-    k_line_extract<<<(unsigned)cdiv(n, kThreads), kThreads, 0, ctx->stream>>>(n, stride, A->d_rowptr, A->d_colidx, A->d_vals, d_lo, d_invw);
-    k_line_factor<<<line_grid(ctx, stride), kLineThreads, 0, ctx->stream>>>(stride, nplanes, d_lo, d_invw, d_mb, d_bad);
+    k_line_extract<<<(unsigned)cdiv(n, kThreads), kThreads, 0, ctx->stream>>>(n, stride, A->d_rowptr, A->d_colidx, A->d_vals, d_lo, d_invw, d_mb);
+    k_line_factor<<<line_grid(ctx, stride), kLineThreads, 0, ctx->stream>>>(stride, nplanes, d_lo, d_invw, d_mb, spd, d_bad);
     mp::count_launch(ctx, 2);
     MP_CUDA(cudaGetLastError());
     int bad = 0;
     MP_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
-    MP_CHECK(!bad, "mp_line_setup: a line block is not positive definite (the operator must be SPD)");
+    MP_CHECK(!bad, spd ? "mp_line_setup: a line block is not positive definite (the operator must be SPD)"
+                       : "mp_line_setup: zero pivot in a line block");
     return 0;
 }
 
@@ -1702,6 +1765,60 @@ extern "C" int mp_solve_pcg_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, c
                 MP_CUDA(cudaGetLastError());
                 MP_TRY(poll(ctx));
                 if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_pcg_line: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
+            }
+        }
+    }
+    return finish_solve(ctx, info);
+}
+
+/* BiCGStab with the line preconditioner for the non-symmetric SUPG transport row (factors from mp_line_setup(..., spd = 0, ...)). */
+extern "C" int mp_solve_bicgstab_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, const double *d_lo, const double *d_invw,
+                                      const double *d_mb, const double *d_b, double *d_x, mp_halo *halo, mp_solve_info *info) {
+    MP_CHECK(ctx && d_lo && d_invw && d_mb && d_b && d_x && info, "mp_solve_bicgstab_line: null argument");
+    MP_TRY(check_csr(A));
+    MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_solve_bicgstab_line: the row count must be a positive multiple of the line stride");
+    MP_CHECK(A->nrow < (int64_t)1 << 31, "mp_solve_bicgstab_line: row count beyond 32-bit indexing");
+    const int64_t n = A->nrow, nc = A->ncol;
+    const int st = (int)stride, nplanes = (int)(n / stride);
+    int64_t nnz = 0;
+    MP_TRY(nnz_of(ctx, A, &nnz));
+    const int lanes = pick_lanes(A, nnz);
+    double *w = nullptr;
+    MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(7 * n + 2 * nc + 8), (void **)&w));
+    double *r = w, *rhat = w + n, *p = w + 2 * n, *v = w + 3 * n, *s = w + 4 * n, *t = w + 5 * n, *f = w + 6 * n, *y = w + 7 * n, *z = w + 7 * n + nc;
+    const int g1 = grid_for(ctx, n), gl = line_grid(ctx, stride);
+    const int every = info->check_every > 0 ? info->check_every : 10;   // rank-independent (collective control flow)
+    int total = 0;
+    for (int restart = 0; restart <= kMaxRestart + 1; ++restart) {   // residual replacement, see mp_solve_pcg
+        MP_TRY((spmv_halo<0, false>(ctx, A, halo, lanes, d_x, v, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, v, d_invw, r, nullptr, rhat, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_RHO0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        MP_TRY(reduce_slots(ctx, S_RHO0, 1));
+        bool done = false, zero_rhs = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done, &zero_rhs));
+        if (zero_rhs) return zero_solution(ctx, d_x, n, info);
+        if (done || total >= info->maxit || restart > kMaxRestart) break;
+        int cur = S_RHO0, nxt = S_RHO1;
+        for (int it = 0; total < info->maxit; ++it) {
+            k_line_fwd_bicg<0><<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, it == 0 ? 1 : 0, r, v, p, d_lo, d_invw, f, ctx->d_scalars, cur);
+            k_line_bwd<true><<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, f, d_mb, y, ctx->d_scalars, cur, cur, 1, 0);
+            MP_TRY((spmv_halo<1, true>(ctx, A, halo, lanes, y, v, rhat, S_RV, 0)));
+            MP_TRY(reduce_slots(ctx, S_RV, 1));
+            k_line_fwd_bicg<1><<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, 0, r, v, s, d_lo, d_invw, f, ctx->d_scalars, cur);
+            k_line_bwd<true><<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, f, d_mb, z, ctx->d_scalars, cur, cur, 1, 0);
+            MP_TRY((spmv_halo<2, true>(ctx, A, halo, lanes, z, t, s, S_TS, S_TT)));
+            MP_TRY(reduce_slots(ctx, S_TS, 2));
+            k_bicg_x<<<g1, kThreads, 0, ctx->stream>>>(n, y, z, s, t, rhat, d_x, r, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, cur, nxt);
+            MP_TRY(reduce_slots(ctx, (nxt < S_RR ? nxt : S_RR), 2));
+            mp::count_launch(ctx, 5);
+            int tmp = cur; cur = nxt; nxt = tmp;
+            ++total;
+            if (total % every == 0 || total == info->maxit) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_bicgstab_line: NaN residual at iteration %d", total); return 4; }
                 if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
             }
         }

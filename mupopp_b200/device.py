@@ -253,11 +253,13 @@ class CsrMatrix:
         check(self.ctx.lib.mp_jacobi_setup(self.ctx.h, C.byref(self.c), ptr(self.dinv)), "mp_jacobi_setup")
         return self.dinv
 
-    def line_setup(self, stride):
-        """Factor the line (block-tridiagonal) Jacobi preconditioner: rows i, i + stride, ... form one line (mp_line_setup)."""
+    def line_setup(self, stride, spd=True):
+        """Factor the line (block-tridiagonal) Jacobi preconditioner: rows i, i + stride, ... form one line (mp_line_setup).
+        `spd`: insist on positive pivots (PCG); False for the non-symmetric transport row.  The three factor arrays are reused."""
         stride = int(stride)
-        lo, invw, mb = (self.ctx.empty(self.nrow) for _ in range(3))
-        check(self.ctx.lib.mp_line_setup(self.ctx.h, C.byref(self.c), stride, ptr(lo), ptr(invw), ptr(mb)), "mp_line_setup")
+        old = getattr(self, "_line", None)
+        lo, invw, mb = old[1:] if old is not None else (self.ctx.empty(self.nrow) for _ in range(3))
+        check(self.ctx.lib.mp_line_setup(self.ctx.h, C.byref(self.c), stride, int(bool(spd)), ptr(lo), ptr(invw), ptr(mb)), "mp_line_setup")
         self._line = (stride, lo, invw, mb)
         return self._line
 
@@ -282,14 +284,15 @@ class CsrMatrix:
 
     def solve(self, method, b, x, rtol=1e-12, atol=0.0, maxit=10000, halo=None, check_every=0, refresh_jacobi=True, restart=50,
               cheb_degree=3, cheb_ratio=30.0, line_stride=0):
-        if method == "pcg_line":
+        if method in ("pcg_line", "bicgstab_line"):
             if getattr(self, "_line", None) is None or self._line[0] != int(line_stride) or refresh_jacobi:
-                self.line_setup(line_stride)
+                self.line_setup(line_stride, spd=method == "pcg_line")
             self.sync_sell()
             info = MpSolveInfo(rtol, atol, int(maxit), int(check_every), 0, 0, 0.0)
             st, lo, invw, mb = self._line
-            check(self.ctx.lib.mp_solve_pcg_line(self.ctx.h, C.byref(self.c), st, ptr(lo), ptr(invw), ptr(mb), ptr(b), ptr(x),
-                                                 halo.h if halo is not None else None, C.byref(info)), "mp_solve_pcg_line")
+            fn = self.ctx.lib.mp_solve_pcg_line if method == "pcg_line" else self.ctx.lib.mp_solve_bicgstab_line
+            check(fn(self.ctx.h, C.byref(self.c), st, ptr(lo), ptr(invw), ptr(mb), ptr(b), ptr(x),
+                     halo.h if halo is not None else None, C.byref(info)), "mp_solve_" + method)
             return SolveResult(info.niter, bool(info.converged), info.relres)
         if self.dinv is None or refresh_jacobi:
             self.jacobi_setup()

@@ -150,7 +150,7 @@ class TransportSolverF:
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
                  rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
-                 vert2dof=None, row_ordered=True, p_precond="line", cheb_degree=3, p_guess="previous"):
+                 vert2dof=None, row_ordered=True, p_precond="line", cheb_degree=3, p_guess="previous", c0_precond="auto"):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
@@ -204,6 +204,8 @@ class TransportSolverF:
                 self.L.line_setup(self.line_stride)
             else:
                 self.p_method = "pcg"
+        # the transport row uses the same lines (non-symmetric tridiagonal blocks, refactored with the matrix every step)
+        self.c0_line = self.line_stride > 0 and c0_method == "bicgstab" and c0_precond != "jacobi"
         self.A = self.plan.new_matrix()
         # state
         self.u = ctx.zeros(Cn * d)
@@ -243,7 +245,10 @@ class TransportSolverF:
         kb = dict(kw)
         kb["maxit"] = min(kw["maxit"], 1000)
         try:
-            r0 = self.A.solve("bicgstab", self.rhs_c0, self.c0_new, **kb)
+            if self.c0_line:      # factors refreshed in assemble_c0_row
+                r0 = self.A.solve("bicgstab_line", self.rhs_c0, self.c0_new, line_stride=self.line_stride, **kb)
+            else:
+                r0 = self.A.solve("bicgstab", self.rhs_c0, self.c0_new, **kb)
             if r0.converged:
                 return r0
         except MpError as e:
@@ -275,6 +280,8 @@ class TransportSolverF:
         self.plan.scatter_vector(self.evec, self.rhs_c0)
         self.A.apply_dirichlet(self.rhs_c0, self.c0_isbc, self.c0_g)
         self.A.jacobi_setup()
+        if self.c0_line:
+            self.A.line_setup(self.line_stride, spd=False)
 
     def assemble_pressure_rhs(self):
         """rhs <- buoyancy load with the NEW c0 minus the prescribed boundary flux, p = 0 rows eliminated (the operator L is constant)."""

@@ -345,3 +345,44 @@ def test_mode_f_step_with_line_preconditioned_pressure(ctx):
         print("mode F periodic=%s: pressure iterations jacobi %d, line %d" % (periodic, out["jacobi"][2], out["line"][2]))
         assert rel(out["line"][0], out["jacobi"][0]) < 1e-10 and rel(out["line"][1], out["jacobi"][1]) < 1e-10
         assert out["line"][2] < out["jacobi"][2]
+
+
+def test_line_bicgstab_on_the_transport_row(ctx):
+    """mp_solve_bicgstab_line (non-symmetric tridiagonal line blocks, mp_line_setup(spd=0)) == LU on a SUPG advection-diffusion row
+    with the flow along the lines, in fewer iterations than Jacobi-BiCGStab."""
+    import ctypes as C
+    import scipy.sparse as sp
+    import scipy.sparse.linalg as spla
+    import mupopp_b200 as mp
+    from mupopp_b200._lib import check, ptr
+    from mupopp_b200.device import DeviceMesh, Plan
+    pm, om = mp.BoxMesh((0, 0, 0), (4, 4, 1), 8, 7, 12), fem.box_mesh((0, 0, 0), (4, 4, 1), 8, 7, 12)
+    stride = 9 * 8
+    dm = DeviceMesh(ctx, pm)
+    plan = Plan(ctx, dm.cells, dm.cells, dm.nvert, dm.nvert)
+    rng = np.random.default_rng(11)
+    u = np.tile(np.array([0.3, -0.2, -4.0]), (om.nc, 1)) + 0.1 * rng.standard_normal((om.nc, 3))
+    emat = ctx.empty(dm.ncell * 16)
+    A = plan.new_matrix()
+    check(ctx.lib.mp_elem_p1_adr_single(ctx.h, C.byref(dm.c), 500.0, 1.0, 0.1, ptr(ctx.to_device(u.ravel())), None, ptr(emat), None))
+    plan.scatter_matrix(emat, A)
+    isbc = (om.coords[:, 2] > 1.0 - 1e-12).astype(np.uint8)
+    bd_ = ctx.to_device(rng.standard_normal(om.nv))
+    A.apply_dirichlet(bd_, ctx.to_device(isbc), ctx.to_device(rng.random(om.nv)))
+    Ao, bo, n = A.to_scipy().tocsr(), bd_.cpu().numpy(), om.nv
+    A.line_setup(stride, spd=False)
+    lo = np.asarray(Ao[np.arange(stride, n), np.arange(0, n - stride)]).ravel()
+    up = np.asarray(Ao[np.arange(0, n - stride), np.arange(stride, n)]).ravel()
+    assert np.abs(lo - up).max() > 1e-3 * np.abs(lo).max()                       # genuinely non-symmetric blocks
+    T = sp.diags([lo, Ao.diagonal(), up], [-stride, 0, stride]).tocsc()
+    r = rng.standard_normal(n)
+    z = ctx.zeros(n)
+    A.line_apply(ctx.to_device(r), z)
+    assert rel(z.cpu().numpy(), spla.splu(T).solve(r)) < 1e-13
+    xo = spla.splu(Ao.tocsc()).solve(bo)
+    x, xj = ctx.zeros(n), ctx.zeros(n)
+    res = A.solve("bicgstab_line", bd_, x, rtol=1e-13, maxit=2000, line_stride=stride, refresh_jacobi=False)
+    resj = A.solve("bicgstab", bd_, xj, rtol=1e-13, maxit=2000)
+    print("line BiCGStab: %d iterations (point Jacobi %d), err %.2e" % (res.niter, resj.niter, rel(x.cpu().numpy(), xo)))
+    assert res.converged and rel(x.cpu().numpy(), xo) < 1e-10
+    assert res.niter < resj.niter
