@@ -75,6 +75,10 @@ int64_t mp_plan_nnz(const mp_plan *plan);
 int32_t mp_plan_max_row_nnz(const mp_plan *plan);
 int mp_plan_export_csr(mp_ctx *ctx, const mp_plan *plan, int32_t *d_rowptr, int32_t *d_colidx);
 int mp_plan_destroy(mp_plan *plan);
+/* dof -> (cell, local row) incidence lists of the plan (row r: d_inc[d_inc_ptr[r] .. d_inc_ptr[r+1]) = cell*lr + li, ascending) and the
+ * CSR slot of every (incidence, local column) pair, uint16 [ninc][lc], 0xffff = not in the pattern.  Any out pointer may be NULL. */
+int mp_plan_incidence(const mp_plan *plan, int64_t *nrow, int32_t *lr, int32_t *lc, int32_t *max_row_nnz, const int32_t **d_rowptr,
+                      const int32_t **d_inc_ptr, const int32_t **d_inc, const uint16_t **d_slot);
 /* SELL-32 layout of the plan's pattern (library-owned device arrays): number of slices, padded entries, pointers */
 int mp_plan_sell_info(const mp_plan *plan, int64_t *nslice, int64_t *nentries, const int32_t **d_sliceptr, const int32_t **d_col);
 /* compressed column indices of the SELL-32 layout (slice-uniform offsets, see mp_csr): number of (slice, j) positions that needed explicit
@@ -126,6 +130,19 @@ int mp_elem_p1_reaction_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport
 int mp_elem_p1_transport(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_ucell,
                          const double *d_c0n, const double *d_c1n, const double *d_c2n, const double *d_c1new,
                          const double *d_c2new, const double *d_fsrc, double *d_elem_mat, double *d_elem_vec);
+
+/* The same c0 row assembled ROW-WISE in one pass, without the element-tensor round trip through HBM: one thread per CSR row walks
+ * the row's incident cells (plan incidence lists, ascending cell id => fixed summation order), recomputes each cell's contribution to
+ * its row and writes the CSR values, the SELL mirror (d_sell_vals, may be NULL), the right-hand side with the symmetric Dirichlet
+ * elimination (d_isbc / d_g over all local dofs; what assemble_system does in modules/mupopp.py:289-303), the Jacobi diagonal d_dinv
+ * (may be NULL) and -- when line_stride > 0 -- the bands of the line preconditioner (d_lo, d_diag, d_up: inputs of mp_line_factor).
+ * P1 plans only (lr == lc == dim + 1). */
+int mp_assemble_p1_transport_rows(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const mp_plan *plan,
+                                  const double *d_ucell, const double *d_c0n, const double *d_c1n, const double *d_c2n,
+                                  const double *d_c1new, const double *d_c2new, const double *d_fsrc, const uint8_t *d_isbc,
+                                  const double *d_g, double *d_vals, double *d_sell_vals, double *d_rhs, double *d_dinv,
+                                  int64_t line_stride, double *d_lo, double *d_diag, double *d_up);
+
 /* single-component form DarcyAdvection.advection_diffusion (mupopp.py:627-664), DG0 velocity variant */
 int mp_elem_p1_adr_single(mp_ctx *ctx, const mp_mesh *mesh, double Pe, double Da, double dt, const double *d_ucell,
                           const double *d_cn, double *d_elem_mat, double *d_elem_vec);
@@ -281,6 +298,8 @@ int mp_solve_pcg_chebyshev(mp_ctx *ctx, const mp_csr *A, const double *d_dinv, c
  * updates, mp_solve_bicgstab_line runs right-preconditioned BiCGStab with the forward sweeps fused into the p / s updates.
  * A->nrow must be a multiple of stride. */
 int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, int spd, double *d_lo, double *d_invw, double *d_mb);
+/* factor from bands already extracted (d_invw holds the diagonal, d_mb the (i, i + stride) entries on entry) */
+int mp_line_factor(mp_ctx *ctx, int64_t nrow, int64_t stride, int spd, const double *d_lo, double *d_invw, double *d_mb);
 int mp_line_apply(mp_ctx *ctx, int64_t nrow, int64_t stride, const double *d_lo, const double *d_invw, const double *d_mb,
                   const double *d_r, double *d_z, double *d_work);
 int mp_solve_pcg_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, const double *d_lo, const double *d_invw, const double *d_mb,

@@ -131,6 +131,11 @@ SIGNATURES = {
     "mp_solve_pcg": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_spectral_bound": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, C.POINTER(C.c_double)]),
     "mp_solve_pcg_chebyshev": (C.c_int, [_VP, C.POINTER(MpCsr), _VP, _VP, _VP, _VP, C.c_int, C.c_double, C.c_double, C.POINTER(MpSolveInfo)]),
+    "mp_plan_incidence": (C.c_int, [_VP, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                    C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP), C.POINTER(_VP)]),
+    "mp_assemble_p1_transport_rows": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP] + [_VP] * 7 + [_VP, _VP]
+                                      + [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
+    "mp_line_factor": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int, _VP, _VP, _VP]),
     "mp_line_setup": (C.c_int, [_VP, C.POINTER(MpCsr), C.c_int64, C.c_int, _VP, _VP, _VP]),
     "mp_solve_bicgstab_line": (C.c_int, [_VP, C.POINTER(MpCsr), C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_line_apply": (C.c_int, [_VP, C.c_int64, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -1681,23 +1681,31 @@ int line_grid(const mp_ctx *ctx, int64_t stride) {
 }
 }  // namespace
 
-extern "C" int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, int spd, double *d_lo, double *d_invw, double *d_mb) {
-    MP_CHECK(ctx && d_lo && d_invw && d_mb, "mp_line_setup: null argument");
-    MP_TRY(check_csr(A));
-    MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_line_setup: the row count must be a positive multiple of the line stride");
-    const int64_t n = A->nrow, nplanes = n / stride;
+extern "C" int mp_line_factor(mp_ctx *ctx, int64_t nrow, int64_t stride, int spd, const double *d_lo, double *d_invw, double *d_mb) {
+    MP_CHECK(ctx && d_lo && d_invw && d_mb, "mp_line_factor: null argument");
+    MP_CHECK(stride > 0 && nrow > 0 && nrow % stride == 0, "mp_line_factor: the row count must be a positive multiple of the line stride");
     int *d_bad = reinterpret_cast<int *>(ctx->d_scalars + S_COUNT + mp::kLocalOff);   // scratch slot (as mp_spectral_bound)
     MP_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), ctx->stream));
-    k_line_extract<<<(unsigned)cdiv(n, kThreads), kThreads, 0, ctx->stream>>>(n, stride, A->d_rowptr, A->d_colidx, A->d_vals, d_lo, d_invw, d_mb);
-    k_line_factor<<<line_grid(ctx, stride), kLineThreads, 0, ctx->stream>>>(stride, nplanes, d_lo, d_invw, d_mb, spd, d_bad);
-    mp::count_launch(ctx, 2);
+    k_line_factor<<<line_grid(ctx, stride), kLineThreads, 0, ctx->stream>>>(stride, nrow / stride, d_lo, d_invw, d_mb, spd, d_bad);
+    mp::count_launch(ctx);
     MP_CUDA(cudaGetLastError());
     int bad = 0;
     MP_CUDA(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     MP_CUDA(cudaStreamSynchronize(ctx->stream));
-    MP_CHECK(!bad, spd ? "mp_line_setup: a line block is not positive definite (the operator must be SPD)"
-                       : "mp_line_setup: zero pivot in a line block");
+    MP_CHECK(!bad, spd ? "mp_line_factor: a line block is not positive definite (the operator must be SPD)"
+                       : "mp_line_factor: zero pivot in a line block");
     return 0;
+}
+
+extern "C" int mp_line_setup(mp_ctx *ctx, const mp_csr *A, int64_t stride, int spd, double *d_lo, double *d_invw, double *d_mb) {
+    MP_CHECK(ctx && d_lo && d_invw && d_mb, "mp_line_setup: null argument");
+    MP_TRY(check_csr(A));
+    MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_line_setup: the row count must be a positive multiple of the line stride");
+    const int64_t n = A->nrow;
+    k_line_extract<<<(unsigned)cdiv(n, kThreads), kThreads, 0, ctx->stream>>>(n, stride, A->d_rowptr, A->d_colidx, A->d_vals, d_lo, d_invw, d_mb);
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
+    return mp_line_factor(ctx, n, stride, spd, d_lo, d_invw, d_mb);
 }
 
 /* z = M^-1 r for the factors of mp_line_setup (tests, other drivers); d_work: nrow doubles */

@@ -611,6 +611,20 @@ extern "C" int mp_plan_row_positions(const mp_plan *p, const int32_t **d_pos) {
     return 0;
 }
 
+extern "C" int mp_plan_incidence(const mp_plan *p, int64_t *nrow, int32_t *lr, int32_t *lc, int32_t *max_row_nnz, const int32_t **d_rowptr,
+                                 const int32_t **d_inc_ptr, const int32_t **d_inc, const uint16_t **d_slot) {
+    MP_CHECK(p && p->d_inc_ptr && p->d_inc, "mp_plan_incidence: bad argument");
+    if (nrow) *nrow = p->nrow;
+    if (lr) *lr = p->lr;
+    if (lc) *lc = p->lc;
+    if (max_row_nnz) *max_row_nnz = p->max_row_nnz;
+    if (d_rowptr) *d_rowptr = p->d_rowptr;
+    if (d_inc_ptr) *d_inc_ptr = p->d_inc_ptr;
+    if (d_inc) *d_inc = p->d_inc;
+    if (d_slot) *d_slot = p->d_slot;
+    return 0;
+}
+
 extern "C" int mp_plan_sell_info(const mp_plan *p, int64_t *nslice, int64_t *nentries, const int32_t **d_sliceptr, const int32_t **d_col) {
     MP_CHECK(p && p->lc > 0 && p->d_sell_ptr, "mp_plan_sell_info: plan has no matrix pattern");
     if (nslice) *nslice = p->nslice;

@@ -150,7 +150,7 @@ class TransportSolverF:
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
                  rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
-                 vert2dof=None, row_ordered=True, p_precond="line", cheb_degree=3, p_guess="previous", c0_precond="auto"):
+                 vert2dof=None, row_ordered=True, p_precond="line", cheb_degree=3, p_guess="previous", c0_precond="auto", fused_rows=False):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
@@ -158,6 +158,7 @@ class TransportSolverF:
         # 200^3, 3-4x fewer reduction points per SpMV -- meant for multi-GPU runs; not yet the default there)
         self.p_method = {"chebyshev": "pcg_chebyshev", "line": "pcg_line"}.get(p_precond, "pcg")
         self.cheb_degree = cheb_degree
+        self.fused_rows = bool(fused_rows)
         self.p_guess = p_guess          # "extrapolate" (2 p^n - p^(n-1)) or "previous" (p^n) as the pressure PCG's initial iterate
         self._p_hist = 0                # pressure solutions of the current time series held in (p, p_old)
         self.halo = halo
@@ -270,9 +271,31 @@ class TransportSolverF:
             self.plan.scatter_vector(self.evec2, self.rhs2)
 
     def assemble_c0_row(self):
-        """A, rhs <- Crank-Nicolson + SUPG row with the lagged velocity u^n and the NEW c1 (, c2); Dirichlet rows eliminated."""
+        """A, rhs <- Crank-Nicolson + SUPG row with the lagged velocity u^n and the NEW c1 (, c2); Dirichlet rows eliminated.
+        `fused_rows=True` uses the fused row-wise kernel (mp_assemble_p1_transport_rows: CSR + SELL values, rhs, Dirichlet, Jacobi diagonal
+        and the line-preconditioner bands in one pass, no element tensor: 8 GB of DRAM traffic instead of 18 GB at 200^3).  It is NOT the
+        default: measured 10.5 ms against 10.2 ms for the element-kernel + scatter pipeline -- recomputing every cell once per incident
+        row makes it issue/latency bound (4.5 G warp instructions, 24 % occupancy at 124 registers; profiles/r2_ncu_line_and_rows.md)."""
         ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
         three = self.model.ncomp == 3
+        if self.fused_rows:
+            A = self.A
+            if A.dinv is None:
+                A.dinv = ctx.empty(A.nrow)
+            line = getattr(A, "_line", None)
+            if self.c0_line and line is None:
+                line = (self.line_stride,) + tuple(ctx.empty(A.nrow) for _ in range(3))
+            st, lo, invw, mb = line if self.c0_line else (0, None, None, None)
+            check(lib.mp_assemble_p1_transport_rows(ctx.h, C.byref(m), C.byref(prm), self.plan.h, ptr(self.u), ptr(self.c0), ptr(self.c1),
+                                                    ptr(self.c2) if three else None, ptr(self.c1_new), ptr(self.c2_new) if three else None,
+                                                    ptr(self.fsrc), ptr(self.c0_isbc), ptr(self.c0_g), ptr(A.vals),
+                                                    ptr(A.sell_vals) if A.sell_vals is not None else None, ptr(self.rhs_c0), ptr(A.dinv),
+                                                    int(st), ptr(lo), ptr(invw), ptr(mb)), "mp_assemble_p1_transport_rows")
+            A.sell_dirty = A.sell_vals is None
+            if self.c0_line:
+                check(lib.mp_line_factor(ctx.h, A.nrow, int(st), 0, ptr(lo), ptr(invw), ptr(mb)), "mp_line_factor")
+                A._line = (st, lo, invw, mb)
+            return
         check(lib.mp_elem_p1_transport(ctx.h, C.byref(m), C.byref(prm), ptr(self.u), ptr(self.c0), ptr(self.c1),
                                        ptr(self.c2) if three else None, ptr(self.c1_new), ptr(self.c2_new) if three else None,
                                        ptr(self.fsrc), ptr(self.emat), ptr(self.evec)), "mp_elem_p1_transport")
