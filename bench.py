@@ -354,6 +354,7 @@ def run_b200(args):
     nroof = min(args.steps, 3)
     ctx.timing(True, 40000)
     ctx.timing_read()
+    s.phase_timing(True)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -364,6 +365,12 @@ def run_b200(args):
     n_spmv, spmv_ms = ctx.timing_read()
     ctx.timing(False)
     ms_roof = ev0.elapsed_time(ev1)
+    phases = {k: v / nroof for k, v in s.phase_times().items()}
+    s.phase_timing(False)
+    if nranks > 1:                                      # max over ranks, phase by phase
+        pt = torch.tensor([phases[k] for k in sorted(phases)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        phases = dict(zip(sorted(phases), pt.tolist()))
 
     if rank == 0:
         peak, peak_src = measured_peak()
@@ -407,7 +414,9 @@ def run_b200(args):
                             "launches_timed": n_spmv, "avg_launch_ms": avg_ms,
                             "timed_in": "separate pass of %d steps from the same saved state (%.1f ms/step with per-launch events)"
                                         % (nroof, ms_roof / nroof),
-                            "share_of_step": spmv_ms / ms_roof}}
+                            "share_of_step": spmv_ms / ms_roof},
+               "phase_ms_per_step": dict(phases, measured_in="the same untimed pass as the roofline (CUDA events at the phase boundaries of "
+                                                              "TransportSolverF.step, max over ranks)")}
         if nranks > 1:
             out["transport"] = "peer memory (CUDA IPC over NVLink): in-kernel allreduce + halo push fused into SpMV" if ctx.peer_enabled() \
                 else "NCCL (ncclSend/ncclRecv halo + ncclAllReduce per inner product)"
@@ -524,7 +533,7 @@ def main():
     ap.add_argument("--workload", default="ccs200", choices=["ccs200", "darcy128", "compaction", "stokes"],
                     help="ccs200 = the contract line (BASELINE configs[2]); the others are the secondary lines of bench_workloads.py")
     ap.add_argument("--size", dest="n", type=int, default=200, help="hexes per direction (200 -> 8 120 601 dofs/field, the metric's size)")
-    ap.add_argument("--ref-n", type=int, default=28, help="sample size of the CPU oracle leg")
+    ap.add_argument("--ref-n", type=int, default=40, help="sample size of the CPU oracle leg")
     ap.add_argument("--transport", default="peer", choices=["peer", "nccl"],
                     help="N > 1: peer-memory windows over NVLink (in-kernel allreduce, halo push fused into SpMV) or plain NCCL")
     ap.add_argument("--pcg-variant", type=int, default=-1, help="-1 auto (single-reduction CG on N > 1 GPUs, classic on one), 0 classic, 1 single-reduction")

@@ -320,8 +320,30 @@ class TransportSolverF:
         check(lib.mp_recover_velocity(ctx.h, C.byref(m), C.byref(prm), ptr(self.K_dev), ptr(self.p), ptr(self.c0_new), ptr(self.u)),
               "mp_recover_velocity")
 
+    def phase_timing(self, on=True):
+        """Record a CUDA event at every phase boundary of step() (on torch's current stream == the context's stream); phase_times()
+        returns the accumulated milliseconds per phase.  Used by bench.py's untimed third pass, never inside a timed region."""
+        self._pt = [] if on else None
+
+    def phase_times(self):
+        names = ("c1_c2_rows_and_solves", "c0_assembly", "c0_solve", "p_rhs", "p_solve", "velocity_recovery")
+        out = dict.fromkeys(names, 0.0)
+        torch.cuda.synchronize()
+        for ev in self._pt or []:
+            for k, nm in enumerate(names):
+                out[nm] += ev[k].elapsed_time(ev[k + 1])
+        return out
+
+    def _mark(self, ev):
+        if ev is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append(e)
+
     def step(self):
         three = self.model.ncomp == 3
+        ev = [] if getattr(self, "_pt", None) is not None else None
+        self._mark(ev)
         kw = dict(rtol=self.rtol, maxit=self.maxit, halo=self.halo, check_every=self.check_every, refresh_jacobi=False)
         # 1. c1 (, c2): consistent-mass solves with the reaction load
         self.assemble_reaction_rows()
@@ -334,13 +356,17 @@ class TransportSolverF:
             r2 = self.M.solve("pcg", self.rhs2, self.c2_new, **kw)
             self._exchange(self.c2_new)
         # 2. c0: CN + SUPG with the lagged velocity u^n
+        self._mark(ev)
         self.assemble_c0_row()
+        self._mark(ev)
         self.c0_new.copy_(self.c0)
         r0 = self._solve_c0(kw)
         self._exchange(self.c0_new)
+        self._mark(ev)
         # 3. pressure with the NEW c0.  Initial guess: p^n, or the linear extrapolation 2 p^n - p^(n-1) once two solutions of THIS
         #    time series exist (fewer PCG iterations for the same answer: the tolerance is relative to ||b||, not to the guess)
         self.assemble_pressure_rhs()
+        self._mark(ev)
         if self.p_guess == "extrapolate" and self._p_hist >= 2:
             self.p_old.mul_(-1.0).add_(self.p, alpha=2.0)            # p_old <- 2 p^n - p^(n-1): becomes the iterate
             self.p, self.p_old = self.p_old, self.p
@@ -349,8 +375,12 @@ class TransportSolverF:
         rp = self.L.solve(self.p_method, self.rhs, self.p, cheb_degree=self.cheb_degree, line_stride=self.line_stride, **kw)
         self._p_hist += 1
         self._exchange(self.p)
+        self._mark(ev)
         # 4. velocity recovery, then rotate the state
         self.recover_velocity()
+        self._mark(ev)
+        if ev is not None:
+            self._pt.append(ev)
         self.c0, self.c0_new = self.c0_new, self.c0
         self.c1, self.c1_new = self.c1_new, self.c1
         if three:
