@@ -351,7 +351,7 @@ def run_b200(args):
     # ---- pass 3 (untimed for the metric): the dominant kernel's launches timed one by one with CUDA events on the launch stream,
     #      over the first steps of the same window (roofline.achieved); kept out of regions 1 and 2 so that neither is perturbed.
     restore()
-    nroof = min(args.steps, 3)
+    nroof = min(args.steps, args.roof_steps)
     ctx.timing(True, 40000)
     ctx.timing_read()
     s.phase_timing(True)
@@ -549,6 +549,7 @@ def main():
                     help="pressure PCG preconditioner: point Jacobi, Chebyshev-Jacobi polynomial, or lattice-line block Jacobi (tridiagonal z-lines)")
     ap.add_argument("--c0-precond", default="auto", choices=["auto", "jacobi"], help="transport-row BiCGStab preconditioner: auto = the pressure's lattice lines when --p-precond line, else Jacobi")
     ap.add_argument("--cheb-degree", type=int, default=3)
+    ap.add_argument("--roof-steps", type=int, default=3, help="steps of the untimed third pass (per-launch SpMV events, phase breakdown)")
     ap.add_argument("--skip-cpu", dest="no_cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--skip-api", dest="no_api", action="store_true", help="e2e through TransportSolverF.step instead of the mupopp/fenics plugin call")
     ap.add_argument("--sides", default="periodic", choices=["natural", "noflow", "periodic"],
