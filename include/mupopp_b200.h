@@ -162,9 +162,14 @@ int mp_elem_p1_cell_load(mp_ctx *ctx, const mp_mesh *mesh, const double *d_ucell
  *   kind 2 GRADT (as GRAD with row derivative x column value)   kind 3 STIFF (dim^2 tensors, geo_ab = |detJ| (Jinv Jinv^T)_ab)
  *   kind 4 SYMGRAD: block (a,b) = (dir/dim, dir%dim) of 2 symgrad(u):symgrad(v) with the STIFF tensors (compaction, mupopp.py:361)
  * coef_kind 0 none | 1 nodal P1 d_coef[nvert], integrated exactly (T0 then has (dim+1) sub-tensors per t) | 2 cellwise d_coef[ncell].
- * T0 comes from mupopp_b200/reference_element.py.  Mode R operators: P2 mass u.v, K div(v) p, div(u) q (mupopp.py:620,804-807,1201-1204). */
+ * T0 comes from mupopp_b200/reference_element.py and is staged in shared memory once per CTA; a CTA then produces tiles of 64 cells with
+ * coalesced stores.  Mode R operators: P2 mass u.v, K div(v) p, div(u) q (mupopp.py:620,804-807,1201-1204). */
 int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
                       const double *d_coef, int coef_kind, double scale, double *d_elem_mat);
+/* the same with ROW-ORDERED output for mp_scatter_matrix_ordered: local row i of cell c is stored at d_elem_mat[d_row_pos[c*lr + i] * lc ...]
+ * (d_row_pos from mp_plan_row_positions of the block's plan; rows the plan does not assemble are skipped) */
+int mp_elem_reftensor_rows(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
+                           const double *d_coef, int coef_kind, double scale, const int32_t *d_row_pos, double *d_elem_mat);
 
 /* quadrature tables (device): weights [nq] (sum = 1/dim!), barycentric coordinates [nq][dim+1], velocity basis values [nq][nbv] */
 typedef struct {

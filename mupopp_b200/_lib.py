@@ -109,6 +109,7 @@ SIGNATURES = {
     "mp_recover_velocity": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, _VP, _VP]),
     "mp_elem_p1_cell_load": (C.c_int, [_VP, C.POINTER(MpMesh), _VP, C.c_int, _VP]),
     "mp_elem_reftensor": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int, C.c_double, _VP]),
+    "mp_elem_reftensor_rows": (C.c_int, [_VP, C.POINTER(MpMesh), C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP, C.c_int, C.c_double, _VP, _VP]),
     "mp_elem_p1_transport_quad": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), C.POINTER(MpQuad), _VP, _VP, _VP, _VP,
                                             _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "mp_cell_fn": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpQuad), C.c_int, C.c_double, _VP, _VP]),

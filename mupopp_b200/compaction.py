@@ -92,19 +92,14 @@ class CompactionMomentumR:
         ctx.axpby(-1.0, phi, 1.0, self.omp)                                   # 1 - phi (nodal: exact P1 coefficient)
         for a in range(d):
             for b in range(d):
-                check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 4, a * d + b, nb2, nb2, ptr(self.T_stiff22), ptr(self.omp), 1, 0.25, ptr(self.emat2)),
-                      "mp_elem_reftensor(symgrad)")
-                self.p22.scatter_matrix(self.emat2, self.Auu[a][b])
+                self.p22.reftensor_scatter(sp.dm, 4, a * d + b, nb2, nb2, self.T_stiff22, self.omp, 1, 0.25, self.emat2, self.Auu[a][b])
         # preconditioner viscous block (1-phi) grad u:grad v
-        check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 3, 0, nb2, nb2, ptr(self.T_stiff22), ptr(self.omp), 1, 1.0, ptr(self.emat2)), "mp_elem_reftensor(stiff)")
-        self.p22.scatter_matrix(self.emat2, self.Puu)
+        self.p22.reftensor_scatter(sp.dm, 3, 0, nb2, nb2, self.T_stiff22, self.omp, 1, 1.0, self.emat2, self.Puu)
         # (q,p): dL phi phi^(1/phi^3) grad p.grad q ;  P: dL/phi grad p.grad q + p q
         check(lib.mp_cell_fn(ctx.h, C.byref(m), C.byref(self.quad), 0, self.dL, ptr(phi), ptr(self.ccoef)), "mp_cell_fn")
-        check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 3, 0, nb1, nb1, ptr(self.T_stiff11), ptr(self.ccoef), 2, 1.0, ptr(self.emat1)), "mp_elem_reftensor(App)")
-        self.p11.scatter_matrix(self.emat1, self.App)
+        self.p11.reftensor_scatter(sp.dm, 3, 0, nb1, nb1, self.T_stiff11, self.ccoef, 2, 1.0, self.emat1, self.App)
         check(lib.mp_cell_fn(ctx.h, C.byref(m), C.byref(self.quad), 1, self.dL, ptr(phi), ptr(self.ccoef)), "mp_cell_fn")
-        check(lib.mp_elem_reftensor(ctx.h, C.byref(m), 3, 0, nb1, nb1, ptr(self.T_stiff11), ptr(self.ccoef), 2, 1.0, ptr(self.emat1)), "mp_elem_reftensor(Ppp)")
-        self.p11.scatter_matrix(self.emat1, self.Ppp)
+        self.p11.reftensor_scatter(sp.dm, 3, 0, nb1, nb1, self.T_stiff11, self.ccoef, 2, 1.0, self.emat1, self.Ppp)
         ctx.axpby(1.0, self.M1.vals, 1.0, self.Ppp.vals)
         # (omega,c): -eta c omega ; P: 0.5 eta c omega
         check(lib.mp_elem_p1_mass_fn(ctx.h, C.byref(m), C.byref(self.quad), 2, self.dL, -1.0, ptr(phi), ptr(self.emat1)), "mp_elem_p1_mass_fn")

@@ -525,26 +525,29 @@ __global__ void __launch_bounds__(kThreads) k_recover_velocity(mp_mesh m, mp_tra
 // A_e[i][j] = scale * sum_t geo_t(cell) * T0[t][i][j]   (FFC's tensor representation): P2 mass, P1xP2 divergence/gradient blocks,
 // stiffness, with an optional exact nodal-P1 or cellwise coefficient.  Used for the mixed (mode R) operators of
 // DarcyAdvection.darcy_bilinear (mupopp.py:620: u.v, K div(v) p, div(u) q) and the Darcy rows of the monolithic forms (:807, :1204).
+// Reference-tensor element kernel (FFC's "tensor representation"): A_e[i][j] = f_c * sum_k W_c[k] * T0[k][i][j], W_c = geometry factors
+// of the cell (x nodal coefficient values when the coefficient is a P1 field).  A CTA stages T0 ONCE in shared memory (north_star (1):
+// "shared-memory staging of the reference element"), then works through tiles of kRefTile cells: one thread per cell computes the
+// geometry factors into shared memory, after which all threads produce the tile's kRefTile x L entries with consecutive threads on
+// consecutive entries -- conflict-free shared-memory reads of T0 and fully coalesced 8-byte stores (the old thread-per-cell kernel
+// re-read T0 from global memory for every entry and wrote L x 8-byte strided stores per warp instruction).
+// `pos` != NULL: row-ordered output for the streaming scatter, local row i of cell c goes to emat[pos[c*lr + i] * lc ...].
+constexpr int kRefTile = 64;
+constexpr int kRefThreads = 256;   // 16 cell groups of 4 cells x 16 entry lanes: the register tiling below needs exactly this block size
+constexpr int kRefMaxK = 9 * 4;     // nT <= D*D = 9 geometry terms, times (D+1) nodal coefficient values
+
 template <int D>
-__global__ void __launch_bounds__(kThreads) k_reftensor(mp_mesh m, int kind, int dir, int L, const double *__restrict__ T0,
-                                                        const double *__restrict__ coef, int coef_kind, double scale,
-                                                        double *__restrict__ emat) {
-    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (c >= m.ncell) return;
-    Geom<D> G;
-    load_geom<D>(m, c, G);
+__device__ __forceinline__ int reftensor_geo(const Geom<D> &G, int kind, int dir, double (&geo)[D * D]) {
     double detJ = G.vol;
 #pragma unroll
     for (int k = 2; k <= D; ++k) detJ *= k;
-    double geo[D * D];
-    int nT;
-    if (kind == 0) { nT = 1; geo[0] = detJ; }
-    else if (kind == 1 || kind == 2) {
-        nT = D;
+    if (kind == 0) { geo[0] = detJ; return 1; }
+    if (kind == 1 || kind == 2) {
 #pragma unroll
         for (int a = 0; a < D; ++a) geo[a] = detJ * G.g[a + 1][dir];
-    } else if (kind == 3) {
-        nT = D * D;
+        return D;
+    }
+    if (kind == 3) {
 #pragma unroll
         for (int a = 0; a < D; ++a)
 #pragma unroll
@@ -554,44 +557,104 @@ __global__ void __launch_bounds__(kThreads) k_reftensor(mp_mesh m, int kind, int
                 for (int i = 0; i < D; ++i) t += G.g[a + 1][i] * G.g[b + 1][i];
                 geo[a * D + b] = detJ * t;
             }
-    } else {
-        // kind 4, SYMGRAD block (ca, cb) = (dir / D, dir % D) of  2 symgrad(u):symgrad(v) = delta_ab grad psi_i.grad psi_j + d_b psi_i d_a psi_j
-        // (compaction.momentum_conservation, mupopp.py:361), contracted with the STIFF reference tensors
-        nT = D * D;
-        const int ca = dir / D, cb = dir % D;
-#pragma unroll
-        for (int a = 0; a < D; ++a)
-#pragma unroll
-            for (int b = 0; b < D; ++b) {
-                double t = G.g[a + 1][cb] * G.g[b + 1][ca];
-                if (ca == cb) {
-#pragma unroll
-                    for (int i = 0; i < D; ++i) t += G.g[a + 1][i] * G.g[b + 1][i];
-                }
-                geo[a * D + b] = detJ * t;
-            }
+        return D * D;
     }
-    double *dst = emat + c * (int64_t)L;
-    if (coef_kind == 1) {
-        double Kv[D + 1];
+    // kind 4, SYMGRAD block (ca, cb) = (dir / D, dir % D) of  2 symgrad(u):symgrad(v) = delta_ab grad psi_i.grad psi_j + d_b psi_i d_a psi_j
+    // (compaction.momentum_conservation, mupopp.py:361), contracted with the STIFF reference tensors
+    const int ca = dir / D, cb = dir % D;
 #pragma unroll
-        for (int v = 0; v <= D; ++v) Kv[v] = coef[G.dof[v]];
-        for (int e = 0; e < L; ++e) {
-            double sum = 0.0;
-            for (int t = 0; t < nT; ++t) {
-                double inner = 0.0;
+    for (int a = 0; a < D; ++a)
 #pragma unroll
-                for (int v = 0; v <= D; ++v) inner += Kv[v] * T0[((int64_t)t * (D + 1) + v) * L + e];
-                sum += geo[t] * inner;
+        for (int b = 0; b < D; ++b) {
+            double t = G.g[a + 1][cb] * G.g[b + 1][ca];
+            if (ca == cb) {
+#pragma unroll
+                for (int i = 0; i < D; ++i) t += G.g[a + 1][i] * G.g[b + 1][i];
             }
-            dst[e] = scale * sum;
+            geo[a * D + b] = detJ * t;
         }
-    } else {
-        const double f = coef_kind == 2 ? scale * coef[c] : scale;
-        for (int e = 0; e < L; ++e) {
-            double sum = 0.0;
-            for (int t = 0; t < nT; ++t) sum += geo[t] * T0[(int64_t)t * L + e];
-            dst[e] = f * sum;
+    return D * D;
+}
+
+template <int D>
+__global__ void __launch_bounds__(kRefThreads) k_reftensor(mp_mesh m, int kind, int dir, int L, int lc, int NK, const double *__restrict__ T0,
+                                                        const double *__restrict__ coef, int coef_kind, double scale,
+                                                        const int32_t *__restrict__ pos, double *__restrict__ emat) {
+    extern __shared__ double sm_ref[];
+    double *T0s = sm_ref;                               // [NK][L]; for coef_kind 1 the global layout is already [t][v][e] = [k][e]
+    double *W = sm_ref + (((size_t)NK * L + 1) & ~(size_t)1);   // [NK + 1][kRefTile]: weights k of every cell of the tile, then the cell factor (16-byte aligned)
+    for (int k = threadIdx.x; k < NK * L; k += blockDim.x) T0s[k] = T0[k];
+    const int64_t ntile = (m.ncell + kRefTile - 1) / kRefTile;
+    // register tile: thread (cg, el) owns cells 4 cg .. 4 cg + 3 of the tile and entries el, el + 16, el + 32, ...: per k it reads 4 entries
+    // of T0 (consecutive lanes -> consecutive addresses) and its 4 cell weights (two 16-byte loads) for 16 FMAs -- 0.4 shared-memory
+    // loads per FMA instead of 2 for one output per thread, which left the kernel shared-memory bound with a P1 coefficient (NK = 36)
+    const int cg = threadIdx.x >> 4, el = threadIdx.x & 15;
+    for (int64_t tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+        const int64_t c0 = tile * kRefTile;
+        const int nc = (int)min((int64_t)kRefTile, m.ncell - c0);
+        __syncthreads();                                // T0s ready / the previous tile's W consumed
+        if ((int)threadIdx.x < kRefTile) {
+            const int cl = threadIdx.x;
+            if (cl < nc) {
+                const int64_t c = c0 + cl;
+                Geom<D> G;
+                load_geom<D>(m, c, G);
+                double geo[D * D];
+                const int nT = reftensor_geo<D>(G, kind, dir, geo);
+                if (coef_kind == 1) {
+                    for (int t = 0; t < nT; ++t)
+#pragma unroll
+                        for (int v = 0; v <= D; ++v) W[(t * (D + 1) + v) * kRefTile + cl] = geo[t] * coef[G.dof[v]];
+                    W[NK * kRefTile + cl] = scale;
+                } else {
+                    for (int t = 0; t < nT; ++t) W[t * kRefTile + cl] = geo[t];
+                    W[NK * kRefTile + cl] = coef_kind == 2 ? scale * coef[c] : scale;
+                }
+            } else {
+                for (int k = 0; k <= NK; ++k) W[k * kRefTile + cl] = 0.0;
+            }
+        }
+        __syncthreads();
+        for (int eb = 0; eb < L; eb += 64) {
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+            int ee[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { ee[j] = eb + el + 16 * j; if (ee[j] >= L) ee[j] = L - 1; }     // clamped loads, masked stores
+            for (int k = 0; k < NK; ++k) {
+                const double2 w01 = *reinterpret_cast<const double2 *>(W + k * kRefTile + 4 * cg);
+                const double2 w23 = *reinterpret_cast<const double2 *>(W + k * kRefTile + 4 * cg + 2);
+                const double w[4] = {w01.x, w01.y, w23.x, w23.y};
+                double t[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) t[j] = T0s[k * L + ee[j]];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] += w[i] * t[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int cl = 4 * cg + i;
+                if (cl >= nc) continue;
+                const double f = W[NK * kRefTile + cl];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int e = eb + el + 16 * j;
+                    if (e >= L) continue;
+                    const double val = f * acc[i][j];
+                    if (pos) {
+                        const int ri = e / lc, cj = e - ri * lc;
+                        const int32_t q = pos[(c0 + cl) * (int64_t)(L / lc) + ri];
+                        if (q >= 0) emat[(int64_t)q * lc + cj] = val;
+                    } else {
+                        emat[(c0 + cl) * (int64_t)L + e] = val;
+                    }
+                }
+            }
         }
     }
 }
@@ -1382,14 +1445,43 @@ extern "C" int mp_apply_dirichlet_sym(mp_ctx *ctx, int64_t nrow, const int32_t *
     return 0;
 }
 
-extern "C" int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
-                                 const double *d_coef, int coef_kind, double scale, double *d_elem_mat) {
+static int reftensor_impl(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0, const double *d_coef,
+                          int coef_kind, double scale, const int32_t *d_row_pos, double *d_elem_mat) {
     MP_TRY(check_mesh(ctx, mesh));
     MP_CHECK(kind >= 0 && kind <= 4 && dir >= 0 && dir < (kind == 4 ? mesh->dim * mesh->dim : mesh->dim) && lr > 0 && lc > 0 && d_T0 && d_elem_mat,
              "mp_elem_reftensor: bad argument");
     MP_CHECK(coef_kind == 0 || d_coef, "mp_elem_reftensor: coefficient pointer is null");
-    DISPATCH_DIM(mesh, k_reftensor, kind, dir, lr * lc, d_T0, d_coef, coef_kind, scale, d_elem_mat);
+    if (mesh->ncell == 0) return 0;
+    const int D = mesh->dim, L = lr * lc;
+    const int nT = kind == 0 ? 1 : (kind <= 2 ? D : D * D);
+    const int NK = coef_kind == 1 ? nT * (D + 1) : nT;
+    const size_t smem = sizeof(double) * ((size_t)NK * L + (size_t)kRefTile * (NK + 1) + 2);
+    MP_CHECK(smem <= 220 * 1024, "mp_elem_reftensor: a %d x %d block with %d reference tensors does not fit in shared memory", lr, lc, NK);
+    const int64_t ntile = cdiv(mesh->ncell, kRefTile);
+    const int per_sm = smem > 100 * 1024 ? 1 : (smem > 48 * 1024 ? 2 : 4);
+    int64_t grid = (int64_t)ctx->num_sm * per_sm;       // persistent CTAs: T0 is staged once per CTA, not once per tile
+    if (grid > ntile) grid = ntile;
+    if (D == 2) {
+        MP_CUDA(cudaFuncSetAttribute(k_reftensor<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_reftensor<2><<<(unsigned)grid, kRefThreads, smem, ctx->stream>>>(*mesh, kind, dir, L, lc, NK, d_T0, d_coef, coef_kind, scale, d_row_pos, d_elem_mat);
+    } else {
+        MP_CUDA(cudaFuncSetAttribute(k_reftensor<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        k_reftensor<3><<<(unsigned)grid, kRefThreads, smem, ctx->stream>>>(*mesh, kind, dir, L, lc, NK, d_T0, d_coef, coef_kind, scale, d_row_pos, d_elem_mat);
+    }
+    mp::count_launch(ctx);
+    MP_CUDA(cudaGetLastError());
     return 0;
+}
+
+extern "C" int mp_elem_reftensor(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
+                                 const double *d_coef, int coef_kind, double scale, double *d_elem_mat) {
+    return reftensor_impl(ctx, mesh, kind, dir, lr, lc, d_T0, d_coef, coef_kind, scale, nullptr, d_elem_mat);
+}
+
+extern "C" int mp_elem_reftensor_rows(mp_ctx *ctx, const mp_mesh *mesh, int kind, int dir, int lr, int lc, const double *d_T0,
+                                      const double *d_coef, int coef_kind, double scale, const int32_t *d_row_pos, double *d_elem_mat) {
+    MP_CHECK(d_row_pos, "mp_elem_reftensor_rows: null row positions");
+    return reftensor_impl(ctx, mesh, kind, dir, lr, lc, d_T0, d_coef, coef_kind, scale, d_row_pos, d_elem_mat);
 }
 
 extern "C" int mp_elem_p1_transport_quad(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const mp_quad *quad,

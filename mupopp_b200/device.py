@@ -206,8 +206,22 @@ class Plan:
         return CsrMatrix(self.ctx, self.nrow, self.ncol, rowptr, colidx, self.ctx.zeros(self.nnz), self.max_row_nnz,
                          plan=self if sell else None)
 
-    def scatter_matrix(self, elem_mat, A):
-        fn = self.ctx.lib.mp_scatter_matrix_ordered if self.ordered else self.ctx.lib.mp_scatter_matrix
+    def row_positions(self):
+        """Device pointer of pos[ncell*lr]: incidence index of (cell, local row) -- where a row-ordered element kernel stores that row."""
+        pos = C.c_void_p()
+        check(self.ctx.lib.mp_plan_row_positions(self.h, C.byref(pos)), "mp_plan_row_positions")
+        return pos
+
+    def reftensor_scatter(self, dm, kind, direction, lr, lc, T0, coef, coef_kind, scale, emat, A):
+        """One reference-tensor block straight into the CSR matrix A: element kernel with row-ordered output (mp_elem_reftensor_rows)
+        followed by the streaming scatter -- the P2/P3 blocks of mode R, compaction and Stokes."""
+        check(self.ctx.lib.mp_elem_reftensor_rows(self.ctx.h, C.byref(dm.c), int(kind), int(direction), int(lr), int(lc), ptr(T0), ptr(coef),
+                                                  int(coef_kind), float(scale), self.row_positions(), ptr(emat)), "mp_elem_reftensor_rows")
+        self.scatter_matrix(emat, A, ordered=True)
+
+    def scatter_matrix(self, elem_mat, A, ordered=None):
+        ordered = self.ordered if ordered is None else ordered
+        fn = self.ctx.lib.mp_scatter_matrix_ordered if ordered else self.ctx.lib.mp_scatter_matrix
         check(fn(self.ctx.h, self.h, ptr(elem_mat), ptr(A.vals)), "mp_scatter_matrix")
         A.sell_dirty = True
 

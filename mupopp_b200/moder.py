@@ -107,10 +107,8 @@ class Spaces:
             scale = scale * float(coef)
         T0 = self.tensor(kind, deg_r, deg_c, nodal)
         emat = ctx.empty(self.dm.ncell * lr * lc)
-        check(ctx.lib.mp_elem_reftensor(ctx.h, C.byref(self.dm.c), kid, int(direction), lr, lc, ptr(T0), ptr(coef) if nodal else None,
-                                        1 if nodal else 0, float(scale), ptr(emat)), "mp_elem_reftensor")
         A = plan.new_matrix(sell=True)
-        plan.scatter_matrix(emat, A)
+        plan.reftensor_scatter(self.dm, kid, direction, lr, lc, T0, coef if nodal else None, 1 if nodal else 0, scale, emat, A)
         return A
 
 

@@ -246,7 +246,7 @@ class TransportSolverF:
         kb = dict(kw)
         kb["maxit"] = min(kw["maxit"], 1000)
         try:
-            if self.c0_line:      # factors refreshed in assemble_c0_row
+            if self.c0_line and getattr(self, "_c0_line_ok", False):      # factors refreshed in assemble_c0_row
                 r0 = self.A.solve("bicgstab_line", self.rhs_c0, self.c0_new, line_stride=self.line_stride, **kb)
             else:
                 r0 = self.A.solve("bicgstab", self.rhs_c0, self.c0_new, **kb)
@@ -292,8 +292,9 @@ class TransportSolverF:
                                                     ptr(A.sell_vals) if A.sell_vals is not None else None, ptr(self.rhs_c0), ptr(A.dinv),
                                                     int(st), ptr(lo), ptr(invw), ptr(mb)), "mp_assemble_p1_transport_rows")
             A.sell_dirty = A.sell_vals is None
+            self._c0_line_ok = False
             if self.c0_line:
-                check(lib.mp_line_factor(ctx.h, A.nrow, int(st), 0, ptr(lo), ptr(invw), ptr(mb)), "mp_line_factor")
+                self._c0_line_ok = self._try(lambda: check(lib.mp_line_factor(ctx.h, A.nrow, int(st), 0, ptr(lo), ptr(invw), ptr(mb)), "mp_line_factor"))
                 A._line = (st, lo, invw, mb)
             return
         check(lib.mp_elem_p1_transport(ctx.h, C.byref(m), C.byref(prm), ptr(self.u), ptr(self.c0), ptr(self.c1),
@@ -303,8 +304,21 @@ class TransportSolverF:
         self.plan.scatter_vector(self.evec, self.rhs_c0)
         self.A.apply_dirichlet(self.rhs_c0, self.c0_isbc, self.c0_g)
         self.A.jacobi_setup()
-        if self.c0_line:
-            self.A.line_setup(self.line_stride, spd=False)
+        self._c0_line_ok = self.c0_line and self._try(lambda: self.A.line_setup(self.line_stride, spd=False))
+
+    @staticmethod
+    def _try(fn):
+        """A line block of the transport row can have a zero pivot (no pivoting inside the tridiagonal LU): that step then uses point Jacobi.
+        The factor kernel's verdict is a device flag read back by every rank, and the blocks are rank-local, so this is NOT collective --
+        but the Jacobi and line variants issue the same exchanges per iteration, and convergence is decided on allreduced scalars."""
+        from ._lib import MpError
+        try:
+            fn()
+            return True
+        except MpError as e:
+            if "pivot" not in str(e):
+                raise
+            return False
 
     def assemble_pressure_rhs(self):
         """rhs <- buoyancy load with the NEW c0 minus the prescribed boundary flux, p = 0 rows eliminated (the operator L is constant)."""

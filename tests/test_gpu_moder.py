@@ -179,3 +179,39 @@ def test_moder_monolithic_step(ctx, dim, n, maker):
         for c in range(dim):
             assert np.linalg.norm(s.u[c].cpu().numpy() - mono.u[c]) < 1e-9 * max(np.linalg.norm(np.concatenate(mono.u)), 1e-300)
         prev = mono
+
+
+@pytest.mark.parametrize("dim,n,deg,nodal", [(3, 2, 2, True), (3, 3, 2, False), (3, 2, 1, True), (2, 9, 1, False), (2, 7, 2, True), (3, 2, 3, False)])
+def test_reftensor_tiles_against_numpy(ctx, dim, n, deg, nodal):
+    """The tiled reference-tensor kernel (T0 staged in shared memory, 64-cell tiles, 4 x 4 register tiles) == a NumPy contraction of the same
+    tensors, cell-ordered and row-ordered output, including tiles that are not full and a shared-memory layout with an odd tensor size."""
+    import ctypes as C
+    import mupopp_b200 as mp
+    from mupopp_b200._lib import check, ptr
+    from mupopp_b200.moder import Spaces
+    mesh = mp.BoxMesh((0, 0, 0), (1.0, 2.0, 3.0), n, n, 2 * n) if dim == 3 else mp.RectangleMesh((0, 0), (2.0, 1.0), n, n + 2)
+    sp = Spaces(ctx, mesh)
+    nb = sp.nb(deg)
+    L = nb * nb
+    T0 = sp.tensor("stiff", deg, deg, nodal)
+    coefh = 0.9 + 0.05 * np.random.default_rng(0).random(sp.n1)
+    coef = ctx.to_device(coefh)
+    nc = mesh.num_cells()
+    X = mesh.coords[mesh.cells]
+    J = np.transpose(X[:, 1:] - X[:, :1], (0, 2, 1))
+    Ji = np.linalg.inv(J)
+    geo = (np.einsum("cai,cbi->cab", Ji, Ji) * np.abs(np.linalg.det(J))[:, None, None]).reshape(nc, dim * dim)
+    T0h = T0.cpu().numpy()
+    if nodal:
+        W = (geo[:, :, None] * coefh[mesh.cells][:, None, :]).reshape(nc, dim * dim * (dim + 1))
+        ref = 0.5 * (W @ T0h.reshape(W.shape[1], L))
+    else:
+        ref = 0.5 * (geo @ T0h.reshape(dim * dim, L))
+    emat = ctx.zeros(nc * L)
+    check(ctx.lib.mp_elem_reftensor(ctx.h, C.byref(sp.dm.c), 3, 0, nb, nb, ptr(T0), ptr(coef) if nodal else None, 1 if nodal else 0, 0.5, ptr(emat)))
+    assert np.abs(emat.cpu().numpy().reshape(nc, L) - ref).max() <= 1e-13 * np.abs(ref).max()
+    plan = sp.plan(deg, deg)
+    A, B = plan.new_matrix(sell=False), plan.new_matrix(sell=False)
+    plan.scatter_matrix(emat, A, ordered=False)
+    plan.reftensor_scatter(sp.dm, 3, 0, nb, nb, T0, coef if nodal else None, 1 if nodal else 0, 0.5, emat, B)
+    assert np.array_equal(A.vals.cpu().numpy(), B.vals.cpu().numpy())
