@@ -1672,6 +1672,72 @@ __global__ void __launch_bounds__(kLineThreads, kLineCtasPerSm) k_line_fwd_bicg(
     }
 }
 
+// Single-reduction (Chronopoulos-Gear) PCG with the line preconditioner, for several GPUs: the vector update of k_cgcg_update fused with
+// the upward sweep (p = u + beta p ; s = w + beta s ; x += alpha p ; r -= alpha s ; f = D^-1 L^-1 r) and the rank-LOCAL sums
+// gamma' = r.M^-1 r (= y^T D^-1 y), rr = r.r left for the SpMV kernel, which folds them into its own exchange (DOT == 3): ONE exchange
+// point per iteration instead of the classic recurrence's three (halo, p.Ap, {r.z, r.r}).
+__global__ void __launch_bounds__(kLineThreads, kLineCtasPerSm) k_line_fwd_cgcg(int stride, int nplanes, int first, const double *__restrict__ w,
+                                                                                const double *__restrict__ u, double *__restrict__ p,
+                                                                                double *__restrict__ s, double *__restrict__ x, double *__restrict__ r,
+                                                                                const double *__restrict__ lo, const double *__restrict__ invw,
+                                                                                double *__restrict__ f, double *partials, mp::ReduceCtl *ctl,
+                                                                                double *scal, int cur, int nxt) {
+    if (!solver_active(scal)) return;
+    const double gamma = scal[S_G0 + cur], delta = scal[S_DELTA];
+    const double beta = first ? 0.0 : safe_div(gamma, scal[S_G0 + nxt]);
+    const double alpha = first ? safe_div(gamma, delta) : safe_div(gamma, delta - beta * safe_div(gamma, scal[S_AL0 + nxt]));
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[S_AL0 + cur] = alpha;          // nobody reads AL[cur] in this kernel
+    double acc[2] = {0.0, 0.0};
+    constexpr int U = kLineU;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < stride; l += gridDim.x * blockDim.x) {
+        double sp = 0.0;
+        double ua[U], wa[U], pa[U], sa[U], xa[U], ra[U], la[U], ia[U], ub[U], wb[U], pb[U], sb[U], xb[U], rb[U], lb[U], ib[U];
+        auto load = [&](int k0, double (&uu)[U], double (&ww)[U], double (&pp)[U], double (&ss)[U], double (&xx)[U], double (&rr)[U],
+                        double (&ll)[U], double (&ii)[U]) {
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int k = k0 + q;
+                if (k < nplanes) {
+                    const int i = k * stride + l;
+                    uu[q] = u[i]; ww[q] = w[i]; xx[q] = x[i]; rr[q] = r[i]; ll[q] = lo[i]; ii[q] = invw[i];
+                    pp[q] = first ? 0.0 : p[i];
+                    ss[q] = first ? 0.0 : s[i];
+                }
+            }
+        };
+        auto work = [&](int k0, double (&uu)[U], double (&ww)[U], double (&pp)[U], double (&ss)[U], double (&xx)[U], double (&rr)[U],
+                        double (&ll)[U], double (&ii)[U]) {
+#pragma unroll
+            for (int q = 0; q < U; ++q) {
+                const int k = k0 + q;
+                if (k < nplanes) {
+                    const int i = k * stride + l;
+                    const double pi = uu[q] + beta * pp[q], si = ww[q] + beta * ss[q];
+                    p[i] = pi;
+                    s[i] = si;
+                    x[i] = xx[q] + alpha * pi;
+                    const double ri = rr[q] - alpha * si;
+                    r[i] = ri;
+                    acc[1] += ri * ri;
+                    const double y = ri - ll[q] * sp;
+                    sp = ii[q] * y;
+                    f[i] = sp;
+                    acc[0] += y * sp;
+                }
+            }
+        };
+        load(0, ua, wa, pa, sa, xa, ra, la, ia);
+        for (int k0 = 0; k0 < nplanes; k0 += 2 * U) {
+            load(k0 + U, ub, wb, pb, sb, xb, rb, lb, ib);
+            work(k0, ua, wa, pa, sa, xa, ra, la, ia);
+            load(k0 + 2 * U, ua, wa, pa, sa, xa, ra, la, ia);
+            work(k0 + U, ub, wb, pb, sb, xb, rb, lb, ib);
+        }
+    }
+    const int sl_[2] = {S_GLOC, S_RRLOC};
+    grid_reduce<2, kLineThreads>(acc, partials, ctl, scal, sl_, false, false, /*exchange=*/false);
+}
+
 int line_grid(const mp_ctx *ctx, int64_t stride) {
     int64_t g = cdiv(stride, kLineThreads);
     int64_t cap = (int64_t)ctx->num_sm * kLineCtasPerSm;     // beyond one wave the lines are spread evenly by the grid-stride loop
@@ -1728,12 +1794,71 @@ extern "C" int mp_line_apply(mp_ctx *ctx, int64_t nrow, int64_t stride, const do
     return 0;
 }
 
+namespace {
+// Single-reduction line-PCG driver (see k_line_fwd_cgcg); same preconditions as solve_pcg_single_reduction.
+int solve_pcg_line_single_reduction(mp_ctx *ctx, const mp_csr *A, int64_t stride, const double *d_lo, const double *d_invw, const double *d_mb,
+                                    const double *d_b, double *d_x, mp_halo *halo, mp_solve_info *info) {
+    const int64_t n = A->nrow, nc = A->ncol;
+    const int st = (int)stride, nplanes = (int)(n / stride);
+    const bool use_halo = halo && halo->peer && halo->nneigh > 0 && ctx->nranks > 1;
+    if (use_halo) MP_TRY(mp::halo_classify(ctx, halo, A->nrow, A->d_sell_sliceptr, A->d_sell_col));
+    mp_halo *H = use_halo ? halo : nullptr;
+    double *wk = nullptr;
+    MP_TRY(mp::ws_get(ctx, 0, sizeof(double) * (size_t)(6 * n + nc + 8), (void **)&wk));
+    double *r = wk, *w = wk + n, *p = wk + 2 * n, *s = wk + 3 * n, *q = wk + 4 * n, *f = wk + 5 * n, *u = wk + 6 * n;   // u carries ghost entries
+    const int g1 = grid_for(ctx, n), gl = line_grid(ctx, stride);
+    const int every = info->check_every > 0 ? info->check_every : 20;
+    int total = 0;
+    for (int restart = 0; restart <= kMaxRestart + 1; ++restart) {
+        MP_TRY((launch_sell<0, false>(ctx, A, H, d_x, q, nullptr, 0, 0)));
+        k_init_residual<<<g1, kThreads, 0, ctx->stream>>>(n, d_b, q, d_invw, r, nullptr, nullptr, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, S_TMP0);
+        mp::count_launch(ctx);
+        MP_CUDA(cudaGetLastError());
+        bool done = false, zero_rhs = false;
+        MP_TRY(start_solve(ctx, info, restart == 0, &done, &zero_rhs));
+        if (zero_rhs) return zero_solution(ctx, d_x, n, info);
+        if (done || total >= info->maxit || restart > kMaxRestart) break;
+        // u = M^-1 r, gamma = r.u (allreduced by the sweep's own reduction), w = A u, delta = w.u
+        k_line_fwd<false><<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, nullptr, nullptr, nullptr, r, d_lo, d_invw, f, ctx->d_partials, ctx->d_ctl,
+                                                                 ctx->d_scalars, S_G0, S_G0, 0);
+        k_line_bwd<true><<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, f, d_mb, u, ctx->d_scalars, S_G0, S_G0, 1, 0);
+        mp::count_launch(ctx, 2);
+        MP_TRY((launch_sell<1, true>(ctx, A, H, u, w, u, S_DELTA, 0)));
+        int cur = 0, nxt = 1;
+        for (int it = 0; total < info->maxit; ++it) {
+            k_line_fwd_cgcg<<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, it == 0 ? 1 : 0, w, u, p, s, d_x, r, d_lo, d_invw, f, ctx->d_partials,
+                                                                   ctx->d_ctl, ctx->d_scalars, cur, nxt);
+            k_line_bwd<true><<<gl, kLineThreads, 0, ctx->stream>>>(st, nplanes, f, d_mb, u, ctx->d_scalars, S_G0, S_G0, 1, 0);
+            mp::count_launch(ctx, 2);
+            MP_TRY((launch_sell<3, true>(ctx, A, H, u, w, u, S_DELTA, S_G0 + nxt)));
+            int tmp = cur; cur = nxt; nxt = tmp;
+            ++total;
+            if (total % every == 0 || total == info->maxit) {
+                MP_CUDA(cudaGetLastError());
+                MP_TRY(poll(ctx));
+                if (!(ctx->h_scalars[S_RR] == ctx->h_scalars[S_RR])) { mp::set_error("mp_solve_pcg_line: NaN residual at iteration %d", total); return 4; }
+                if (!(ctx->h_scalars[S_RR] > ctx->h_scalars[S_TOL2])) break;
+            }
+        }
+    }
+    return finish_solve(ctx, info);
+}
+}  // namespace
+
 extern "C" int mp_solve_pcg_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, const double *d_lo, const double *d_invw,
                                  const double *d_mb, const double *d_b, double *d_x, mp_halo *halo, mp_solve_info *info) {
     MP_CHECK(ctx && d_lo && d_invw && d_mb && d_b && d_x && info, "mp_solve_pcg_line: null argument");
     MP_TRY(check_csr(A));
     MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_solve_pcg_line: the row count must be a positive multiple of the line stride");
     MP_CHECK(A->nrow < (int64_t)1 << 31, "mp_solve_pcg_line: row count beyond 32-bit indexing");
+    {   // several GPUs (or option pcg_variant = 1): the single-reduction recurrence, one exchange point per iteration
+        const bool sell = A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0;
+        const bool multi = ctx->nranks > 1 && halo && halo->nneigh > 0;
+        const bool comm_ok = !multi || (ctx->peer && halo->peer && halo->nown == A->nrow);
+        const int variant = ctx->pcg_variant < 0 ? (multi ? 1 : 0) : ctx->pcg_variant;
+        if (variant == 1 && sell && comm_ok && (ctx->nranks == 1 || ctx->peer))
+            return solve_pcg_line_single_reduction(ctx, A, stride, d_lo, d_invw, d_mb, d_b, d_x, halo, info);
+    }
     const int64_t n = A->nrow, nc = A->ncol, nplanes = n / stride;
     int64_t nnz = 0;
     MP_TRY(nnz_of(ctx, A, &nnz));

@@ -142,6 +142,18 @@ def test_single_reduction_pcg_matches_direct(ctx, reset_options, c8):
         assert rel(x.cpu().numpy(), xo) < 1e-9, variant
         its[variant] = res.niter
     assert its[1] <= 1.3 * its[0] + 10, its
+    # the same two recurrences with the lattice-line preconditioner (mp_solve_pcg_line: classic on one GPU, single-reduction on several)
+    stride = 15 * 15
+    itl = {}
+    for variant in (0, 1):
+        ctx.set_option("pcg_variant", variant)
+        x = ctx.zeros(dm.nvert)
+        res = A.solve("pcg_line", b, x, rtol=1e-12, maxit=20000, line_stride=stride)
+        assert res.converged, (variant, res)
+        assert rel(x.cpu().numpy(), xo) < 1e-9, variant
+        itl[variant] = res.niter
+    assert itl[1] <= 1.3 * itl[0] + 10 and itl[0] < its[0], (itl, its)
+    ctx.set_option("pcg_variant", -1)
     # zero right-hand side: x = 0 whatever the initial guess
     x = ctx.to_device(rng.standard_normal(dm.nvert))
     res = A.solve("pcg", ctx.zeros(dm.nvert), x, rtol=1e-12)
