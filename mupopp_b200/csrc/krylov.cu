@@ -1851,11 +1851,13 @@ extern "C" int mp_solve_pcg_line(mp_ctx *ctx, const mp_csr *A, int64_t stride, c
     MP_TRY(check_csr(A));
     MP_CHECK(stride > 0 && A->nrow > 0 && A->nrow % stride == 0, "mp_solve_pcg_line: the row count must be a positive multiple of the line stride");
     MP_CHECK(A->nrow < (int64_t)1 << 31, "mp_solve_pcg_line: row count beyond 32-bit indexing");
-    {   // several GPUs (or option pcg_variant = 1): the single-reduction recurrence, one exchange point per iteration
+    {   // option pcg_variant = 1: the single-reduction recurrence, one exchange point per iteration.  NOT the multi-GPU default here:
+        // measured at 200^3 it is slower on 2 GPUs (50.2 vs 47.5 ms/step: 128 N instead of 104 N bytes per iteration) and no faster on 8
+        // (21.3 vs 21.0 ms/step) -- with a third of the iterations left, the exchanges are no longer what limits the line-PCG
         const bool sell = A->d_sell_val && A->d_sell_col && A->d_sell_sliceptr && ctx->spmv_variant == 0;
         const bool multi = ctx->nranks > 1 && halo && halo->nneigh > 0;
         const bool comm_ok = !multi || (ctx->peer && halo->peer && halo->nown == A->nrow);
-        const int variant = ctx->pcg_variant < 0 ? (multi ? 1 : 0) : ctx->pcg_variant;
+        const int variant = ctx->pcg_variant == 1 ? 1 : 0;
         if (variant == 1 && sell && comm_ok && (ctx->nranks == 1 || ctx->peer))
             return solve_pcg_line_single_reduction(ctx, A, stride, d_lo, d_invw, d_mb, d_b, d_x, halo, info);
     }

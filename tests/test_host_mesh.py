@@ -74,3 +74,24 @@ def test_face_numbering_and_p3_tables_match_oracle(dim):
             t1, d1 = ref.tabulate(deg, pts)
             t2, d2 = fem.tabulate(deg, pts)
             assert np.allclose(t1, t2, rtol=0, atol=1e-15) and np.allclose(d1, d2, rtol=0, atol=1e-14)
+
+
+def test_lattice_line_stride_of_structured_meshes_and_slabs():
+    """Rows per lattice plane (the line preconditioner's stride): BoxMesh / RectangleMesh, periodic x/y dofs, z-slab partitions (owned
+    planes first), and 0 for meshes without lattice structure (they fall back to point Jacobi)."""
+    import mupopp_b200 as mp
+    from mupopp_b200 import partition
+    from mupopp_b200.mesh import Mesh, box_periodic_map
+    from mupopp_b200.transport import lattice_line_stride
+    box = ((0.0, 0.0, 0.0), (4.0, 4.0, 1.0))
+    m = mp.BoxMesh(box[0], box[1], 5, 4, 6)
+    assert lattice_line_stride(m) == 6 * 5
+    pm = box_periodic_map(m, (0, 1))
+    assert lattice_line_stride(m, pm.vert2dof) == 5 * 4 and pm.ndof == 5 * 4 * 7
+    assert lattice_line_stride(mp.RectangleMesh((0, 0), (2, 1), 7, 3)) == 8
+    for per in (False, True):
+        for rank in range(3):
+            part = partition.slab_partition(box, (5, 4, 6), rank, 3, periodic_xy=per)
+            st = lattice_line_stride(part.mesh, part.vert2dof, part.n_owned)
+            assert st == (20 if per else 30) and part.n_owned % st == 0
+    assert lattice_line_stride(Mesh(m.coords, m.cells)) == 0            # no lattice information: point Jacobi
