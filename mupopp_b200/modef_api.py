@@ -102,7 +102,7 @@ def boundary_data_from_bcs(W, bcs):
 class ModeFStepper:
     """One mode-F problem behind `solve(a == L, sol, bcs)`: owns the TransportSolverF, moves Function blocks in and out."""
 
-    def __init__(self, ctx, W, bcs, model, f_nodal, rtol=1e-12, maxit=50000, p_precond="line"):
+    def __init__(self, ctx, W, bcs, model, f_nodal, rtol=1e-12, maxit=50000, p_precond="line", lagged_velocity="cache"):
         self.ctx, self.W, self.bcs = ctx, W, list(bcs)       # references keep the ids used in cache keys alive
         per = W.periodic
         self.sig = bc_signature(bcs)
@@ -112,6 +112,14 @@ class ModeFStepper:
         self._lump = None
         self._edges = None
         self._tmp = ctx.zeros(self.s.nown)
+        # "cache": the lagged cellwise velocity u^n travels with the previous Function (Function.cell_velocity, device resident);
+        # "recover": u^n is recomputed from (p^n, c0^n) at the start of the solve -- mode F DEFINES u as that function of the state
+        # (TransportSolverF.recover_velocity), so a host-resident workflow need not ship the 3*ncell doubles of the DG0 field.
+        # The two agree bit for bit whenever the previous state came out of a mode-F solve; they differ only for a user-supplied
+        # initial velocity (ignored by "recover").
+        if lagged_velocity not in ("cache", "recover"):
+            raise ValueError("mupopp_b200_lagged_velocity must be 'cache' or 'recover'")
+        self.lagged_velocity = lagged_velocity
 
     def refresh(self, bcs, model, f_nodal):
         """Per solve: new physical parameters (dt may change), boundary VALUES if their fingerprint changed, source term."""
@@ -134,7 +142,11 @@ class ModeFStepper:
     def load_state(self, prev):
         s, d = self.s, self.W.mesh.dim
         nc = s.model.ncomp
-        if getattr(prev, "cell_velocity", None) is not None:
+        if self.lagged_velocity == "recover":
+            s.p.copy_(prev.blocks[d])
+            s.c0_new.copy_(prev.blocks[d + 1])
+            s.recover_velocity()                     # u^n = -(K/phi) (grad p^n + sigma rho(c0^n) zhat), cell by cell
+        elif getattr(prev, "cell_velocity", None) is not None:
             s.u.copy_(prev.cell_velocity)
         else:      # a user-supplied nodal velocity (the scripts start from zero): cell value = mean of the cell's vertex values
             cd = s.dm.cell_dofs.long()       # (P2 blocks of a non-periodic space: their first entries are the vertex values)

@@ -403,9 +403,11 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
             # meshes, point Jacobi elsewhere) | "default" (= "line")
             pc = str(solver_parameters.get("preconditioner", "default")).lower()
             pc = "line" if pc in ("default", "none") else pc
-            key = ("multiF", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.sigma, id(model.K) if not np.isscalar(model.K) else model.K, pc)
+            lag = str(solver_parameters.get("mupopp_b200_lagged_velocity", "cache")).lower()
+            key = ("multiF", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.sigma, id(model.K) if not np.isscalar(model.K) else model.K, pc, lag)
             if key not in _CACHE:
-                _CACHE[key] = ModeFStepper(ctx, W, bcs, model, fs, rtol=float(solver_parameters.get("relative_tolerance", 1e-12)), p_precond=pc)
+                _CACHE[key] = ModeFStepper(ctx, W, bcs, model, fs, rtol=float(solver_parameters.get("relative_tolerance", 1e-12)), p_precond=pc,
+                                           lagged_velocity=lag)
             st = _CACHE[key]
             st.refresh(bcs, model, fs)
             return st.step(d["sol_prev"], u)

@@ -204,3 +204,39 @@ def test_mode_selection_and_time_dependent_bc(ctx):
         a, L = ccs.advection_diffusion_three_component(W, mesh, s0, 0.1, f_source=fx.Constant(0.0), K=1.0)
         fx.solve(a == L, s, bcs, solver_parameters={"mupopp_b200_mode": mode})
         assert np.allclose(s.get(3)[topv], 0.3), mode
+
+
+def test_lagged_velocity_recovered_from_the_state(ctx):
+    """solver_parameters={"mupopp_b200_lagged_velocity": "recover"}: the cellwise velocity of the previous state is recomputed from (p, c0)
+    instead of travelling with the Function -- bit-identical to the cached one whenever the previous state came out of a mode-F solve, so a
+    host-resident workflow only ships the public blocks of the mixed Function (what bench.py's e2e leg does)."""
+    import mupopp_b200.fenics as fx
+    from mupopp_b200 import mupopp as api
+    mesh = fx.UnitSquareMesh(8, 8)
+    cell = mesh.ufl_cell()
+    Qc = fx.FiniteElement("Lagrange", cell, 1)
+    W = fx.FunctionSpace(mesh, fx.MixedElement([fx.VectorElement("Lagrange", cell, 2), Qc, Qc, Qc, Qc]))
+    top = lambda x: x[1] > 1.0 - fx.DOLFIN_EPS
+    bcs = [fx.DirichletBC(W.sub(0), fx.Constant((0.0, -0.5)), top), fx.DirichletBC(W.sub(2), fx.Constant(0.1), top)]
+    ccs = api.CCS(Pe=500, Da=0.1, phi=0.05, alpha=1e-3)
+    prm = {"mupopp_b200_mode": "F"}
+    s0, s1, s2 = fx.Function(W), fx.Function(W), fx.Function(W)
+    s0.blocks[4].fill_(0.1)
+    for prev, new in ((s0, s1), (s1, s2)):                          # two steps with the cached velocity
+        a, L = ccs.advection_diffusion_three_component(W, mesh, prev, 0.1, f_source=fx.Constant(1.0), K=1.0)
+        fx.solve(a == L, new, bcs, solver_parameters=prm)
+    assert float(s2.cell_velocity.abs().max()) > 0.0
+    # third step: (a) from s2 with its cached velocity, (b) from a copy of s2's PUBLIC blocks only, velocity recovered on the device
+    ra, rb, bare = fx.Function(W), fx.Function(W), fx.Function(W)
+    for dst, src in zip(bare.blocks, s2.blocks):
+        dst.copy_(src)
+    assert bare.cell_velocity is None
+    a, L = ccs.advection_diffusion_three_component(W, mesh, s2, 0.1, f_source=fx.Constant(1.0), K=1.0)
+    fx.solve(a == L, ra, bcs, solver_parameters=prm)
+    a, L = ccs.advection_diffusion_three_component(W, mesh, bare, 0.1, f_source=fx.Constant(1.0), K=1.0)
+    fx.solve(a == L, rb, bcs, solver_parameters=dict(prm, mupopp_b200_lagged_velocity="recover"))
+    for k in range(len(ra.blocks)):
+        assert np.array_equal(ra.get(k), rb.get(k)), k
+    assert np.array_equal(ra.cell_velocity.cpu().numpy(), rb.cell_velocity.cpu().numpy())
+    with pytest.raises(ValueError):
+        fx.solve(a == L, rb, bcs, solver_parameters=dict(prm, mupopp_b200_lagged_velocity="nonsense"))
