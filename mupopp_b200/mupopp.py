@@ -402,7 +402,7 @@ def _dispatch_solve(form, u, bcs, solver_parameters):
             # "preconditioner" (dolfin's solver_parameters key): "jacobi" | "chebyshev" | "line" (lattice-line block Jacobi on structured
             # meshes, point Jacobi elsewhere) | "default" (= "line")
             pc = str(solver_parameters.get("preconditioner", "default")).lower()
-            pc = "line" if pc in ("default", "none") else pc
+            pc = pc if pc in ("jacobi", "chebyshev", "line") else "line"        # DOLFIN names ("amg", "ilu", "default", ...) -> the best one here
             lag = str(solver_parameters.get("mupopp_b200_lagged_velocity", "cache")).lower()
             key = ("multiF", id(W), _bc_key(bcs), model.reaction, nc, model.SUPG, model.sigma, id(model.K) if not np.isscalar(model.K) else model.K, pc, lag)
             if key not in _CACHE:

@@ -201,9 +201,9 @@ class TransportSolverF:
         self.line_stride = 0
         if self.p_method == "pcg_line":
             self.line_stride = lattice_line_stride(mesh, vert2dof, self.nown)
-            if self.line_stride > 0:
-                self.L.line_setup(self.line_stride)
-            else:
+            if self.line_stride > 0 and not self._try(lambda: self.L.line_setup(self.line_stride)):
+                self.line_stride = 0                 # a line block that is not SPD (should not happen for div(k grad p)): point Jacobi
+            if self.line_stride == 0:
                 self.p_method = "pcg"
         # the transport row uses the same lines (non-symmetric tridiagonal blocks, refactored with the matrix every step)
         self.c0_line = self.line_stride > 0 and c0_method == "bicgstab" and c0_precond != "jacobi"
@@ -316,7 +316,7 @@ class TransportSolverF:
             fn()
             return True
         except MpError as e:
-            if "pivot" not in str(e):
+            if "pivot" not in str(e) and "positive definite" not in str(e):
                 raise
             return False
 
