@@ -133,6 +133,7 @@ struct mp_ctx {
     int spmv_c8 = 1;        // use the compressed SELL columns (9 instead of 12 bytes per nonzero) when the operator has them
     int spmv_lpr = 0;       // lanes per row of the SELL kernels: 0 = from the operator size, else 1 / 2 / 4
     int line_prefetch = 0;  // line preconditioner sweeps: L2 prefetch distance in planes (0 = off; measured: no gain once the sweeps run as one wave)
+    int minres_graph = 1;   // mp_solve_minres: replay six iterations at a time as a CUDA graph (the block recurrences are launch bound)
     int pcg_variant = -1;   // -1 auto (single-reduction CG on several GPUs, classic on one), 0 classic two-reduction PCG, 1 single-reduction
     bool timing = false;
     std::vector<cudaEvent_t> tev;   // pairs (start, stop)

@@ -159,6 +159,7 @@ int mp_ctx_set_option(mp_ctx *c, const char *name, int value) {
     MP_CHECK(c && name, "mp_ctx_set_option: null argument");
     if (!strcmp(name, "spmv_variant")) { c->spmv_variant = value; return 0; }
     if (!strcmp(name, "spmv_c8")) { c->spmv_c8 = value; return 0; }
+    if (!strcmp(name, "minres_graph")) { c->minres_graph = value ? 1 : 0; return 0; }
     if (!strcmp(name, "line_prefetch")) { MP_CHECK(value >= 0 && value <= 256, "line_prefetch must be 0..256 planes"); c->line_prefetch = value; return 0; }
     if (!strcmp(name, "pcg_variant")) { MP_CHECK(value >= -1 && value <= 1, "pcg_variant must be -1, 0 or 1"); c->pcg_variant = value; return 0; }
     if (!strcmp(name, "spmv_lpr")) { MP_CHECK(value == 0 || value == 1 || value == 2 || value == 4, "spmv_lpr must be 0, 1, 2 or 4"); c->spmv_lpr = value; return 0; }

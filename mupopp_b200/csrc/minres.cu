@@ -280,7 +280,19 @@ extern "C" int mp_solve_minres(mp_ctx *ctx, const mp_block_op *op, const mp_bloc
     static_assert(sizeof(MrState) == 16 * sizeof(double), "MrState layout");
     MrState h[2];
     const int g = grid_n(ctx, n);
-    const int every = info->check_every > 0 ? info->check_every : 25;
+    constexpr int kMrGraphIters = 6;
+    bool use_graph = ctx->minres_graph != 0;
+    const int every = info->check_every > 0 ? info->check_every : (use_graph ? 4 * kMrGraphIters : 25);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    cudaStream_t cstream = nullptr;
+    int64_t per_graph = 0;
+    auto release_graph = [&]() {
+        if (gexec) cudaGraphExecDestroy(gexec);
+        if (graph) cudaGraphDestroy(graph);
+        if (cstream) cudaStreamDestroy(cstream);
+        gexec = nullptr; graph = nullptr; cstream = nullptr;
+    };
     int total = 0;
     double bnorm = 0.0, relres = 0.0;
     bool converged = false;
@@ -311,9 +323,10 @@ extern "C" int mp_solve_minres(mp_ctx *ctx, const mp_block_op *op, const mp_bloc
         MP_CUDA(cudaMemsetAsync(v_old, 0, sizeof(double) * (size_t)n, ctx->stream));
         MP_CUDA(cudaMemsetAsync(w_old, 0, sizeof(double) * (size_t)n, ctx->stream));
         MP_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)n, ctx->stream));
-        int cur = 0;
+        int cur = 0, inner = 0;
         bool inner_done = false;
-        for (int it = 0; total < info->maxit && !inner_done; ++it) {
+        // one iteration of the recurrence on the current pointer configuration (v's rotate with period 3, z and the state set with period 2)
+        auto one_iteration = [&]() -> int {
             MrState *sc = st + cur, *sn = st + (cur ^ 1);
             k_mr_scale<<<g, kThreads, 0, ctx->stream>>>(n, 1.0, z, nullptr, z, sc, 1);                  // z <- z / gamma
             MP_TRY(block_apply(ctx, op, z, Az, xm, sc));
@@ -325,25 +338,63 @@ extern "C" int mp_solve_minres(mp_ctx *ctx, const mp_block_op *op, const mp_bloc
             k_mr_dot<<<g, kThreads, 0, ctx->stream>>>(n, z_new, v_new, ctx->d_partials, ctx->d_ctl, ctx->d_scalars, sc);   // z_new.v_new
             k_mr_update<<<g, kThreads, 0, ctx->stream>>>(n, z, w_old, w, w_new, d_x, sc, sn, ctx->d_scalars);
             mp::count_launch(ctx, 2);
-            // rotate
             double *tp = v_old; v_old = v; v = v_new; v_new = tp;
             tp = w_old; w_old = w; w = w_new; w_new = tp;
             tp = z; z = z_new; z_new = tp;
             cur ^= 1;
-            ++total;
-            if (total % every == 0 || total == info->maxit) {
+            return 0;
+        };
+        while (total < info->maxit && !inner_done) {
+            // An iteration is ~100 launches of kernels that run a few microseconds each on these block systems (3 x 10^4 .. 10^6 rows): the
+            // recurrence is launch bound.  Six iterations bring every rotating pointer back to where it started, so they are captured ONCE
+            // into a CUDA graph (on a side stream: the context's stream may be the legacy default stream, which cannot be captured) and
+            // replayed; every kernel reads its scalars from device memory and is a no-op once converged, so the replay needs no host input.
+            if (use_graph && !gexec && info->maxit - total >= kMrGraphIters) {
+                cudaStream_t orig = ctx->stream;
+                const int64_t l0 = ctx->launches;
+                int rc = 0;
+                if (!cstream && cudaStreamCreateWithFlags(&cstream, cudaStreamNonBlocking) != cudaSuccess) rc = 1;
+                if (!rc && cudaStreamBeginCapture(cstream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) rc = 1;
+                if (!rc) {
+                    ctx->stream = cstream;
+                    for (int k = 0; k < kMrGraphIters && !rc; ++k) rc = one_iteration();
+                    ctx->stream = orig;
+                    if (cudaStreamEndCapture(cstream, &graph) != cudaSuccess || !graph) rc = 1;
+                }
+                per_graph = ctx->launches - l0;
+                ctx->launches = l0;                                      // captured, not run
+                if (!rc && cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) rc = 1;
+                if (rc) {                                                // no graph: plain launches (the pointers are back in place either way)
+                    cudaGetLastError();
+                    use_graph = false;
+                    gexec = nullptr;
+                }
+            }
+            if (use_graph && gexec && info->maxit - total >= kMrGraphIters) {
+                MP_CUDA(cudaGraphLaunch(gexec, ctx->stream));
+                ctx->launches += per_graph;
+                total += kMrGraphIters;
+                inner += kMrGraphIters;
+            } else {
+                MP_TRY(one_iteration());
+                ++total;
+                ++inner;
+            }
+            if (total % every == 0 || total >= info->maxit) {
                 MP_CUDA(cudaGetLastError());
                 MP_CUDA(cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
                 MP_CUDA(cudaStreamSynchronize(ctx->stream));
-                const MrState &s = h[cur];
-                if (!(s.rr == s.rr)) { mp::set_error("mp_solve_minres: NaN residual at iteration %d", total); return 4; }
-                if (!(s.rr > s.tol2)) {
+                const MrState &sv = h[cur];
+                if (!(sv.rr == sv.rr)) { release_graph(); mp::set_error("mp_solve_minres: NaN residual at iteration %d", total); return 4; }
+                if (!(sv.rr > sv.tol2)) {
                     inner_done = true;
-                    total = total - (it + 1) + (int)s.iter;       // the recurrence stopped counting when it converged
+                    total = total - inner + (int)sv.iter;        // the recurrence stopped counting when it converged
                 }
             }
         }
+        if (inner % kMrGraphIters != 0) release_graph();         // the pointers did not end where the graph expects them: capture again
     }
+    release_graph();
     if (!converged) {                                                // report the TRUE preconditioned residual of the final iterate
         MP_TRY(block_apply(ctx, op, d_x, Az, xm, nullptr));
         MP_CUDA(cudaMemcpyAsync(v, d_b, sizeof(double) * (size_t)n, cudaMemcpyDeviceToDevice, ctx->stream));
