@@ -21,7 +21,7 @@ ap = argparse.Namespace(n=n, sides="periodic", rtol=1e-12, maxit=50000, c0_metho
 s = bench.build_problem(ctx, ap, 0, 1)
 for _ in range(3):
     s.step()                                  # a developed state: non-trivial velocity and concentrations
-for fused in ([True] if only == "fused" else [False, True]):
+for fused in ([True] if only == "fused" else ([False] if only == "pipeline" else [False, True])):
     s.fused_rows = fused
     for _ in range(2):
         s.assemble_c0_row()
