@@ -125,6 +125,10 @@ int mp_elem_p1_stiffness(mp_ctx *ctx, const mp_mesh *mesh, const double *d_K, do
 /* c1/c2 rows: elem_b1 = int w (c1n - dt R2/(1-phi)), elem_b2 = int w (c2n + dt R3/(1-phi)) (NULL when ncomp==2) */
 int mp_elem_p1_reaction_rhs(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_c0n,
                             const double *d_c1n, const double *d_c2n, double *d_elem_b1, double *d_elem_b2);
+/* the reaction load alone: elem_T[c][i] = scale * int w_i R(c0n, c1n) (R = c0 c1 or c0 c1^2, prm->reaction).  The c1 and c2 rows share it up to
+ * the factors -dt frac[1] Da/(1-phi) and +dt frac[2] Da/(1-phi), so one mass solve serves both increments. */
+int mp_elem_p1_reaction_load(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_c0n,
+                             const double *d_c1n, double scale, double *d_elem_T);
 /* c0 row (Crank-Nicolson + SUPG, mupopp.py:823-848 / :934-958 / :1231-1258) with the lagged DG0 velocity d_ucell[c][dim]:
  * elem_mat (may be NULL to skip) and elem_vec; the new c1/c2 enter the rhs through the SUPG residual. */
 int mp_elem_p1_transport(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_ucell,

@@ -137,6 +137,7 @@ SIGNATURES = {
     "mp_assemble_p1_transport_rows": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP] + [_VP] * 7 + [_VP, _VP]
                                       + [_VP, _VP, _VP, _VP, C.c_int64, _VP, _VP, _VP]),
     "mp_line_factor": (C.c_int, [_VP, C.c_int64, C.c_int64, C.c_int, _VP, _VP, _VP]),
+    "mp_elem_p1_reaction_load": (C.c_int, [_VP, C.POINTER(MpMesh), C.POINTER(MpTransportParams), _VP, _VP, C.c_double, _VP]),
     "mp_line_setup": (C.c_int, [_VP, C.POINTER(MpCsr), C.c_int64, C.c_int, _VP, _VP, _VP]),
     "mp_solve_bicgstab_line": (C.c_int, [_VP, C.POINTER(MpCsr), C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP, C.POINTER(MpSolveInfo)]),
     "mp_line_apply": (C.c_int, [_VP, C.c_int64, C.c_int64, _VP, _VP, _VP, _VP, _VP, _VP]),

@@ -311,6 +311,26 @@ __global__ void __launch_bounds__(kThreads) k_p1_reaction_rhs(mp_mesh m, mp_tran
     }
 }
 
+// the reaction load alone: elem_T[i] = int w_i R(c0, c1)  (R = c0 c1 or c0 c1^2).  The c1 and c2 rows are M c1' = M c1 - k2 T and
+// M c2' = M c2 + k3 T, so ONE mass solve for d = -k2 M^-1 T gives both increments (TransportSolverF._solve_reaction_rows_shared);
+// assembling T directly avoids the cancellation of (M c1 - k2 T) - M c1.
+template <int D>
+__global__ void __launch_bounds__(kThreads) k_p1_reaction_load(mp_mesh m, mp_transport_params P, const double *__restrict__ c0n,
+                                                               const double *__restrict__ c1n, double scale, double *__restrict__ eT) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= m.ncell) return;
+    Geom<D> G;
+    load_geom<D>(m, c, G);
+    double a0[D + 1], a1[D + 1], Ti[D + 1], mean;
+    gather<D>(c0n, G, a0);
+    gather<D>(c1n, G, a1);
+    reaction_ints<D>(P.reaction, a0, a1, Ti, mean);
+    double b[D + 1];
+#pragma unroll
+    for (int i = 0; i <= D; ++i) b[i] = scale * G.vol * Ti[i];
+    store_vec<D>(m, eT, c, b);
+}
+
 // c0 row, Crank-Nicolson + SUPG with the lagged velocity (mupopp.py:823-848, :934-958, :1231-1258):
 //   eta (c0-c0n) + dt [eta u.grad(cm) + grad(eta).grad(cm)/Pe] + dt R1/phi eta - beta dt f eta + tau (u.grad eta) r
 //   r = c0-c0n + dt (u.grad(cm) + R1/phi) - beta dt f + (c1-c1n + dt R2/(1-phi)) [+ (c2-c2n - dt R3/(1-phi))]
@@ -1351,6 +1371,14 @@ extern "C" int mp_elem_p1_reaction_rhs(mp_ctx *ctx, const mp_mesh *mesh, const m
     MP_CHECK(prm && d_c0n && d_c1n && d_elem_b1, "mp_elem_p1_reaction_rhs: null argument");
     MP_CHECK(prm->ncomp == 2 || (d_c2n && d_elem_b2), "mp_elem_p1_reaction_rhs: ncomp==3 needs c2n and elem_b2");
     DISPATCH_DIM(mesh, k_p1_reaction_rhs, *prm, d_c0n, d_c1n, d_c2n, d_elem_b1, d_elem_b2);
+    return 0;
+}
+
+extern "C" int mp_elem_p1_reaction_load(mp_ctx *ctx, const mp_mesh *mesh, const mp_transport_params *prm, const double *d_c0n,
+                                        const double *d_c1n, double scale, double *d_elem_T) {
+    MP_TRY(check_mesh(ctx, mesh));
+    MP_CHECK(prm && d_c0n && d_c1n && d_elem_T, "mp_elem_p1_reaction_load: null argument");
+    DISPATCH_DIM(mesh, k_p1_reaction_load, *prm, d_c0n, d_c1n, scale, d_elem_T);
     return 0;
 }
 

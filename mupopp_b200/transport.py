@@ -150,7 +150,7 @@ class TransportSolverF:
 
     def __init__(self, ctx: Context, mesh, model: TransportModel, bdata: BoundaryDataF, f_source=None,
                  rtol=1e-12, maxit=20000, check_every=0, halo=None, n_owned=None, c0_method="bicgstab", gmres_restart=30,
-                 vert2dof=None, row_ordered=True, p_precond="line", cheb_degree=3, p_guess="previous", c0_precond="auto", fused_rows=False):
+                 vert2dof=None, row_ordered=True, p_precond="line", cheb_degree=3, p_guess="previous", c0_precond="auto", fused_rows=False, shared_reaction_solve=True):
         """`vert2dof`: optional P1 dof of every vertex (periodic space); all fields, K, f_source and `bdata` are then in dof numbering."""
         self.ctx, self.model, self.rtol, self.maxit, self.check_every = ctx, model, rtol, maxit, check_every
         self.c0_method, self.gmres_restart = c0_method, gmres_restart
@@ -159,6 +159,7 @@ class TransportSolverF:
         self.p_method = {"chebyshev": "pcg_chebyshev", "line": "pcg_line"}.get(p_precond, "pcg")
         self.cheb_degree = cheb_degree
         self.fused_rows = bool(fused_rows)
+        self.shared_reaction_solve = bool(shared_reaction_solve)
         self.p_guess = p_guess          # "extrapolate" (2 p^n - p^(n-1)) or "previous" (p^n) as the pressure PCG's initial iterate
         self._p_hist = 0                # pressure solutions of the current time series held in (p, p_old)
         self.halo = halo
@@ -270,6 +271,25 @@ class TransportSolverF:
         if three:
             self.plan.scatter_vector(self.evec2, self.rhs2)
 
+    def _solve_reaction_rows_shared(self, kw):
+        """The c1 and c2 rows (mupopp.py:936-937, 1234-1235) have the SAME load up to a factor:
+             M c1' = M c1 - k2 T ,  M c2' = M c2 + k3 T ,   T_i = int w_i R(c0, c1),  k2/k3 = frac[1]/frac[2]
+        so one mass solve for the common increment d = c1' - c1 = -k2 M^-1 T gives both: c1' = c1 + d, c2' = c2 - (frac[2]/frac[1]) d.
+        Algebraically identical to the two solves of the reference's monolithic system; the tolerance applies to the increment, which
+        is stricter for the fields themselves."""
+        ctx, lib, m, prm = self.ctx, self.ctx.lib, self.dm.c, self.prm
+        k2 = prm.dt * prm.frac[1] * prm.Da / (1.0 - prm.phi)
+        check(lib.mp_elem_p1_reaction_load(ctx.h, C.byref(m), C.byref(prm), ptr(self.c0), ptr(self.c1), -k2, ptr(self.evec)), "mp_elem_p1_reaction_load")
+        self.plan.scatter_vector(self.evec, self.rhs)                 # -k2 T, assembled directly (no cancellation against M c1)
+        d = self.c2_new
+        d.zero_()
+        r1 = self.M.solve("pcg", self.rhs, d, **kw)
+        self._exchange(d)
+        self.c1_new.copy_(self.c1).add_(d)
+        d.mul_(-float(self.model.fracs[2]) / float(self.model.fracs[1])).add_(self.c2)      # d is c2_new
+        from .device import SolveResult
+        return r1, SolveResult(0, r1.converged, r1.relres)
+
     def assemble_c0_row(self):
         """A, rhs <- Crank-Nicolson + SUPG row with the lagged velocity u^n and the NEW c1 (, c2); Dirichlet rows eliminated.
         `fused_rows=True` uses the fused row-wise kernel (mp_assemble_p1_transport_rows: CSR + SELL values, rhs, Dirichlet, Jacobi diagonal
@@ -360,15 +380,18 @@ class TransportSolverF:
         self._mark(ev)
         kw = dict(rtol=self.rtol, maxit=self.maxit, halo=self.halo, check_every=self.check_every, refresh_jacobi=False)
         # 1. c1 (, c2): consistent-mass solves with the reaction load
-        self.assemble_reaction_rows()
-        self.c1_new.copy_(self.c1)
-        r1 = self.M.solve("pcg", self.rhs, self.c1_new, **kw)
-        self._exchange(self.c1_new)
-        r2 = None
-        if three:
-            self.c2_new.copy_(self.c2)
-            r2 = self.M.solve("pcg", self.rhs2, self.c2_new, **kw)
-            self._exchange(self.c2_new)
+        if three and self.shared_reaction_solve and self.model.fracs[1] != 0.0:
+            r1, r2 = self._solve_reaction_rows_shared(kw)
+        else:
+            self.assemble_reaction_rows()
+            self.c1_new.copy_(self.c1)
+            r1 = self.M.solve("pcg", self.rhs, self.c1_new, **kw)
+            self._exchange(self.c1_new)
+            r2 = None
+            if three:
+                self.c2_new.copy_(self.c2)
+                r2 = self.M.solve("pcg", self.rhs2, self.c2_new, **kw)
+                self._exchange(self.c2_new)
         # 2. c0: CN + SUPG with the lagged velocity u^n
         self._mark(ev)
         self.assemble_c0_row()

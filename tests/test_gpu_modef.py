@@ -438,3 +438,29 @@ def test_fused_rowwise_c0_assembly_equals_element_pipeline(ctx, dim, periodic):
     assert rel(b["invw"], a["invw"]) < 1e-11 and rel(b["mb"], a["mb"]) < 1e-11
     assert (a["vals"] != 0).sum() == (b["vals"] != 0).sum()                      # the same entries eliminated by the Dirichlet rows
     assert rel(b["c0"], a["c0"]) < 1e-10 and rel(b["p"], a["p"]) < 1e-10
+
+
+def test_shared_reaction_solve_equals_two_mass_solves(ctx):
+    """The c1 and c2 rows share their load up to a factor (mupopp.py:936-937, 1234-1235), so the default step does ONE mass solve for the common
+    increment; the fields equal those of the two separate solves to solver tolerance, natural and periodic walls."""
+    import mupopp_b200 as mp
+    from mupopp_b200.mesh import box_periodic_map
+    from mupopp_b200.transport import TransportModel, TransportSolverF, make_boundary_data
+    pm = mp.BoxMesh((0, 0, 0), (4, 4, 1), 7, 6, 9)
+    top = lambda x: x[2] > 1.0 - 1e-12
+    model = TransportModel.ccs_three_component(Pe=500.0, Da=0.1, phi=0.05, alpha=1e-8, dt=0.1, K=1.0, zh=(0.0, 0.0, 1.0))
+    for periodic in (False, True):
+        pmap = box_periodic_map(pm, (0, 1)) if periodic else None
+        bd = make_boundary_data(pm, top, lambda x: np.array([0.0, 0.0, -0.5]), top, 0.1, periodic=pmap)
+        out = {}
+        for shared in (False, True):
+            s = TransportSolverF(ctx, pm, model, bd, rtol=1e-13, vert2dof=None if pmap is None else pmap.vert2dof, shared_reaction_solve=shared)
+            s.set_state(c1=0.1 * np.ones(s.nloc))
+            for _ in range(4):
+                res = s.step()
+            assert all(r is None or r.converged or r.relres < 1e-12 for r in res.values())
+            assert (res["c2"].niter == 0) == shared
+            out[shared] = {k: getattr(s, k).cpu().numpy().copy() for k in ("c0", "c1", "c2", "p")}
+        assert np.abs(out[True]["c2"]).max() > 1e-6                      # the precipitate has formed: not a trivial comparison
+        for k in ("c0", "c1", "c2", "p"):
+            assert rel(out[True][k], out[False][k]) < 1e-10, (periodic, k)
