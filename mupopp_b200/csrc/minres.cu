@@ -283,16 +283,23 @@ extern "C" int mp_solve_minres(mp_ctx *ctx, const mp_block_op *op, const mp_bloc
     constexpr int kMrGraphIters = 6;
     bool use_graph = ctx->minres_graph != 0;
     const int every = info->check_every > 0 ? info->check_every : (use_graph ? 4 * kMrGraphIters : 25);
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    cudaStream_t cstream = nullptr;
+    struct GraphHolder {                 // released on every exit path of the solve (the MP_TRY / MP_CUDA macros return early)
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaStream_t stream = nullptr;
+        void release() {
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+            if (stream) cudaStreamDestroy(stream);
+            exec = nullptr; graph = nullptr; stream = nullptr;
+        }
+        ~GraphHolder() { release(); }
+    } gh;
+    cudaGraph_t &graph = gh.graph;
+    cudaGraphExec_t &gexec = gh.exec;
+    cudaStream_t &cstream = gh.stream;
     int64_t per_graph = 0;
-    auto release_graph = [&]() {
-        if (gexec) cudaGraphExecDestroy(gexec);
-        if (graph) cudaGraphDestroy(graph);
-        if (cstream) cudaStreamDestroy(cstream);
-        gexec = nullptr; graph = nullptr; cstream = nullptr;
-    };
+    auto release_graph = [&]() { gh.release(); };
     int total = 0;
     double bnorm = 0.0, relres = 0.0;
     bool converged = false;
@@ -323,7 +330,7 @@ extern "C" int mp_solve_minres(mp_ctx *ctx, const mp_block_op *op, const mp_bloc
         MP_CUDA(cudaMemsetAsync(v_old, 0, sizeof(double) * (size_t)n, ctx->stream));
         MP_CUDA(cudaMemsetAsync(w_old, 0, sizeof(double) * (size_t)n, ctx->stream));
         MP_CUDA(cudaMemsetAsync(w, 0, sizeof(double) * (size_t)n, ctx->stream));
-        int cur = 0, inner = 0;
+        int cur = 0, inner = 0, last_poll = total;
         bool inner_done = false;
         // one iteration of the recurrence on the current pointer configuration (v's rotate with period 3, z and the state set with period 2)
         auto one_iteration = [&]() -> int {
@@ -380,7 +387,8 @@ extern "C" int mp_solve_minres(mp_ctx *ctx, const mp_block_op *op, const mp_bloc
                 ++total;
                 ++inner;
             }
-            if (total % every == 0 || total >= info->maxit) {
+            if (total - last_poll >= every || total >= info->maxit) {
+                last_poll = total;
                 MP_CUDA(cudaGetLastError());
                 MP_CUDA(cudaMemcpyAsync(h, st, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
                 MP_CUDA(cudaStreamSynchronize(ctx->stream));
