@@ -279,19 +279,21 @@ def periodic_map_from_subdomain(mesh, pbc):
     ext = float(np.max(X.max(0) - X.min(0)))
     lo = X.min(0)
     scale = 1.0 / (1e-7 * ext)
-    key_of = lambda p: tuple(np.round((np.asarray(p) - lo) * scale).astype(np.int64))
-    is_master = {int(v): bool(pbc.inside(X[v], True)) for v in bverts}
-    where = {key_of(X[v]): int(v) for v in bverts if is_master[int(v)]}
+    keys_of = lambda P: list(map(tuple, np.round((np.asarray(P) - lo) * scale).astype(np.int64).tolist()))     # vectorised: one NumPy call
+    bverts = [int(v) for v in bverts]
+    Xb = X[bverts]
+    is_master = [bool(pbc.inside(x, True)) for x in Xb]                     # the user's Python callbacks are the unavoidable per-point cost
+    kb = keys_of(Xb)
+    where = {k: v for k, v, im in zip(kb, bverts, is_master) if im}
     master = np.arange(X.shape[0])
-    y = np.zeros(d)
+    slaves = [i for i, im in enumerate(is_master) if not im]
+    Y = Xb[slaves].copy()
+    for row, i in enumerate(slaves):
+        pbc.map(Xb[i], Y[row])
     axes = set()
-    for v in bverts:
-        v = int(v)
-        if is_master[v]:
-            continue
-        y[:] = X[v]
-        pbc.map(X[v], y)
-        m = where.get(key_of(y))
+    for k, i in zip(keys_of(Y) if slaves else [], slaves):
+        v = bverts[i]
+        m = where.get(k)
         if m is not None and m != v:
             master[v] = m
             axes.update(int(a) for a in np.nonzero(np.abs(X[v] - X[m]) > 1e-9 * ext)[0])
@@ -675,8 +677,10 @@ class DirichletBC:
         vin = np.zeros(mesh.num_vertices(), dtype=bool)
         vin[bverts] = [self._mark(vx[i]) for i in bverts]
         inside = vin[fv].all(1)
-        for f in np.nonzero(inside)[0]:
-            inside[f] = self._mark(vx[fv[f]].mean(0))
+        cand = np.nonzero(inside)[0]
+        mid = vx[fv[cand]].mean(1)                    # facet midpoints, one NumPy call
+        for f, xm in zip(cand, mid):
+            inside[f] = self._mark(xm)
         return inside
 
     def dofs_and_values(self):
@@ -695,8 +699,10 @@ class DirichletBC:
             vin = np.zeros(mesh.num_vertices(), dtype=bool)
             vin[bverts] = [self._mark(vx[i]) for i in bverts]
             inside = vin[fv].all(1)
-            for f in np.nonzero(inside)[0]:
-                inside[f] = self._mark(vx[fv[f]].mean(0))
+            cand = np.nonzero(inside)[0]
+            mid = vx[fv[cand]].mean(1)                # facet midpoints, one NumPy call
+            for f, xm in zip(cand, mid):
+                inside[f] = self._mark(xm)
             marked = np.nonzero(inside)[0]
         degree = self.space.blocks[self.block_ids[0]][0]
         ncomp = len(self.block_ids)
