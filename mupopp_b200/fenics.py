@@ -255,6 +255,16 @@ class Box:
         self.p0, self.p1 = p0, p1
 
 
+class Sphere:
+    """mshr.Sphere(center, radius) stand-in: without CGAL the bounding cube is meshed (run/sphere_archer/sphere.py:91-92)."""
+
+    def __init__(self, center, radius):
+        c = [float(center[i]) for i in range(3)]
+        r = float(radius)
+        self.center, self.radius = c, r
+        self.p0, self.p1 = [ci - r for ci in c], [ci + r for ci in c]
+
+
 def generate_mesh(domain, resolution):
     """mshr.generate_mesh stand-in: a structured mesh with cell size ~ (domain diagonal)/resolution (CGAL is not available)."""
     p0, p1 = domain.p0, domain.p1
