@@ -168,3 +168,32 @@ def test_stokes_poiseuille_known_answer(dim):
         assert np.abs(st.u[a]).max() < 1e-10
     # grad(u):grad(v) + div(v) p form: -lap(u) - grad(p) = 0 with u_x = y(1-y) gives dp/dx = +2, p = 0 at the natural outflow x = 2
     assert np.abs(st.p - 2.0 * (m.coords[:, 0] - 2.0)).max() < 1e-9
+
+
+def test_c1_and_c2_rows_share_one_increment():
+    """The identity behind TransportSolverF's single mass solve: in the three-component forms (mupopp.py:936-937, 1234-1235) the c1 and c2
+    rows are M c1' = M c1 - k2 T and M c2' = M c2 + k3 T with the SAME reaction load T, so c2' - c2 = -(frac[2]/frac[1]) (c1' - c1).
+    Checked on the oracle's own (LU-solved) step, natural and periodic walls."""
+    import scipy.sparse.linalg as spla
+    from oracle import fem, forms, modef
+    box = ((0.0, 0.0, 0.0), (4.0, 4.0, 1.0))
+    m = fem.box_mesh(box[0], box[1], 5, 4, 6)
+    asm = forms.Assembler(m)
+    prm = forms.ccs_three_component_params(Pe=500.0, Da=0.1, phi=0.05, alpha=1e-8, dt=0.1, K=1.0, zhat=(0.0, 0.0, 1.0))
+    rng = np.random.default_rng(2)
+    for periodic in (False, True):
+        P = None
+        nd = m.nv
+        if periodic:
+            P, dof = modef.periodic_prolongation(m, (0, 1), box[0], box[1])
+            nd = P.shape[1]
+        st = modef.StateF(u=np.zeros((m.nc, 3)), p=np.zeros(nd), c0=0.05 + 0.03 * rng.random(nd), c1=0.1 + 0.02 * rng.random(nd), c2=0.01 * rng.random(nd))
+        S = modef.StepSystems(asm, prm, st, np.zeros(nd), None, P)
+        M1, b1 = S.c1()
+        M2, b2 = S.c2()
+        lu = spla.splu(M1.tocsc())
+        d1 = lu.solve(b1) - st.c1
+        d2 = spla.splu(M2.tocsc()).solve(b2) - st.c2
+        ratio = prm.fracs[2] / prm.fracs[1]
+        assert np.linalg.norm(d1) > 1e-8
+        assert np.linalg.norm(d2 + ratio * d1) <= 1e-12 * np.linalg.norm(d2)
