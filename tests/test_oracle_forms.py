@@ -196,4 +196,4 @@ def test_c1_and_c2_rows_share_one_increment():
         d2 = spla.splu(M2.tocsc()).solve(b2) - st.c2
         ratio = prm.fracs[2] / prm.fracs[1]
         assert np.linalg.norm(d1) > 1e-8
-        assert np.linalg.norm(d2 + ratio * d1) <= 1e-12 * np.linalg.norm(d2)
+        assert np.linalg.norm(d2 + ratio * d1) <= 1e-10 * np.linalg.norm(d2)          # (the increments are 1e-4 of the fields: rounding of c + d)
